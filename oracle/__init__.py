@@ -15,6 +15,7 @@ from .flat_oracle import (  # noqa: F401
     c_max_threads,
     np_search_f64,
     np_search_blas,
+    torch_search_blas,
     np_synth_rows,
     np_read_index,
     np_write_index,

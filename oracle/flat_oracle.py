@@ -201,6 +201,44 @@ def np_search_blas(xb, xq, k, metric=METRIC_L2, bs_q=4096, bs_b=1024 * 16):
     return D, I
 
 
+def torch_search_blas(xb, xq, k, metric=METRIC_L2, bs_q=4096, bs_b=16384, nthreads=0):
+    """Same restatement as np_search_blas with the sgemm done by torch's CPU BLAS (MKL, the library
+    faiss-cpu wheels link) and selection by torch.topk; the fastest CPU form available here, used as
+    the all-cores baseline in bench.py.  xb / xq: numpy fp32."""
+    import torch
+
+    if nthreads > 0:
+        torch.set_num_threads(nthreads)
+    xb_t = torch.from_numpy(_f32(xb))
+    xq_t = torch.from_numpy(_f32(xq))
+    nb, nq = xb_t.shape[0], xq_t.shape[0]
+    l2 = metric == METRIC_L2
+    xn = (xb_t * xb_t).sum(1) if l2 else None
+    D = np.empty((nq, k), np.float32)
+    I = np.empty((nq, k), np.int64)
+    for i0 in range(0, nq, bs_q):
+        q = xq_t[i0:i0 + bs_q]
+        qn = (q * q).sum(1) if l2 else None
+        bk = torch.empty((q.shape[0], 0), dtype=torch.float32)
+        bi = torch.empty((q.shape[0], 0), dtype=torch.int64)
+        for j0 in range(0, nb, bs_b):
+            xs = xb_t[j0:j0 + bs_b]
+            ip = q @ xs.T
+            if l2:
+                keys = ip.mul_(-2.0).add_(qn[:, None]).add_(xn[None, j0:j0 + bs_b]).clamp_(min=0)
+            else:
+                keys = ip.neg_()
+            kk = min(k, keys.shape[1])
+            v, idx = torch.topk(keys, kk, dim=1, largest=False)
+            bk = torch.cat([bk, v], 1)
+            bi = torch.cat([bi, idx + j0], 1)
+            if bk.shape[1] > 16 * k:
+                v, o = torch.topk(bk, min(k, bk.shape[1]), dim=1, largest=False)
+                bk, bi = v, torch.gather(bi, 1, o)
+        D[i0:i0 + bs_q], I[i0:i0 + bs_q] = _finish(bk.numpy(), bi.numpy(), k, metric)
+    return D, I
+
+
 _M1 = np.uint64(0xBF58476D1CE4E5B9)
 _M2 = np.uint64(0x94D049BB133111EB)
 

@@ -1,0 +1,227 @@
+// common.cuh -- shared device/host helpers for the flat-search kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <float.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/b200flat.h"
+
+namespace b2f {
+
+constexpr int kWarp = 32;
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74
+
+// Selection keys are "smaller is better": L2 -> squared distance, IP -> -inner product.
+// Candidates are totally ordered by (key, id); id -1 (empty slot) compares as the largest id,
+// so an empty slot (FLT_MAX, -1) loses against everything that faiss would admit.
+struct Cand {
+    float key;
+    int32_t id;
+};
+
+__host__ __device__ __forceinline__ bool cand_less(float ka, int32_t ia, float kb, int32_t ib) {
+    return ka < kb || (ka == kb && (uint32_t)ia < (uint32_t)ib);
+}
+
+// ---- warp-level helpers ------------------------------------------------------------------------
+
+// Sum V values across the warp with V-1 + (5 - log2 V) * V shuffles instead of 5 * V: after the
+// call lane l holds the warp-wide total of v[l & (V-1)] in v[0].  V must be a power of two <= 32.
+template <int V>
+__device__ __forceinline__ void warp_multi_reduce(float (&v)[V], int lane) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        if (s >= V) {
+#pragma unroll
+            for (int i = 0; i < V; i++) v[i] += __shfl_xor_sync(kFull, v[i], s);
+        } else {
+            const bool upper = (lane & s) != 0;
+#pragma unroll
+            for (int i = 0; i < s; i++) {
+                float send = upper ? v[i] : v[i + s];
+                float keep = upper ? v[i + s] : v[i];
+                v[i] = keep + __shfl_xor_sync(kFull, send, s);
+            }
+        }
+    }
+}
+
+// Insert (key,id) into an ascending (key,id)-sorted list of length k held in shared/global memory,
+// dropping the last element.  Called by all 32 lanes with the same arguments.  The caller has
+// already established (key,id) < list[k-1].
+__device__ __forceinline__ void warp_sorted_insert(float* lk, int32_t* li, int k, float key, int32_t id,
+                                                   int lane) {
+    for (int base = ((k - 1) / kWarp) * kWarp; base >= 0; base -= kWarp) {
+        const int j = base + lane;
+        float nk = 0.f;
+        int32_t ni = 0;
+        bool wr = false;
+        if (j < k) {
+            const float ck = lk[j];
+            const int32_t ci = li[j];
+            if (cand_less(key, id, ck, ci)) {  // new element lands at or before j
+                wr = true;
+                if (j > 0 && cand_less(key, id, lk[j - 1], li[j - 1])) {
+                    nk = lk[j - 1];
+                    ni = li[j - 1];
+                } else {
+                    nk = key;
+                    ni = id;
+                }
+            }
+        }
+        __syncwarp();
+        if (wr) {
+            lk[j] = nk;
+            li[j] = ni;
+        }
+        __syncwarp();
+    }
+}
+
+// Merge up to 32 ascending lists (list l starts at keys + l*stride, length len) into the k best,
+// written by lane 0 to (ok, oi).  One warp.  Lists may contain (FLT_MAX,-1) padding.
+__device__ __forceinline__ void warp_merge_lists(const float* keys, const int32_t* ids, int nlists, int len,
+                                                 int64_t stride, int k, float* ok, int32_t* oi, int lane) {
+    int pos = 0;
+    float hk = FLT_MAX;
+    int32_t hi = -1;
+    const bool have = lane < nlists;
+    if (have && len > 0) {
+        hk = keys[(int64_t)lane * stride];
+        hi = ids[(int64_t)lane * stride];
+    }
+    for (int o = 0; o < k; o++) {
+        float bk = hk;
+        int32_t bi = hi;
+        int bl = lane;
+#pragma unroll
+        for (int s = 16; s >= 1; s >>= 1) {
+            float tk = __shfl_xor_sync(kFull, bk, s);
+            int32_t ti = __shfl_xor_sync(kFull, bi, s);
+            int tl = __shfl_xor_sync(kFull, bl, s);
+            if (cand_less(tk, ti, bk, bi) || (tk == bk && ti == bi && tl < bl)) {
+                bk = tk;
+                bi = ti;
+                bl = tl;
+            }
+        }
+        if (lane == 0) {
+            ok[o] = bk;
+            oi[o] = bi;
+        }
+        if (lane == bl && have) {
+            pos++;
+            if (pos < len) {
+                hk = keys[(int64_t)lane * stride + pos];
+                hi = ids[(int64_t)lane * stride + pos];
+            } else {
+                hk = FLT_MAX;
+                hi = -1;
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+// ---- host-side error plumbing ------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+
+#define B2F_CUDA(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            b2f::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return B2F_ECUDA;                                                                       \
+        }                                                                                           \
+    } while (0)
+
+#define B2F_TRY(expr)            \
+    do {                         \
+        int _rc = (expr);        \
+        if (_rc != B2F_OK) return _rc; \
+    } while (0)
+
+// ---- kernel launchers (one per .cu file) -------------------------------------------------------
+
+// K1: fp32 exact-difference streaming scan. q: [nq, d] device fp32, nq <= 8 per call.
+// Produces sorted per-CTA partial lists: pk/pi [nq][nparts][k]; returns nparts via *nparts_out
+// (fixed by the launch geometry; caller sizes the buffers with scan_max_parts()).
+int scan_max_parts();
+// qsel (optional, device): query slot i reads row qsel[i] of q (certification fallback).
+int launch_scan_f32(const float* rows, int64_t n, int d, int metric, const float* q, const int32_t* qsel, int nq,
+                    int k, float* pk, int32_t* pi, int* nparts_out, cudaStream_t st);
+// same scan over bf16-stored rows (B2F_STORE_BF16), pitch in elements
+int launch_scan_bf16(const __nv_bfloat16* rows, int64_t pitch, int64_t n, int d, int metric, const float* q,
+                     const int32_t* qsel, int nq, int k, float* pk, int32_t* pi, int* nparts_out, cudaStream_t st);
+
+// K3: merge nparts sorted lists per query into the best kout: pk/pi [nq][nparts][klist] -> ok/oi [nq][kout]
+int launch_merge_parts(const float* pk, const int32_t* pi, int nq, int nparts, int klist, int kout, float* ok,
+                       int32_t* oi, cudaStream_t st);
+// final formatting: keys -> faiss distances, int32 local ids -> int64 labels (+offset), padding.
+// qsel (optional) scatters row r of the input to output row qsel[r].
+int launch_finalize(const float* keys, const int32_t* ids, int nq, int kin, int k, int metric, int64_t id_offset,
+                    const int32_t* qsel, float* D, int64_t* I, cudaStream_t st);
+// multi-GPU merge of [nparts][nq][k] faiss-formatted lists
+int launch_merge_faiss(int metric, int64_t nq, int64_t k, int nparts, const float* Dp, const int64_t* Ip, float* D,
+                       int64_t* I, cudaStream_t st);
+
+// K5: ingest. src fp32 [n,d] (device) -> rows fp32 (optional), bf16 scan copy (pitch dpad), norms.
+// stats (device, 2 floats): running max |bf16(x)|^2 and max |x - bf16(x)|^2 (certification bound).
+int launch_ingest(const float* src, int64_t n, int d, float* rows_f32, __nv_bfloat16* scan, int64_t dpad,
+                  float* norms, float* stats, cudaStream_t st);
+// K7: pooling (+normalise) of encoder output, optionally fused with the ingest writes.
+int launch_pool(const float* hidden, const int64_t* mask, int64_t B, int64_t T, int d, int pool, int normalize,
+                float* out_f32, __nv_bfloat16* scan, int64_t dpad, float* norms, float* stats, cudaStream_t st);
+int launch_synth(uint64_t seed, int64_t row0, int64_t nrows, int d, int normalize, float* out, cudaStream_t st);
+// query preparation for the tensor path: bf16 copy (pitch dpad, rows padded to nq_pad with zeros),
+// |q|^2 in fp32 and the norm of the bf16 rounding error of each query.
+int launch_prep_queries(const float* q, int nq, int nq_pad, int d, __nv_bfloat16* qb, int64_t dpad, float* qnorm,
+                        float* qerr, cudaStream_t st);
+int launch_bf16_to_f32(const __nv_bfloat16* src, int64_t pitch, int64_t n, int d, float* dst, cudaStream_t st);
+
+// K4: exact fp32 re-rank of coarse candidates + certification.
+struct RerankArgs {
+    const float* rows_f32;          // authoritative fp32 rows (or null)
+    const __nv_bfloat16* rows_bf16; // authoritative bf16 rows when storage is bf16
+    int64_t pitch_bf16;
+    const float* q;                 // [nq, d] fp32
+    const float* qnorm;             // |q|^2
+    const float* qerr;              // |q - bf16(q)|
+    const float* cand_key;          // [nq, kp] coarse keys (sorted ascending)
+    const int32_t* cand_id;         // [nq, kp]
+    int nq, kp, k, d, metric;
+    int64_t ntotal;
+    float max_row_norm;             // max |x~| over the index (bf16 copy)
+    float max_row_err;              // max |x - bf16(x)| over the index (0 for bf16 storage)
+    int certify;
+    float* out_key;                 // [nq, k] exact keys
+    int32_t* out_id;                // [nq, k]
+    int32_t* fail_list;             // queries that could not be certified
+    int32_t* fail_count;
+};
+int launch_rerank(const RerankArgs& a, cudaStream_t st);
+
+// K2: tcgen05 / TMEM / TMA contraction with fused top-k (gemm_topk_sm100.cu)
+struct TensorScanPlan {
+    int nq_tiles;      // ceil(nq / 128)
+    int nsplits;       // database streams per query tile
+    int kp;            // candidates kept per (query, stream)
+    size_t smem_bytes;
+};
+int plan_tensor_scan(int nq, int64_t n, int d, int kp, TensorScanPlan* plan);
+int launch_tensor_scan(const __nv_bfloat16* scan, int64_t dpad, const float* norms, int64_t n, int metric,
+                       const __nv_bfloat16* qb, int nq, int nq_pad, const TensorScanPlan& plan, float* pk,
+                       int32_t* pi, cudaStream_t st);
+
+}  // namespace b2f

@@ -1,0 +1,444 @@
+// gemm_topk_sm100.cu -- K2: the query x database contraction on 5th-gen tensor cores with a fused
+// |x|^2 - 2 q.x epilogue and on-chip top-k'.  The distance matrix is never written anywhere.
+//
+// Replaces faiss's exhaustive_L2sqr_blas / exhaustive_inner_product_blas (sgemm over 4096 x 1024
+// blocks + heap update; the nq >= 20 path behind index.search, faiss_store.py:64,
+// rag_datastore_manager.py:218) with one persistent, warp-specialised sm_100a kernel:
+//
+//   warp 0   TMA producer: cp.async.bulk.tensor.2d of a [128 x 64] bf16 query block and a
+//            [256 x 64] bf16 database block per pipeline stage (SWIZZLE_128B), mbarrier complete_tx
+//   warp 1   MMA issuer: one elected lane issues tcgen05.mma.cta_group::1.kind::f16, M=128 (queries)
+//            x N=256 (database rows) x K=16, fp32 accumulators in TMEM; tcgen05.commit frees the
+//            smem stage / publishes the accumulator
+//   warp 2   TMEM allocator (512 columns = two 128x256 fp32 accumulators, double buffered)
+//   warp 3   bias loader: |x~|^2 of the 256 rows of the tile (+inf for rows past the end) -> smem
+//   warps 4-7  epilogue: tcgen05.ld 32 columns at a time; thread t owns query t of the tile, so the
+//            running top-k' is thread-private: key = bias[col] - 2*acc (L2) or -acc (IP) is compared
+//            with a register threshold; the rare survivor replaces the root of the thread's max-heap
+//            (shared memory, [slot][thread] layout => conflict free).  At the end each heap is sorted
+//            and written as the (query, split) partial list.
+//
+// Work split: grid = nq_tiles x nsplits (<= 148 CTAs, one per SM); CTA (qt, s) streams database tiles
+// [s*NT/nsplits, (s+1)*NT/nsplits) against query tile qt.  CTAs that share a split walk the same
+// database tiles at the same time, so the database is fetched from HBM ~once and re-read from L2.
+//
+// Roofline: nq <= 128 -> HBM-bound, algorithmic bytes n * dpad * 2; large nq -> tensor-bound,
+// 2 * nq * n * d flop.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace b2f {
+
+namespace k2 {
+
+constexpr int BM = 128;        // queries per tile  (UMMA M)
+constexpr int BN = 256;        // database rows per tile (UMMA N)
+constexpr int BK = 64;         // bf16 elements per stage along d: 128 bytes = one swizzle atom
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 3;
+constexpr int A_BYTES = BM * BK * 2;  // 16 KB
+constexpr int B_BYTES = BN * BK * 2;  // 32 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int THREADS = 256;
+constexpr int EPI_THREADS = 128;
+constexpr int TMEM_COLS = 512;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(x), "r"(y)
+        : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (rows of 128 bytes, 8-row atoms 1024 B apart)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);  // start address
+    d |= (uint64_t)1 << 16;                  // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;        // stride byte offset: next 8-row group
+    d |= (uint64_t)1 << 46;                  // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                  // SWIZZLE_128B
+    return d;
+}
+
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=256
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int KP>
+struct Smem {
+    static constexpr size_t stages_off = 0;
+    static constexpr size_t heapk_off = (size_t)STAGES * STAGE_BYTES;
+    static constexpr size_t heapi_off = heapk_off + (size_t)EPI_THREADS * KP * 4;
+    static constexpr size_t bias_off = heapi_off + (size_t)EPI_THREADS * KP * 4;
+    static constexpr size_t bar_off = bias_off + 2 * BN * 4;
+    static constexpr int nbars = 2 * STAGES + 6;
+    static constexpr size_t tmem_off = bar_off + nbars * 8;
+    static constexpr size_t total = tmem_off + 16;
+    static constexpr size_t alloc = total + 1024;  // slack for manual 1024-byte alignment
+};
+
+// thread-private max-heap in shared memory, element j of thread t at [j * 128 + t].
+// sift (key,id) down from the root of the first n heap slots.
+template <int KP>
+__device__ __forceinline__ void heap_sift_down_n(float* hk, int32_t* hi, int tid, int n, float key, int32_t id) {
+    int i = 0;
+    while (true) {
+        const int l = 2 * i + 1;
+        if (l >= n) break;
+        int m = l;
+        float mk = hk[l * EPI_THREADS + tid];
+        int32_t mi = hi[l * EPI_THREADS + tid];
+        if (l + 1 < n) {
+            const float rk = hk[(l + 1) * EPI_THREADS + tid];
+            const int32_t ri = hi[(l + 1) * EPI_THREADS + tid];
+            if (cand_less(mk, mi, rk, ri)) {
+                m = l + 1;
+                mk = rk;
+                mi = ri;
+            }
+        }
+        if (!cand_less(key, id, mk, mi)) break;
+        hk[i * EPI_THREADS + tid] = mk;
+        hi[i * EPI_THREADS + tid] = mi;
+        i = m;
+    }
+    hk[i * EPI_THREADS + tid] = key;
+    hi[i * EPI_THREADS + tid] = id;
+}
+
+// Rare path of the epilogue, kept out of line so the 32x-unrolled compare loop stays small:
+// replace the heap root (the current worst of the thread's k' best) and return the new threshold.
+template <int KP>
+__device__ __noinline__ float heap_push(float* hk, int32_t* hi, int tid, float key, int32_t id) {
+    heap_sift_down_n<KP>(hk, hi, tid, KP, key, id);
+    return hk[tid];
+}
+
+template <int KP, bool L2>
+__global__ void __launch_bounds__(THREADS, 1)
+tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
+                   const float* __restrict__ norms, int64_t n, int nq, int kblocks, int nq_tiles, int nsplits,
+                   float* __restrict__ pk, int32_t* __restrict__ pi) {
+    using L = Smem<KP>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    float* heap_k = reinterpret_cast<float*>(smem + L::heapk_off);
+    int32_t* heap_i = reinterpret_cast<int32_t*>(smem + L::heapi_off);
+    float* bias = reinterpret_cast<float*>(smem + L::bias_off);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::bar_off);
+    uint64_t* full_bar = bars;                     // [STAGES]  TMA -> MMA
+    uint64_t* empty_bar = bars + STAGES;           // [STAGES]  MMA -> TMA
+    uint64_t* tmem_full = bars + 2 * STAGES;       // [2]       MMA -> epilogue
+    uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // [2]       epilogue -> MMA, bias loader
+    uint64_t* bias_full = bars + 2 * STAGES + 4;   // [2]       bias loader -> epilogue
+    uint32_t* tmem_base_holder = reinterpret_cast<uint32_t*>(smem + L::tmem_off);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qt = blockIdx.x % nq_tiles, split = blockIdx.x / nq_tiles;
+    const int64_t ntiles = (n + BN - 1) / BN;
+    const int64_t t_begin = ntiles * split / nsplits, t_end = ntiles * (split + 1) / nsplits;
+    const int my_tiles = (int)(t_end - t_begin);
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_q)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_x)) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; s++) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; a++) {
+            mbar_init(&tmem_full[a], 1);
+            mbar_init(&tmem_empty[a], 4);  // one arrive per epilogue warp
+            mbar_init(&bias_full[a], 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_holder)),
+                     "r"((uint32_t)TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_holder;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = 0; t < my_tiles; t++) {
+                const int row0 = (int)((t_begin + t) * BN);
+                for (int kb = 0; kb < kblocks; kb++) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + (size_t)stage * STAGE_BYTES;
+                    mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+                    tma_load_2d(sa, &map_q, kb * BK, qt * BM, &full_bar[stage]);
+                    tma_load_2d(sa + A_BYTES, &map_x, kb * BK, row0, &full_bar[stage]);
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = 0; t < my_tiles; t++) {
+                const int acc = t & 1;
+                const uint32_t acc_phase = (t >> 1) & 1;
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < kblocks; kb++) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
+                    const uint64_t adesc = make_smem_desc(sa);
+                    const uint64_t bdesc = make_smem_desc(sa + A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; k++) {
+                        // advance both descriptors by 32 bytes (16 bf16) inside the 128-byte swizzle atom
+                        umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit(&tmem_full[acc]);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 3) {
+        // ===================== bias loader =====================
+        for (int t = 0; t < my_tiles; t++) {
+            const int acc = t & 1;
+            const uint32_t acc_phase = (t >> 1) & 1;
+            mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+            const int64_t row0 = (t_begin + t) * BN;
+#pragma unroll
+            for (int j = 0; j < BN / 32; j++) {
+                const int64_t row = row0 + j * 32 + lane;
+                float b = __int_as_float(0x7f800000);  // +inf: rows past the end never pass the threshold
+                if (row < n) b = L2 ? __ldg(norms + row) : 0.f;
+                bias[acc * BN + j * 32 + lane] = b;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bias_full[acc]);
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue: fused distance + top-k' =====================
+        const int tid = threadIdx.x - 128;            // 0..127 == TMEM lane == query row in the tile
+        const int wq = warp & 3;                      // TMEM lane quarter this warp may access
+        const int qrow = qt * BM + tid;
+        const bool active = qrow < nq;
+        for (int j = 0; j < KP; j++) {
+            heap_k[j * EPI_THREADS + tid] = FLT_MAX;
+            heap_i[j * EPI_THREADS + tid] = -1;
+        }
+        float thr = FLT_MAX;
+        for (int t = 0; t < my_tiles; t++) {
+            const int acc = t & 1;
+            const uint32_t acc_phase = (t >> 1) & 1;
+            mbar_wait(&bias_full[acc], acc_phase);
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const int32_t row0 = (int32_t)((t_begin + t) * BN);
+            const float* tb = bias + acc * BN;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; c++) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * BN + c * 32), r);
+                tmem_ld_wait();
+                if (active) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        const float s = __uint_as_float(r[j]);
+                        const float key = L2 ? fmaf(-2.f, s, tb[c * 32 + j]) : tb[c * 32 + j] - s;
+                        if (key < thr) thr = heap_push<KP>(heap_k, heap_i, tid, key, row0 + c * 32 + j);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+        // heap sort (ascending) and write the partial list of (query, split)
+        if (active) {
+            for (int m = KP - 1; m > 0; m--) {
+                const float lk_ = heap_k[m * EPI_THREADS + tid];
+                const int32_t li_ = heap_i[m * EPI_THREADS + tid];
+                heap_k[m * EPI_THREADS + tid] = heap_k[tid];
+                heap_i[m * EPI_THREADS + tid] = heap_i[tid];
+                heap_sift_down_n<KP>(heap_k, heap_i, tid, m, lk_, li_);
+            }
+            float* ok = pk + ((int64_t)qrow * nsplits + split) * KP;
+            int32_t* oi = pi + ((int64_t)qrow * nsplits + split) * KP;
+            for (int j = 0; j < KP; j++) {
+                ok[j] = heap_k[j * EPI_THREADS + tid];
+                oi[j] = heap_i[j * EPI_THREADS + tid];
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+    }
+}
+
+// ---- host side --------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+static int make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows, uint64_t pitch_elems, uint32_t box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return B2F_ECUDA;
+    }
+    cuuint64_t dims[2] = {inner, rows};
+    cuuint64_t strides[1] = {pitch_elems * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+        return B2F_ECUDA;
+    }
+    return B2F_OK;
+}
+
+template <int KP, bool L2>
+static int launch_k2(const CUtensorMap& mq, const CUtensorMap& mx, const float* norms, int64_t n, int nq, int kblocks,
+                     const TensorScanPlan& plan, float* pk, int32_t* pi, cudaStream_t st) {
+    auto kern = tensor_scan_kernel<KP, L2>;
+    static bool configured = false;
+    if (!configured) {
+        B2F_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<KP>::alloc));
+        configured = true;
+    }
+    kern<<<plan.nq_tiles * plan.nsplits, THREADS, Smem<KP>::alloc, st>>>(mq, mx, norms, n, nq, kblocks, plan.nq_tiles,
+                                                                        plan.nsplits, pk, pi);
+    B2F_CUDA(cudaGetLastError());
+    return B2F_OK;
+}
+
+}  // namespace k2
+
+int plan_tensor_scan(int nq, int64_t n, int d, int kp, TensorScanPlan* plan) {
+    if (kp != 32 && kp != 64) return B2F_EINVAL;
+    if (n <= 0 || nq <= 0) return B2F_EINVAL;
+    (void)d;
+    plan->kp = kp;
+    plan->nq_tiles = (nq + k2::BM - 1) / k2::BM;
+    const int64_t ntiles = (n + k2::BN - 1) / k2::BN;
+    int ns = kNumSMs / plan->nq_tiles;
+    if (ns < 1) ns = 1;
+    if (ns > ntiles) ns = (int)ntiles;
+    plan->nsplits = ns;
+    plan->smem_bytes = kp == 32 ? k2::Smem<32>::alloc : k2::Smem<64>::alloc;
+    return B2F_OK;
+}
+
+int launch_tensor_scan(const __nv_bfloat16* scan, int64_t dpad, const float* norms, int64_t n, int metric,
+                       const __nv_bfloat16* qb, int nq, int nq_pad, const TensorScanPlan& plan, float* pk, int32_t* pi,
+                       cudaStream_t st) {
+    CUtensorMap mq, mx;
+    B2F_TRY(k2::make_map(&mq, qb, (uint64_t)dpad, (uint64_t)nq_pad, (uint64_t)dpad, k2::BM));
+    B2F_TRY(k2::make_map(&mx, scan, (uint64_t)dpad, (uint64_t)n, (uint64_t)dpad, k2::BN));
+    const int kblocks = (int)(dpad / k2::BK);
+    const bool l2 = metric == B2F_METRIC_L2;
+    if (plan.kp == 32)
+        return l2 ? k2::launch_k2<32, true>(mq, mx, norms, n, nq, kblocks, plan, pk, pi, st)
+                  : k2::launch_k2<32, false>(mq, mx, norms, n, nq, kblocks, plan, pk, pi, st);
+    if (plan.kp == 64)
+        return l2 ? k2::launch_k2<64, true>(mq, mx, norms, n, nq, kblocks, plan, pk, pi, st)
+                  : k2::launch_k2<64, false>(mq, mx, norms, n, nq, kblocks, plan, pk, pi, st);
+    set_error("tensor scan: k' = %d not supported", plan.kp);
+    return B2F_EINVAL;
+}
+
+}  // namespace b2f

@@ -1,0 +1,910 @@
+// index.cu -- host side of the C ABI (include/b200flat.h): device storage, ingest, the search
+// pipelines (K1 scan | K2 tensor scan -> K3 merge -> K4 re-rank -> finalize), FAISS-compatible
+// file I/O.  No CPU compute path exists here: without a usable sm_100 device every compute entry
+// point returns B2F_ENOGPU.
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+
+namespace b2f {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace b2f
+
+using namespace b2f;
+
+struct b2f_index {
+    int d = 0, metric = 1, storage = 0, device = 0;
+    int64_t ntotal = 0, cap = 0, dpad = 0;
+    float* rows_f32 = nullptr;        // [cap, d]      authoritative rows (B2F_STORE_F32)
+    __nv_bfloat16* scan = nullptr;    // [cap, dpad]   bf16 scan copy (authoritative for B2F_STORE_BF16)
+    float* norms = nullptr;           // [cap]         |bf16 row|^2 in fp32
+    float* stats = nullptr;           // [2] device    max |x~|^2, max |x - x~|^2
+    cudaStream_t stream = nullptr;
+    char* ws = nullptr;               // device workspace (grow only)
+    size_t ws_bytes = 0;
+    char* pinned = nullptr;           // host staging
+    size_t pinned_bytes = 0;
+    std::vector<cudaEvent_t> ev;      // profiling events
+    std::mutex mu;
+    b2f_stats st{};
+    float host_stats[2] = {0.f, 0.f};
+    bool stats_dirty = true;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+int check_device(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        set_error("no CUDA device available (%s); this engine has no CPU path", e == cudaSuccess ? "count=0" : cudaGetErrorString(e));
+        return B2F_ENOGPU;
+    }
+    if (device < 0 || device >= n) {
+        set_error("device %d out of range [0,%d)", device, n);
+        return B2F_EINVAL;
+    }
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, device) != cudaSuccess || p.major != 10) {
+        cudaGetLastError();
+        set_error("device %d is not sm_100 (Blackwell B200); kernels are built for sm_100a only", device);
+        return B2F_ENOGPU;
+    }
+    return B2F_OK;
+}
+
+// simple bump allocator over the index workspace
+struct Bump {
+    char* base;
+    size_t off = 0;
+    explicit Bump(char* b) : base(b) {}
+    template <typename T>
+    T* take(size_t count) {
+        off = align_up(off, 256);
+        T* p = reinterpret_cast<T*>(base + off);
+        off += count * sizeof(T);
+        return p;
+    }
+};
+
+int ensure_ws(b2f_index* ix, size_t bytes) {
+    if (bytes <= ix->ws_bytes) return B2F_OK;
+    if (ix->ws) {
+        B2F_CUDA(cudaStreamSynchronize(ix->stream));
+        B2F_CUDA(cudaDeviceSynchronize());
+        B2F_CUDA(cudaFree(ix->ws));
+        ix->ws = nullptr;
+        ix->ws_bytes = 0;
+    }
+    bytes = align_up(bytes + (bytes >> 2), 1 << 20);
+    cudaError_t e = cudaMalloc(&ix->ws, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error("workspace cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        return B2F_ENOMEM;
+    }
+    ix->ws_bytes = bytes;
+    return B2F_OK;
+}
+
+int ensure_pinned(b2f_index* ix, size_t bytes) {
+    if (bytes <= ix->pinned_bytes) return B2F_OK;
+    if (ix->pinned) {
+        B2F_CUDA(cudaStreamSynchronize(ix->stream));
+        B2F_CUDA(cudaFreeHost(ix->pinned));
+        ix->pinned = nullptr;
+        ix->pinned_bytes = 0;
+    }
+    cudaError_t e = cudaMallocHost(&ix->pinned, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error("cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        return B2F_ENOMEM;
+    }
+    ix->pinned_bytes = bytes;
+    return B2F_OK;
+}
+
+int ensure_capacity(b2f_index* ix, int64_t need) {
+    if (need <= ix->cap) return B2F_OK;
+    if (need > (int64_t)INT32_MAX - 64) {
+        set_error("a single index holds at most 2^31-65 rows (row-shard across GPUs beyond that)");
+        return B2F_EINVAL;
+    }
+    int64_t ncap = ix->cap + ix->cap / 2;
+    if (ncap < need) ncap = need;
+    if (ncap < 1024) ncap = 1024;
+    float* nrows = nullptr;
+    __nv_bfloat16* nscan = nullptr;
+    float* nnorm = nullptr;
+    cudaError_t e = cudaSuccess;
+    if (ix->storage == B2F_STORE_F32) e = cudaMalloc(&nrows, (size_t)ncap * ix->d * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&nscan, (size_t)ncap * ix->dpad * sizeof(__nv_bfloat16));
+    if (e == cudaSuccess) e = cudaMalloc(&nnorm, (size_t)ncap * sizeof(float));
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(nrows);
+        cudaFree(nscan);
+        cudaFree(nnorm);
+        set_error("device allocation for %lld rows failed: %s", (long long)ncap, cudaGetErrorString(e));
+        return B2F_ENOMEM;
+    }
+    if (ix->ntotal > 0) {
+        if (nrows) B2F_CUDA(cudaMemcpyAsync(nrows, ix->rows_f32, (size_t)ix->ntotal * ix->d * sizeof(float), cudaMemcpyDeviceToDevice, ix->stream));
+        B2F_CUDA(cudaMemcpyAsync(nscan, ix->scan, (size_t)ix->ntotal * ix->dpad * sizeof(__nv_bfloat16), cudaMemcpyDeviceToDevice, ix->stream));
+        B2F_CUDA(cudaMemcpyAsync(nnorm, ix->norms, (size_t)ix->ntotal * sizeof(float), cudaMemcpyDeviceToDevice, ix->stream));
+        ix->st.launches += 0;
+    }
+    B2F_CUDA(cudaStreamSynchronize(ix->stream));
+    B2F_CUDA(cudaDeviceSynchronize());  // other streams may still be searching the old buffers
+    cudaFree(ix->rows_f32);
+    cudaFree(ix->scan);
+    cudaFree(ix->norms);
+    ix->rows_f32 = nrows;
+    ix->scan = nscan;
+    ix->norms = nnorm;
+    ix->cap = ncap;
+    ix->st.bytes_rows = nrows ? (int64_t)ncap * ix->d * 4 : (int64_t)ncap * ix->dpad * 2;
+    ix->st.bytes_scan = (nrows ? (int64_t)ncap * ix->dpad * 2 : 0) + (int64_t)ncap * 4;
+    return B2F_OK;
+}
+
+cudaEvent_t get_event(b2f_index* ix, size_t i) {
+    while (ix->ev.size() <= i) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+        ix->ev.push_back(e);
+    }
+    return ix->ev[i];
+}
+
+int refresh_host_stats(b2f_index* ix, cudaStream_t st) {
+    if (!ix->stats_dirty) return B2F_OK;
+    B2F_CUDA(cudaMemcpyAsync(ix->host_stats, ix->stats, 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    B2F_CUDA(cudaStreamSynchronize(st));
+    ix->stats_dirty = false;
+    return B2F_OK;
+}
+
+// make `st` wait for everything queued so far on the index's own stream (ingest) and vice versa
+int order_after(cudaStream_t waiter, cudaStream_t producer, b2f_index* ix) {
+    if (waiter == producer) return B2F_OK;
+    cudaEvent_t e = get_event(ix, 0);
+    if (!e) {
+        set_error("cudaEventCreate failed");
+        return B2F_ECUDA;
+    }
+    B2F_CUDA(cudaEventRecord(e, producer));
+    B2F_CUDA(cudaStreamWaitEvent(waiter, e, 0));
+    return B2F_OK;
+}
+
+int largest_pow2_le(int x) {
+    int p = 1;
+    while (p * 2 <= x) p *= 2;
+    return p;
+}
+
+// ---- K1 pipeline: scan groups of <= 8 queries -------------------------------------------------
+// qsel_dev (optional): the list of query rows to process (nsel of them), results scattered to those rows.
+int run_scan(b2f_index* ix, const float* qd, const int32_t* qsel_dev, int nsel, int k, float* Dd, int64_t* Id,
+             int64_t id_offset, Bump& bump, cudaStream_t st, bool profile, size_t ev_base, int* n_main) {
+    const int dq = ix->storage == B2F_STORE_F32 ? (ix->d % 4 == 0 ? ix->d : ix->d) : (int)align_up(ix->d, 8);
+    int g = 8;
+    g = g < largest_pow2_le(1024 / k > 0 ? 1024 / k : 1) ? g : largest_pow2_le(1024 / k > 0 ? 1024 / k : 1);
+    const int by_smem = (int)(16384 / (dq > 0 ? dq : 1));
+    if (by_smem < 1) {
+        set_error("d=%d too large for the streaming scan", ix->d);
+        return B2F_EINVAL;
+    }
+    g = g < largest_pow2_le(by_smem) ? g : largest_pow2_le(by_smem);
+    const int maxparts = scan_max_parts();
+    float* pk = bump.take<float>((size_t)g * maxparts * k);
+    int32_t* pi = bump.take<int32_t>((size_t)g * maxparts * k);
+    float* mk = bump.take<float>((size_t)g * k);
+    int32_t* mi = bump.take<int32_t>((size_t)g * k);
+    for (int q0 = 0; q0 < nsel; q0 += g) {
+        const int nq = nsel - q0 < g ? nsel - q0 : g;
+        int nparts = 0;
+        const float* qptr = qsel_dev ? qd : qd + (int64_t)q0 * ix->d;
+        const int32_t* sel = qsel_dev ? qsel_dev + q0 : nullptr;
+        if (profile) B2F_CUDA(cudaEventRecord(get_event(ix, ev_base + 2 * (size_t)*n_main), st));
+        if (ix->storage == B2F_STORE_F32)
+            B2F_TRY(launch_scan_f32(ix->rows_f32, ix->ntotal, ix->d, ix->metric, qptr, sel, nq, k, pk, pi, &nparts, st));
+        else
+            B2F_TRY(launch_scan_bf16(ix->scan, ix->dpad, ix->ntotal, ix->d, ix->metric, qptr, sel, nq, k, pk, pi, &nparts, st));
+        if (profile) B2F_CUDA(cudaEventRecord(get_event(ix, ev_base + 2 * (size_t)*n_main + 1), st));
+        (*n_main)++;
+        B2F_TRY(launch_merge_parts(pk, pi, nq, nparts, k, k, mk, mi, st));
+        if (sel)
+            B2F_TRY(launch_finalize(mk, mi, nq, k, k, ix->metric, id_offset, sel, Dd, Id, st));
+        else
+            B2F_TRY(launch_finalize(mk, mi, nq, k, k, ix->metric, id_offset, nullptr, Dd + (int64_t)q0 * k, Id + (int64_t)q0 * k, st));
+        ix->st.launches += 3;
+        ix->st.last_launches += 3;
+    }
+    return B2F_OK;
+}
+
+size_t scan_ws_bytes(int k) {
+    const size_t g = 8, mp = (size_t)scan_max_parts();
+    return 2 * (g * mp * k * 4 + 256) + 2 * (g * k * 4 + 256) + 4096;
+}
+
+int tensor_kprime(int k, int slack) {
+    int kp = slack > 0 ? k + slack : (k + 22 > 2 * k ? k + 22 : 2 * k);
+    // the fused epilogue keeps per-thread candidate buffers of a few fixed sizes
+    if (kp <= 32) return 32;
+    if (kp <= 64) return 64;
+    if (kp <= 128) return 128;
+    return kp;  // unsupported by K2; caller falls back to the scan
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int b2f_version(void) { return B2F_VERSION; }
+
+const char* b2f_last_error(void) { return g_err; }
+
+int b2f_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    int ok = 0;
+    for (int i = 0; i < n; i++) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ok++;
+    }
+    return ok;
+}
+
+int b2f_index_create(int32_t d, int32_t metric, int32_t storage, int32_t device, b2f_index** out) {
+    if (!out) {
+        set_error("out is NULL");
+        return B2F_EINVAL;
+    }
+    *out = nullptr;
+    if (d <= 0 || d > 16384) {
+        set_error("d=%d out of range [1,16384]", d);
+        return B2F_EINVAL;
+    }
+    if (metric != B2F_METRIC_L2 && metric != B2F_METRIC_INNER_PRODUCT) {
+        set_error("metric %d not supported (0 = inner product, 1 = L2)", metric);
+        return B2F_EINVAL;
+    }
+    if (storage != B2F_STORE_F32 && storage != B2F_STORE_BF16) {
+        set_error("storage %d not supported", storage);
+        return B2F_EINVAL;
+    }
+    B2F_TRY(check_device(device));
+    DeviceGuard g(device);
+    b2f_index* ix = new (std::nothrow) b2f_index();
+    if (!ix) return B2F_ENOMEM;
+    ix->d = d;
+    ix->metric = metric;
+    ix->storage = storage;
+    ix->device = device;
+    ix->dpad = (int64_t)align_up((size_t)d, 64);
+    cudaError_t e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&ix->stats, 2 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemset(ix->stats, 0, 2 * sizeof(float));
+    if (e != cudaSuccess) {
+        set_error("index init failed: %s", cudaGetErrorString(e));
+        delete ix;
+        return B2F_ECUDA;
+    }
+    *out = ix;
+    return B2F_OK;
+}
+
+int b2f_index_destroy(b2f_index* ix) {
+    if (!ix) return B2F_OK;
+    DeviceGuard g(ix->device);
+    cudaDeviceSynchronize();
+    cudaFree(ix->rows_f32);
+    cudaFree(ix->scan);
+    cudaFree(ix->norms);
+    cudaFree(ix->stats);
+    cudaFree(ix->ws);
+    if (ix->pinned) cudaFreeHost(ix->pinned);
+    for (cudaEvent_t e : ix->ev) cudaEventDestroy(e);
+    if (ix->stream) cudaStreamDestroy(ix->stream);
+    delete ix;
+    return B2F_OK;
+}
+
+int b2f_index_reset(b2f_index* ix) {
+    if (!ix) {
+        set_error("index is NULL");
+        return B2F_EINVAL;
+    }
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    ix->ntotal = 0;
+    B2F_CUDA(cudaMemsetAsync(ix->stats, 0, 2 * sizeof(float), ix->stream));
+    B2F_CUDA(cudaStreamSynchronize(ix->stream));
+    ix->stats_dirty = true;
+    return B2F_OK;
+}
+
+int b2f_index_reserve(b2f_index* ix, int64_t nrows) {
+    if (!ix) {
+        set_error("index is NULL");
+        return B2F_EINVAL;
+    }
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    return ensure_capacity(ix, nrows);
+}
+
+int64_t b2f_index_ntotal(const b2f_index* ix) { return ix ? ix->ntotal : -1; }
+int32_t b2f_index_d(const b2f_index* ix) { return ix ? ix->d : -1; }
+int32_t b2f_index_metric(const b2f_index* ix) { return ix ? ix->metric : -1; }
+int32_t b2f_index_storage(const b2f_index* ix) { return ix ? ix->storage : -1; }
+int32_t b2f_index_device(const b2f_index* ix) { return ix ? ix->device : -1; }
+
+int b2f_index_stats(const b2f_index* ix, b2f_stats* out) {
+    if (!ix || !out) {
+        set_error("NULL argument");
+        return B2F_EINVAL;
+    }
+    *out = ix->st;
+    return B2F_OK;
+}
+
+// ---- add -------------------------------------------------------------------------------------------
+static int add_device_rows(b2f_index* ix, const float* src_dev, int64_t n, cudaStream_t st) {
+    // src_dev: [n, d] fp32 on the device (may alias the tail of rows_f32)
+    float* rows_out = nullptr;
+    if (ix->storage == B2F_STORE_F32) {
+        float* dst = ix->rows_f32 + ix->ntotal * ix->d;
+        if (src_dev != dst) rows_out = dst;
+    }
+    B2F_TRY(launch_ingest(src_dev, n, ix->d, rows_out, ix->scan + ix->ntotal * ix->dpad, ix->dpad,
+                          ix->norms + ix->ntotal, ix->stats, st));
+    ix->st.launches++;
+    return B2F_OK;
+}
+
+int b2f_index_add(b2f_index* ix, int64_t n, const float* x, int32_t mem, void* stream) {
+    if (!ix || n < 0 || (n > 0 && !x)) {
+        set_error("add: bad arguments");
+        return B2F_EINVAL;
+    }
+    if (n == 0) return B2F_OK;
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    if (!g.ok) {
+        set_error("cudaSetDevice(%d) failed", ix->device);
+        return B2F_ENOGPU;
+    }
+    B2F_TRY(ensure_capacity(ix, ix->ntotal + n));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ix->stream;
+    if (mem == B2F_MEM_DEVICE) {
+        B2F_TRY(add_device_rows(ix, x, n, st));
+        ix->ntotal += n;
+    } else if (ix->storage == B2F_STORE_F32) {
+        // host -> final location, then derive the scan copy in place
+        float* dst = ix->rows_f32 + ix->ntotal * ix->d;
+        B2F_CUDA(cudaMemcpyAsync(dst, x, (size_t)n * ix->d * sizeof(float), cudaMemcpyHostToDevice, st));
+        B2F_TRY(add_device_rows(ix, dst, n, st));
+        ix->ntotal += n;
+    } else {
+        // bf16 storage: stage fp32 chunks through the workspace
+        const int64_t chunk = (64LL << 20) / ((int64_t)ix->d * 4) > 0 ? (64LL << 20) / ((int64_t)ix->d * 4) : 1;
+        B2F_TRY(ensure_ws(ix, (size_t)chunk * ix->d * 4 + 4096));
+        for (int64_t r0 = 0; r0 < n; r0 += chunk) {
+            const int64_t m = n - r0 < chunk ? n - r0 : chunk;
+            B2F_CUDA(cudaMemcpyAsync(ix->ws, x + r0 * ix->d, (size_t)m * ix->d * 4, cudaMemcpyHostToDevice, st));
+            B2F_TRY(add_device_rows(ix, reinterpret_cast<const float*>(ix->ws), m, st));
+            ix->ntotal += m;
+        }
+    }
+    ix->stats_dirty = true;
+    if (mem == B2F_MEM_HOST) B2F_CUDA(cudaStreamSynchronize(st));
+    return B2F_OK;
+}
+
+int b2f_index_add_synth(b2f_index* ix, uint64_t seed, int64_t row0, int64_t nrows, int32_t normalize) {
+    if (!ix || nrows < 0) {
+        set_error("add_synth: bad arguments");
+        return B2F_EINVAL;
+    }
+    if (nrows == 0) return B2F_OK;
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    B2F_TRY(ensure_capacity(ix, ix->ntotal + nrows));
+    cudaStream_t st = ix->stream;
+    if (ix->storage == B2F_STORE_F32) {
+        float* dst = ix->rows_f32 + ix->ntotal * ix->d;
+        B2F_TRY(launch_synth(seed, row0, nrows, ix->d, normalize, dst, st));
+        B2F_TRY(add_device_rows(ix, dst, nrows, st));
+        ix->ntotal += nrows;
+        ix->st.launches++;
+    } else {
+        const int64_t chunk = (256LL << 20) / ((int64_t)ix->d * 4) > 0 ? (256LL << 20) / ((int64_t)ix->d * 4) : 1;
+        B2F_TRY(ensure_ws(ix, (size_t)chunk * ix->d * 4 + 4096));
+        for (int64_t r0 = 0; r0 < nrows; r0 += chunk) {
+            const int64_t m = nrows - r0 < chunk ? nrows - r0 : chunk;
+            B2F_TRY(launch_synth(seed, row0 + r0, m, ix->d, normalize, reinterpret_cast<float*>(ix->ws), st));
+            B2F_TRY(add_device_rows(ix, reinterpret_cast<const float*>(ix->ws), m, st));
+            ix->ntotal += m;
+            ix->st.launches++;
+        }
+    }
+    ix->stats_dirty = true;
+    B2F_CUDA(cudaStreamSynchronize(st));
+    return B2F_OK;
+}
+
+int b2f_index_add_pooled(b2f_index* ix, const float* hidden, const int64_t* mask, int64_t B, int64_t T, int32_t pool,
+                         int32_t normalize, void* stream) {
+    if (!ix || B < 0 || (B > 0 && !hidden)) {
+        set_error("add_pooled: bad arguments");
+        return B2F_EINVAL;
+    }
+    if (B == 0) return B2F_OK;
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    B2F_TRY(ensure_capacity(ix, ix->ntotal + B));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ix->stream;
+    float* rows_out = ix->storage == B2F_STORE_F32 ? ix->rows_f32 + ix->ntotal * ix->d : nullptr;
+    B2F_TRY(launch_pool(hidden, mask, B, T, ix->d, pool, normalize, rows_out, ix->scan + ix->ntotal * ix->dpad, ix->dpad,
+                        ix->norms + ix->ntotal, ix->stats, st));
+    ix->st.launches++;
+    ix->ntotal += B;
+    ix->stats_dirty = true;
+    return B2F_OK;
+}
+
+int b2f_pool_normalize(const float* hidden, const int64_t* mask, int64_t B, int64_t T, int32_t d, int32_t pool,
+                       int32_t normalize, float* out, int32_t device, void* stream) {
+    if (B < 0 || d <= 0 || (B > 0 && (!hidden || !out))) {
+        set_error("pool_normalize: bad arguments");
+        return B2F_EINVAL;
+    }
+    B2F_TRY(check_device(device));
+    DeviceGuard g(device);
+    return launch_pool(hidden, mask, B, T, d, pool, normalize, out, nullptr, 0, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int b2f_synth_rows(uint64_t seed, int64_t row0, int64_t nrows, int32_t d, int32_t normalize, float* out, int32_t device,
+                   void* stream) {
+    if (nrows < 0 || d <= 0 || (nrows > 0 && !out)) {
+        set_error("synth_rows: bad arguments");
+        return B2F_EINVAL;
+    }
+    B2F_TRY(check_device(device));
+    DeviceGuard g(device);
+    return launch_synth(seed, row0, nrows, d, normalize, out, (cudaStream_t)stream);
+}
+
+int b2f_merge_topk(int32_t metric, int64_t nq, int64_t k, int32_t nparts, const float* D_parts, const int64_t* I_parts,
+                   float* D, int64_t* I, int32_t device, void* stream) {
+    if (nq < 0 || k <= 0 || !D_parts || !I_parts || !D || !I) {
+        set_error("merge_topk: bad arguments");
+        return B2F_EINVAL;
+    }
+    B2F_TRY(check_device(device));
+    DeviceGuard g(device);
+    return launch_merge_faiss(metric, nq, k, nparts, D_parts, I_parts, D, I, (cudaStream_t)stream);
+}
+
+// ---- search ----------------------------------------------------------------------------------------
+int b2f_index_search(b2f_index* ix, int64_t nq64, const float* q, int64_t k64, float* D, int64_t* I, int32_t mem,
+                     void* stream, const b2f_search_params* params) {
+    if (!ix) {
+        set_error("index is NULL");
+        return B2F_EINVAL;
+    }
+    if (k64 <= 0) {
+        set_error("k must be > 0 (faiss asserts k > 0)");
+        return B2F_EINVAL;
+    }
+    if (k64 > 1024) {
+        set_error("k=%lld > 1024 is not supported by the GPU selection kernels", (long long)k64);
+        return B2F_EINVAL;
+    }
+    if (nq64 < 0 || nq64 > (1 << 24) || (nq64 > 0 && (!q || !D || !I))) {
+        set_error("search: bad arguments");
+        return B2F_EINVAL;
+    }
+    if (nq64 == 0) return B2F_OK;
+    const int nq = (int)nq64, k = (int)k64;
+    b2f_search_params P{};
+    if (params) P = *params;
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    if (!g.ok) {
+        set_error("cudaSetDevice(%d) failed", ix->device);
+        return B2F_ENOGPU;
+    }
+    cudaStream_t st = stream ? (cudaStream_t)stream : ix->stream;
+    B2F_TRY(order_after(st, ix->stream, ix));
+    const bool host = mem == B2F_MEM_HOST;
+    const bool profile = P.profile != 0;
+
+    int algo = P.algo;
+    const int scan_max = P.scan_max_nq > 0 ? P.scan_max_nq : 8;
+    int kp = tensor_kprime(k, P.slack);
+    TensorScanPlan plan{};
+    bool tensor_ok = kp <= 128 && ix->ntotal > 0 && plan_tensor_scan(nq, ix->ntotal, ix->d, kp, &plan) == B2F_OK;
+    if (algo == B2F_ALGO_AUTO) algo = (nq <= scan_max || !tensor_ok) ? B2F_ALGO_SCAN : B2F_ALGO_TENSOR;
+    if (algo == B2F_ALGO_TENSOR && !tensor_ok && ix->ntotal > 0) {
+        set_error("tensor path unavailable for k=%d (k' = %d > 128) or this shape", k, kp);
+        return B2F_EINVAL;
+    }
+    const int certify = P.certify >= 0 ? 1 : 0;
+
+    // ---- workspace -----------------------------------------------------------------------------
+    size_t need = 8192;
+    if (host) need += align_up((size_t)nq * ix->d * 4, 256) + align_up((size_t)nq * k * 4, 256) + align_up((size_t)nq * k * 8, 256);
+    need += scan_ws_bytes(k);
+    if (algo == B2F_ALGO_TENSOR) {
+        const size_t nq_pad = (size_t)plan.nq_tiles * 128;
+        need += align_up(nq_pad * ix->dpad * 2, 256) + 2 * align_up(nq_pad * 4, 256);
+        need += 2 * align_up(nq_pad * plan.nsplits * kp * 4, 256);  // partial lists
+        need += 2 * align_up((size_t)nq * kp * 4, 256);             // merged coarse
+        need += 2 * align_up((size_t)nq * k * 4, 256);              // exact
+        need += align_up((size_t)nq * 4, 256) + 256;                // fail list + count
+    }
+    B2F_TRY(ensure_ws(ix, need));
+    Bump bump(ix->ws);
+
+    const float* qd = q;
+    float* Dd = D;
+    int64_t* Id = I;
+    if (host) {
+        float* qbuf = bump.take<float>((size_t)nq * ix->d);
+        Dd = bump.take<float>((size_t)nq * k);
+        Id = bump.take<int64_t>((size_t)nq * k);
+        B2F_CUDA(cudaMemcpyAsync(qbuf, q, (size_t)nq * ix->d * 4, cudaMemcpyHostToDevice, st));
+        qd = qbuf;
+    }
+    ix->st.searches++;
+    ix->st.last_launches = 0;
+    ix->st.last_algo = algo;
+    ix->st.last_kprime = 0;
+    int n_main = 0;
+    const size_t ev_tot = 1, ev_main = 3;
+    if (profile) B2F_CUDA(cudaEventRecord(get_event(ix, ev_tot), st));
+
+    if (ix->ntotal == 0) {
+        B2F_TRY(launch_finalize(nullptr, nullptr, nq, 0, k, ix->metric, P.id_offset, nullptr, Dd, Id, st));
+        ix->st.launches++;
+        ix->st.last_launches++;
+    } else if (algo == B2F_ALGO_SCAN) {
+        B2F_TRY(run_scan(ix, qd, nullptr, nq, k, Dd, Id, P.id_offset, bump, st, profile, ev_main, &n_main));
+    } else {
+        const int nq_pad = plan.nq_tiles * 128;
+        ix->st.last_kprime = kp;
+        __nv_bfloat16* qb = bump.take<__nv_bfloat16>((size_t)nq_pad * ix->dpad);
+        float* qnorm = bump.take<float>(nq_pad);
+        float* qerr = bump.take<float>(nq_pad);
+        float* pk = bump.take<float>((size_t)nq_pad * plan.nsplits * kp);
+        int32_t* pi = bump.take<int32_t>((size_t)nq_pad * plan.nsplits * kp);
+        float* ck = bump.take<float>((size_t)nq * kp);
+        int32_t* ci = bump.take<int32_t>((size_t)nq * kp);
+        float* xk = bump.take<float>((size_t)nq * k);
+        int32_t* xi = bump.take<int32_t>((size_t)nq * k);
+        int32_t* fail_list = bump.take<int32_t>(nq);
+        int32_t* fail_count = bump.take<int32_t>(1);
+        B2F_TRY(refresh_host_stats(ix, st));
+        B2F_CUDA(cudaMemsetAsync(fail_count, 0, 4, st));
+        B2F_TRY(launch_prep_queries(qd, nq, nq_pad, ix->d, qb, ix->dpad, qnorm, qerr, st));
+        if (profile) B2F_CUDA(cudaEventRecord(get_event(ix, ev_main), st));
+        B2F_TRY(launch_tensor_scan(ix->scan, ix->dpad, ix->norms, ix->ntotal, ix->metric, qb, nq, nq_pad, plan, pk, pi, st));
+        if (profile) B2F_CUDA(cudaEventRecord(get_event(ix, ev_main + 1), st));
+        n_main = 1;
+        B2F_TRY(launch_merge_parts(pk, pi, nq, plan.nsplits, kp, kp, ck, ci, st));
+        RerankArgs ra{};
+        ra.rows_f32 = ix->storage == B2F_STORE_F32 ? ix->rows_f32 : nullptr;
+        ra.rows_bf16 = ix->scan;
+        ra.pitch_bf16 = ix->dpad;
+        ra.q = qd;
+        ra.qnorm = qnorm;
+        ra.qerr = qerr;
+        ra.cand_key = ck;
+        ra.cand_id = ci;
+        ra.nq = nq;
+        ra.kp = kp;
+        ra.k = k;
+        ra.d = ix->d;
+        ra.metric = ix->metric;
+        ra.ntotal = ix->ntotal;
+        ra.max_row_norm = sqrtf(ix->host_stats[0]);
+        ra.max_row_err = ix->storage == B2F_STORE_F32 ? sqrtf(ix->host_stats[1]) : 0.f;
+        ra.certify = certify;
+        ra.out_key = xk;
+        ra.out_id = xi;
+        ra.fail_list = fail_list;
+        ra.fail_count = fail_count;
+        B2F_TRY(launch_rerank(ra, st));
+        B2F_TRY(launch_finalize(xk, xi, nq, k, k, ix->metric, P.id_offset, nullptr, Dd, Id, st));
+        ix->st.launches += 5;
+        ix->st.last_launches += 5;
+        if (certify) {
+            B2F_TRY(ensure_pinned(ix, 4096));
+            int32_t* hcount = reinterpret_cast<int32_t*>(ix->pinned);
+            B2F_CUDA(cudaMemcpyAsync(hcount, fail_count, 4, cudaMemcpyDeviceToHost, st));
+            B2F_CUDA(cudaStreamSynchronize(st));
+            const int nfail = *hcount;
+            if (nfail > 0) {
+                ix->st.fallback_queries += nfail;
+                int dummy = 0;
+                B2F_TRY(run_scan(ix, qd, fail_list, nfail, k, Dd, Id, P.id_offset, bump, st, false, 0, &dummy));
+            }
+        }
+    }
+    if (profile) B2F_CUDA(cudaEventRecord(get_event(ix, ev_tot + 1), st));
+    if (host) {
+        B2F_CUDA(cudaMemcpyAsync(D, Dd, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, st));
+        B2F_CUDA(cudaMemcpyAsync(I, Id, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, st));
+        B2F_CUDA(cudaStreamSynchronize(st));
+    }
+    if (profile) {
+        B2F_CUDA(cudaEventSynchronize(get_event(ix, ev_tot + 1)));
+        float ms = 0.f, tot = 0.f;
+        for (int i = 0; i < n_main; i++) {
+            float t = 0.f;
+            B2F_CUDA(cudaEventElapsedTime(&t, get_event(ix, ev_main + 2 * (size_t)i), get_event(ix, ev_main + 2 * (size_t)i + 1)));
+            ms += t;
+        }
+        B2F_CUDA(cudaEventElapsedTime(&tot, get_event(ix, ev_tot), get_event(ix, ev_tot + 1)));
+        ix->st.last_main_ms = ms;
+        ix->st.last_total_ms = tot;
+        ix->st.last_main_launches = n_main;
+    }
+    return B2F_OK;
+}
+
+int b2f_index_reconstruct(b2f_index* ix, int64_t i0, int64_t n, float* out, int32_t mem, void* stream) {
+    if (!ix || !out || n < 0) {
+        set_error("reconstruct: bad arguments");
+        return B2F_EINVAL;
+    }
+    if (i0 < 0 || i0 + n > ix->ntotal) {
+        set_error("reconstruct: rows [%lld, %lld) out of range [0, %lld)", (long long)i0, (long long)(i0 + n), (long long)ix->ntotal);
+        return B2F_ERANGE;
+    }
+    if (n == 0) return B2F_OK;
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    cudaStream_t st = stream ? (cudaStream_t)stream : ix->stream;
+    B2F_TRY(order_after(st, ix->stream, ix));
+    const size_t bytes = (size_t)n * ix->d * 4;
+    if (ix->storage == B2F_STORE_F32) {
+        B2F_CUDA(cudaMemcpyAsync(out, ix->rows_f32 + i0 * ix->d, bytes, mem == B2F_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
+    } else if (mem == B2F_MEM_DEVICE) {
+        B2F_TRY(launch_bf16_to_f32(ix->scan + i0 * ix->dpad, ix->dpad, n, ix->d, out, st));
+        ix->st.launches++;
+    } else {
+        B2F_TRY(ensure_ws(ix, bytes + 4096));
+        B2F_TRY(launch_bf16_to_f32(ix->scan + i0 * ix->dpad, ix->dpad, n, ix->d, reinterpret_cast<float*>(ix->ws), st));
+        ix->st.launches++;
+        B2F_CUDA(cudaMemcpyAsync(out, ix->ws, bytes, cudaMemcpyDeviceToHost, st));
+    }
+    if (mem == B2F_MEM_HOST) B2F_CUDA(cudaStreamSynchronize(st));
+    return B2F_OK;
+}
+
+// ---- file I/O (FAISS IndexFlat layout; see include/b200flat.h) --------------------------------------
+static const size_t kIoChunk = 32u << 20;
+
+int b2f_index_write(b2f_index* ix, const char* path) {
+    if (!ix || !path) {
+        set_error("write: bad arguments");
+        return B2F_EINVAL;
+    }
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    FILE* f = fopen(path, "wb");
+    if (!f) {
+        set_error("could not open %s for writing", path);
+        return B2F_EIO;
+    }
+    const char* cc = ix->metric == B2F_METRIC_L2 ? "IxF2" : "IxFI";
+    const int32_t d32 = ix->d, mt = ix->metric;
+    const int64_t nt = ix->ntotal, dummy = 1 << 20;
+    const uint8_t tr = 1;
+    const uint64_t sz = (uint64_t)ix->ntotal * ix->d;
+    bool ok = fwrite(cc, 1, 4, f) == 4 && fwrite(&d32, 4, 1, f) == 1 && fwrite(&nt, 8, 1, f) == 1 &&
+              fwrite(&dummy, 8, 1, f) == 1 && fwrite(&dummy, 8, 1, f) == 1 && fwrite(&tr, 1, 1, f) == 1 &&
+              fwrite(&mt, 4, 1, f) == 1 && fwrite(&sz, 8, 1, f) == 1;
+    int rc = B2F_OK;
+    if (ok && ix->ntotal > 0) {
+        const int64_t rows_per = (int64_t)(kIoChunk / ((size_t)ix->d * 4)) > 0 ? (int64_t)(kIoChunk / ((size_t)ix->d * 4)) : 1;
+        const size_t cbytes = (size_t)rows_per * ix->d * 4;
+        rc = ensure_pinned(ix, 2 * cbytes);
+        if (rc == B2F_OK && ix->storage == B2F_STORE_BF16) rc = ensure_ws(ix, 2 * cbytes + 4096);
+        cudaEvent_t evs[2] = {get_event(ix, 1), get_event(ix, 2)};
+        int64_t pending_rows[2] = {0, 0};
+        int slot = 0;
+        // double-buffered: D2H of chunk i+1 overlaps fwrite of chunk i
+        for (int64_t r0 = 0; rc == B2F_OK && ok && r0 < ix->ntotal + rows_per; r0 += rows_per, slot ^= 1) {
+            if (r0 < ix->ntotal) {
+                const int64_t m = ix->ntotal - r0 < rows_per ? ix->ntotal - r0 : rows_per;
+                char* hbuf = ix->pinned + (size_t)slot * cbytes;
+                cudaError_t e;
+                if (ix->storage == B2F_STORE_F32) {
+                    e = cudaMemcpyAsync(hbuf, ix->rows_f32 + r0 * ix->d, (size_t)m * ix->d * 4, cudaMemcpyDeviceToHost, ix->stream);
+                } else {
+                    float* dbuf = reinterpret_cast<float*>(ix->ws + (size_t)slot * cbytes);
+                    rc = launch_bf16_to_f32(ix->scan + r0 * ix->dpad, ix->dpad, m, ix->d, dbuf, ix->stream);
+                    ix->st.launches++;
+                    e = cudaMemcpyAsync(hbuf, dbuf, (size_t)m * ix->d * 4, cudaMemcpyDeviceToHost, ix->stream);
+                }
+                if (e == cudaSuccess) e = cudaEventRecord(evs[slot], ix->stream);
+                if (e != cudaSuccess) {
+                    set_error("write: device read failed: %s", cudaGetErrorString(e));
+                    rc = B2F_ECUDA;
+                }
+                pending_rows[slot] = m;
+            } else {
+                pending_rows[slot] = 0;
+            }
+            const int prev = slot ^ 1;
+            if (rc == B2F_OK && r0 > 0 && pending_rows[prev] > 0) {
+                if (cudaEventSynchronize(evs[prev]) != cudaSuccess) {
+                    set_error("write: event sync failed");
+                    rc = B2F_ECUDA;
+                } else {
+                    const size_t cnt = (size_t)pending_rows[prev] * ix->d;
+                    ok = fwrite(ix->pinned + (size_t)prev * cbytes, 4, cnt, f) == cnt;
+                    pending_rows[prev] = 0;
+                }
+            }
+        }
+    }
+    if (fclose(f) != 0) ok = false;
+    if (rc != B2F_OK) return rc;
+    if (!ok) {
+        set_error("short write to %s", path);
+        return B2F_EIO;
+    }
+    return B2F_OK;
+}
+
+int b2f_index_read(const char* path, int32_t storage, int32_t device, b2f_index** out) {
+    if (!path || !out) {
+        set_error("read: bad arguments");
+        return B2F_EINVAL;
+    }
+    *out = nullptr;
+    FILE* f = fopen(path, "rb");
+    if (!f) {
+        set_error("could not open %s for reading", path);
+        return B2F_EIO;
+    }
+    char cc[4];
+    int32_t d32 = 0, mt = 0;
+    int64_t nt = 0, dm[2];
+    uint8_t tr = 0;
+    uint64_t sz = 0;
+    bool ok = fread(cc, 1, 4, f) == 4;
+    if (ok && memcmp(cc, "IxF2", 4) != 0 && memcmp(cc, "IxFI", 4) != 0 && memcmp(cc, "IxFl", 4) != 0) {
+        fclose(f);
+        set_error("%s is not an IndexFlat file (fourcc %.4s)", path, cc);
+        return B2F_EFORMAT;
+    }
+    ok = ok && fread(&d32, 4, 1, f) == 1 && fread(&nt, 8, 1, f) == 1 && fread(dm, 8, 2, f) == 2 &&
+         fread(&tr, 1, 1, f) == 1 && fread(&mt, 4, 1, f) == 1;
+    if (ok && mt > 1) {
+        float arg;
+        ok = fread(&arg, 4, 1, f) == 1;
+    }
+    ok = ok && fread(&sz, 8, 1, f) == 1;
+    if (!ok || d32 <= 0 || nt < 0 || sz != (uint64_t)nt * (uint64_t)d32) {
+        fclose(f);
+        set_error("%s: truncated or inconsistent IndexFlat header", path);
+        return B2F_EFORMAT;
+    }
+    if (mt != B2F_METRIC_L2 && mt != B2F_METRIC_INNER_PRODUCT) {
+        fclose(f);
+        set_error("%s: metric_type %d is not supported (only L2 and inner product)", path, mt);
+        return B2F_EFORMAT;
+    }
+    b2f_index* ix = nullptr;
+    int rc = b2f_index_create(d32, mt, storage, device, &ix);
+    if (rc != B2F_OK) {
+        fclose(f);
+        return rc;
+    }
+    {
+        DeviceGuard g(device);
+        rc = ensure_capacity(ix, nt);
+        const int64_t rows_per = (int64_t)(kIoChunk / ((size_t)d32 * 4)) > 0 ? (int64_t)(kIoChunk / ((size_t)d32 * 4)) : 1;
+        const size_t cbytes = (size_t)rows_per * d32 * 4;
+        if (rc == B2F_OK && nt > 0) rc = ensure_pinned(ix, 2 * cbytes);
+        if (rc == B2F_OK && nt > 0 && storage == B2F_STORE_BF16) rc = ensure_ws(ix, 2 * cbytes + 4096);
+        cudaEvent_t evs[2] = {get_event(ix, 1), get_event(ix, 2)};
+        bool used[2] = {false, false};
+        int slot = 0;
+        // double-buffered: fread of chunk i+1 overlaps H2D + ingest of chunk i
+        for (int64_t r0 = 0; rc == B2F_OK && r0 < nt; r0 += rows_per, slot ^= 1) {
+            const int64_t m = nt - r0 < rows_per ? nt - r0 : rows_per;
+            char* hbuf = ix->pinned + (size_t)slot * cbytes;
+            if (used[slot] && cudaEventSynchronize(evs[slot]) != cudaSuccess) {
+                set_error("read: event sync failed");
+                rc = B2F_ECUDA;
+                break;
+            }
+            const size_t cnt = (size_t)m * d32;
+            if (fread(hbuf, 4, cnt, f) != cnt) {
+                set_error("%s: truncated payload", path);
+                rc = B2F_EFORMAT;
+                break;
+            }
+            cudaError_t e;
+            const float* src;
+            if (storage == B2F_STORE_F32) {
+                float* dst = ix->rows_f32 + ix->ntotal * d32;
+                e = cudaMemcpyAsync(dst, hbuf, cnt * 4, cudaMemcpyHostToDevice, ix->stream);
+                src = dst;
+            } else {
+                float* dbuf = reinterpret_cast<float*>(ix->ws + (size_t)slot * cbytes);
+                e = cudaMemcpyAsync(dbuf, hbuf, cnt * 4, cudaMemcpyHostToDevice, ix->stream);
+                src = dbuf;
+            }
+            if (e != cudaSuccess) {
+                set_error("read: H2D failed: %s", cudaGetErrorString(e));
+                rc = B2F_ECUDA;
+                break;
+            }
+            rc = add_device_rows(ix, src, m, ix->stream);
+            if (rc != B2F_OK) break;
+            cudaEventRecord(evs[slot], ix->stream);
+            used[slot] = true;
+            ix->ntotal += m;
+        }
+        if (rc == B2F_OK && cudaStreamSynchronize(ix->stream) != cudaSuccess) {
+            set_error("read: stream sync failed");
+            rc = B2F_ECUDA;
+        }
+        ix->stats_dirty = true;
+    }
+    fclose(f);
+    if (rc != B2F_OK) {
+        b2f_index_destroy(ix);
+        return rc;
+    }
+    *out = ix;
+    return B2F_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,266 @@
+// ingest.cu -- K5 (add: fp32 rows -> authoritative rows + bf16 scan copy + norms, one pass),
+// K7 (fused encoder epilogue: CLS / masked-mean pool, optional L2 normalise, written straight into
+// index storage), query preparation for the tensor path, and the synthetic-row generator.
+// All HBM-bound elementwise / row-reduction work: one warp (or CTA) per row, 16-byte accesses.
+#include "common.cuh"
+
+namespace b2f {
+
+// Non-negative floats order like their bit patterns, so integer atomicMax works.
+__device__ __forceinline__ void atomic_max_nonneg(float* addr, float v) {
+    atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) v += __shfl_xor_sync(kFull, v, s);
+    return v;
+}
+
+// Writes one element group of a row to every derived store and returns (bf16(x)^2, (x-bf16(x))^2).
+__device__ __forceinline__ void emit_elem(float x, int64_t row, int col, int d, float* rows_f32,
+                                          __nv_bfloat16* scan, int64_t dpad, float& nn, float& ee) {
+    if (rows_f32) rows_f32[row * d + col] = x;
+    const __nv_bfloat16 b = __float2bfloat16_rn(x);
+    const float xb = __bfloat162float(b);
+    if (scan) scan[row * dpad + col] = b;
+    nn = fmaf(xb, xb, nn);
+    const float e = x - xb;
+    ee = fmaf(e, e, ee);
+}
+
+// stats[0] = max |bf16(x)|^2, stats[1] = max |x - bf16(x)|^2 over every row ever ingested
+__global__ void __launch_bounds__(256)
+ingest_kernel(const float* __restrict__ src, int64_t n, int d, float* __restrict__ rows_f32,
+              __nv_bfloat16* __restrict__ scan, int64_t dpad, float* __restrict__ norms, float* __restrict__ stats) {
+    const int lane = threadIdx.x & 31;
+    const int64_t wpg = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < n; row += wpg) {
+        float nn = 0.f, ee = 0.f;
+        if ((d & 3) == 0) {
+            for (int c = lane * 4; c < d; c += 128) {
+                const float4 x = ldg_stream(reinterpret_cast<const float4*>(src + row * d + c));
+                if (rows_f32) *reinterpret_cast<float4*>(rows_f32 + row * d + c) = x;
+                const __nv_bfloat162 lo = __floats2bfloat162_rn(x.x, x.y), hi = __floats2bfloat162_rn(x.z, x.w);
+                if (scan) {
+                    uint2 pk;
+                    pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+                    pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+                    *reinterpret_cast<uint2*>(scan + row * dpad + c) = pk;
+                }
+                const float b0 = __low2float(lo), b1 = __high2float(lo), b2 = __low2float(hi), b3 = __high2float(hi);
+                nn = fmaf(b0, b0, nn); nn = fmaf(b1, b1, nn); nn = fmaf(b2, b2, nn); nn = fmaf(b3, b3, nn);
+                const float e0 = x.x - b0, e1 = x.y - b1, e2 = x.z - b2, e3 = x.w - b3;
+                ee = fmaf(e0, e0, ee); ee = fmaf(e1, e1, ee); ee = fmaf(e2, e2, ee); ee = fmaf(e3, e3, ee);
+            }
+        } else {
+            for (int c = lane; c < d; c += 32) emit_elem(src[row * d + c], row, c, d, rows_f32, scan, dpad, nn, ee);
+        }
+        if (scan)
+            for (int c = d + lane; c < dpad; c += 32) scan[row * dpad + c] = __float2bfloat16_rn(0.f);
+        nn = warp_sum(nn);
+        ee = warp_sum(ee);
+        if (lane == 0) {
+            if (norms) norms[row] = nn;
+            if (stats) {
+                atomic_max_nonneg(stats, nn);
+                atomic_max_nonneg(stats + 1, ee);
+            }
+        }
+    }
+}
+
+int launch_ingest(const float* src, int64_t n, int d, float* rows_f32, __nv_bfloat16* scan, int64_t dpad, float* norms,
+                  float* stats, cudaStream_t st) {
+    if (n <= 0) return B2F_OK;
+    const int wpb = 8;
+    int64_t blocks = (n + wpb - 1) / wpb;
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    ingest_kernel<<<(unsigned)blocks, wpb * 32, 0, st>>>(src, n, d, rows_f32, scan, dpad, norms, stats);
+    B2F_CUDA(cudaGetLastError());
+    return B2F_OK;
+}
+
+// K7.  One CTA per sequence.  hidden [B,T,d] fp32, mask [B,T] int64 (may be null = all ones).
+// CLS: row = hidden[b,0,:] (vectorization.py:44).  MEAN: sum_t mask*h / max(sum_t mask, 1e-9).
+// normalize: row /= max(|row|, 1e-12).  The result goes to out_f32 [B,d] (index rows or a plain
+// output) and, when given, the bf16 scan copy / norms / stats of the index -- no host bounce.
+__global__ void __launch_bounds__(256)
+pool_kernel(const float* __restrict__ hidden, const int64_t* __restrict__ mask, int64_t T, int d, int pool, int normalize,
+            float* __restrict__ out_f32, __nv_bfloat16* __restrict__ scan, int64_t dpad, float* __restrict__ norms,
+            float* __restrict__ stats) {
+    extern __shared__ float srow[];  // [d]
+    __shared__ float red[3][8];
+    const int64_t b = blockIdx.x;
+    const float* h = hidden + b * T * d;
+    float cnt = 1.f;
+    if (pool == B2F_POOL_MEAN) {
+        float c = 0.f;
+        for (int64_t t = 0; t < T; t++) c += mask ? (float)mask[b * T + t] : 1.f;  // uniform, L1-broadcast
+        cnt = fmaxf(c, 1e-9f);
+    }
+    float ss = 0.f;
+    for (int c = threadIdx.x; c < d; c += blockDim.x) {
+        float v;
+        if (pool == B2F_POOL_CLS) {
+            v = h[c];
+        } else {
+            float acc = 0.f;
+            for (int64_t t = 0; t < T; t++) {
+                const float m = mask ? (float)mask[b * T + t] : 1.f;
+                if (m != 0.f) acc = fmaf(m, h[t * d + c], acc);
+            }
+            v = acc / cnt;
+        }
+        srow[c] = v;
+        ss = fmaf(v, v, ss);
+    }
+    ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) red[0][threadIdx.x >> 5] = ss;
+    __syncthreads();
+    float tot = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) tot += red[0][w];
+    const float scale = normalize ? 1.f / fmaxf(sqrtf(tot), 1e-12f) : 1.f;
+    float nn = 0.f, ee = 0.f;
+    for (int c = threadIdx.x; c < d; c += blockDim.x) emit_elem(srow[c] * scale, b, c, d, out_f32, scan, dpad, nn, ee);
+    if (scan)
+        for (int c = d + threadIdx.x; c < dpad; c += blockDim.x) scan[b * dpad + c] = __float2bfloat16_rn(0.f);
+    nn = warp_sum(nn);
+    ee = warp_sum(ee);
+    if ((threadIdx.x & 31) == 0) {
+        red[1][threadIdx.x >> 5] = nn;
+        red[2][threadIdx.x >> 5] = ee;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float n2 = 0.f, e2 = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) { n2 += red[1][w]; e2 += red[2][w]; }
+        if (norms) norms[b] = n2;
+        if (stats) {
+            atomic_max_nonneg(stats, n2);
+            atomic_max_nonneg(stats + 1, e2);
+        }
+    }
+}
+
+int launch_pool(const float* hidden, const int64_t* mask, int64_t B, int64_t T, int d, int pool, int normalize,
+                float* out_f32, __nv_bfloat16* scan, int64_t dpad, float* norms, float* stats, cudaStream_t st) {
+    if (B <= 0) return B2F_OK;
+    if (T <= 0 || (pool != B2F_POOL_CLS && pool != B2F_POOL_MEAN)) {
+        set_error("pool: bad T=%lld or pool mode %d", (long long)T, pool);
+        return B2F_EINVAL;
+    }
+    if ((size_t)d * 4 > 48 * 1024) {
+        set_error("pool: d=%d too large", d);
+        return B2F_EINVAL;
+    }
+    pool_kernel<<<(unsigned)B, 256, (size_t)d * 4, st>>>(hidden, mask, T, d, pool, normalize, out_f32, scan, dpad, norms, stats);
+    B2F_CUDA(cudaGetLastError());
+    return B2F_OK;
+}
+
+// ---- synthetic rows: bit-identical twin of oracle/flat_oracle.c orc_synth_rows ---------------------
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+    z ^= z >> 30; z *= 0xbf58476d1ce4e5b9ULL;
+    z ^= z >> 27; z *= 0x94d049bb133111ebULL;
+    z ^= z >> 31; return z;
+}
+__device__ __forceinline__ int32_t synth_int(uint64_t seed, uint64_t idx) {
+    const uint64_t a = mix64(seed + 0x9E3779B97F4A7C15ULL * (2 * idx + 1));
+    const uint64_t b = mix64(a ^ 0xD1B54A32D192ED03ULL);
+    const uint64_t c = mix64(b + idx);
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        s += (uint32_t)((a >> (16 * i)) & 0xffff);
+        s += (uint32_t)((b >> (16 * i)) & 0xffff);
+        s += (uint32_t)((c >> (16 * i)) & 0xffff);
+    }
+    return (int32_t)s - 393210;
+}
+
+__global__ void __launch_bounds__(256)
+synth_kernel(uint64_t seed, int64_t row0, int64_t nrows, int d, int normalize, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t wpg = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < nrows; r += wpg) {
+        const uint64_t base = (uint64_t)(row0 + r) * (uint64_t)d;
+        if (!normalize) {
+            for (int c = lane; c < d; c += 32) out[r * d + c] = (float)synth_int(seed, base + c) * (1.0f / 65536.0f);
+        } else {
+            long long ss = 0;
+            for (int c = lane; c < d; c += 32) {
+                const long long v = synth_int(seed, base + c);
+                ss += v * v;
+            }
+#pragma unroll
+            for (int s = 16; s >= 1; s >>= 1) ss += __shfl_xor_sync(kFull, ss, s);
+            const double nrm = sqrt((double)ss);
+            for (int c = lane; c < d; c += 32) {
+                const double v = (double)synth_int(seed, base + c);
+                out[r * d + c] = ss > 0 ? (float)(v / nrm) : 0.f;
+            }
+        }
+    }
+}
+
+int launch_synth(uint64_t seed, int64_t row0, int64_t nrows, int d, int normalize, float* out, cudaStream_t st) {
+    if (nrows <= 0) return B2F_OK;
+    int64_t blocks = (nrows + 7) / 8;
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    synth_kernel<<<(unsigned)blocks, 256, 0, st>>>(seed, row0, nrows, d, normalize, out);
+    B2F_CUDA(cudaGetLastError());
+    return B2F_OK;
+}
+
+// ---- query preparation for the tensor path -------------------------------------------------------
+// qb: [nq_pad, dpad] bf16 (zero padded), qnorm[r] = |bf16(q_r)|^2, qerr[r] = |q_r - bf16(q_r)|
+__global__ void __launch_bounds__(256)
+prep_queries_kernel(const float* __restrict__ q, int nq, int nq_pad, int d, __nv_bfloat16* __restrict__ qb, int64_t dpad,
+                    float* __restrict__ qnorm, float* __restrict__ qerr) {
+    const int lane = threadIdx.x & 31;
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= nq_pad) return;
+    float nn = 0.f, ee = 0.f;
+    for (int c = lane; c < dpad; c += 32) {
+        float x = (r < nq && c < d) ? q[(int64_t)r * d + c] : 0.f;
+        const __nv_bfloat16 b = __float2bfloat16_rn(x);
+        const float xb = __bfloat162float(b);
+        qb[(int64_t)r * dpad + c] = b;
+        nn = fmaf(xb, xb, nn);
+        ee = fmaf(x - xb, x - xb, ee);
+    }
+    nn = warp_sum(nn);
+    ee = warp_sum(ee);
+    if (lane == 0 && r < nq) {
+        qnorm[r] = nn;
+        qerr[r] = sqrtf(ee);
+    }
+}
+
+int launch_prep_queries(const float* q, int nq, int nq_pad, int d, __nv_bfloat16* qb, int64_t dpad, float* qnorm,
+                        float* qerr, cudaStream_t st) {
+    if (nq_pad <= 0) return B2F_OK;
+    prep_queries_kernel<<<(nq_pad + 7) / 8, 256, 0, st>>>(q, nq, nq_pad, d, qb, dpad, qnorm, qerr);
+    B2F_CUDA(cudaGetLastError());
+    return B2F_OK;
+}
+
+__global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ src, int64_t pitch, int64_t n, int d,
+                                   float* __restrict__ dst) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * d) return;
+    const int64_t r = t / d;
+    const int c = (int)(t - r * d);
+    dst[t] = __bfloat162float(src[r * pitch + c]);
+}
+
+int launch_bf16_to_f32(const __nv_bfloat16* src, int64_t pitch, int64_t n, int d, float* dst, cudaStream_t st) {
+    const int64_t total = n * d;
+    if (total <= 0) return B2F_OK;
+    bf16_to_f32_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, pitch, n, d, dst);
+    B2F_CUDA(cudaGetLastError());
+    return B2F_OK;
+}
+
+}  // namespace b2f

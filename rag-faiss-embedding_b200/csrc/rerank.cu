@@ -1,0 +1,132 @@
+// rerank.cu -- K4: exact fp32 re-rank of the tensor path's coarse candidates + certification.
+//
+// The tcgen05 pass ranks rows by a bf16-rounded, expanded-form key.  Here every candidate's distance
+// is recomputed the way the reference computes it (fp32, exact-difference form for L2 -- faiss
+// fvec_L2sqr; fp32 dot product for IP), the k' candidates are re-sorted by (distance, id) and the
+// best k are emitted.  A query is *certified* when the rounding-error bound proves that no row
+// outside its candidate list can beat its k-th result; uncertified queries are listed for the exact
+// streaming scan (K1), so the final answer never depends on bf16.
+//
+// Bound (L2).  x~, q~ = bf16-rounded row / query, e_x = |x - x~| <= E, e_q = |q - q~|.
+//   coarse c(x) = |q~|^2 + |x~|^2 - 2 <q~,x~> + nu,  |nu| <= NU (fp32 accumulation noise)
+//   every non-candidate has c(x) >= c_k'  (the k'-th smallest coarse value)
+//   sqrt(dist(q,x)) = |q - x| >= |q~ - x~| - e_q - e_x >= sqrt(max(c_k' - NU, 0)) - e_q - E =: L
+//   certified  <=>  L > 0 and L^2 > tau_k  (tau_k = exact k-th best distance among the candidates)
+// Bound (IP).  <q,x> <= <q~,x~> + |q| e_x + |x~| e_q  ->  U = s_k' + NU + |q| E + Xmax e_q;
+//   certified  <=>  U < tau_k (k-th largest exact inner product).
+#include "common.cuh"
+
+namespace b2f {
+
+constexpr int kRerankThreads = 128;
+
+__global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    float* ek = smem;                                        // [kp] exact keys
+    int32_t* ei = reinterpret_cast<int32_t*>(smem + a.kp);  // [kp]
+    __shared__ float s_tau;
+    __shared__ int s_nvalid;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q = blockIdx.x;
+    const float* qv = a.q + (int64_t)q * a.d;
+    const bool l2 = a.metric == B2F_METRIC_L2;
+    if (threadIdx.x == 0) {
+        s_tau = FLT_MAX;
+        s_nvalid = 0;
+    }
+    __syncthreads();
+    for (int c = warp; c < a.kp; c += kRerankThreads / 32) {
+        const int32_t id = a.cand_id[(int64_t)q * a.kp + c];
+        float acc = 0.f;
+        if (id >= 0) {
+            if (a.rows_f32) {
+                const float* x = a.rows_f32 + (int64_t)id * a.d;
+                for (int j = lane; j < a.d; j += 32) {
+                    if (l2) {
+                        const float t = x[j] - qv[j];
+                        acc = fmaf(t, t, acc);
+                    } else {
+                        acc = fmaf(x[j], qv[j], acc);
+                    }
+                }
+            } else {
+                const __nv_bfloat16* x = a.rows_bf16 + (int64_t)id * a.pitch_bf16;
+                for (int j = lane; j < a.d; j += 32) {
+                    const float xv = __bfloat162float(x[j]);
+                    if (l2) {
+                        const float t = xv - qv[j];
+                        acc = fmaf(t, t, acc);
+                    } else {
+                        acc = fmaf(xv, qv[j], acc);
+                    }
+                }
+            }
+#pragma unroll
+            for (int s = 16; s >= 1; s >>= 1) acc += __shfl_xor_sync(kFull, acc, s);
+        }
+        if (lane == 0) {
+            const bool ok = id >= 0 && !(acc != acc);  // NaN never enters (faiss heap semantics)
+            ek[c] = ok ? (l2 ? acc : -acc) : FLT_MAX;
+            ei[c] = ok ? id : -1;
+            if (id >= 0) atomicAdd(&s_nvalid, 1);
+        }
+    }
+    __syncthreads();
+    // rank sort by (key, id, slot); ranks are a permutation of [0, kp)
+    for (int t = threadIdx.x; t < a.kp; t += kRerankThreads) {
+        const float mk = ek[t];
+        const int32_t mi = ei[t];
+        int rank = 0;
+        for (int j = 0; j < a.kp; j++) {
+            const float ok_ = ek[j];
+            const int32_t oi_ = ei[j];
+            rank += (cand_less(ok_, oi_, mk, mi) || (ok_ == mk && oi_ == mi && j < t)) ? 1 : 0;
+        }
+        if (rank < a.k) {
+            a.out_key[(int64_t)q * a.k + rank] = mk;
+            a.out_id[(int64_t)q * a.k + rank] = mi;
+        }
+        if (rank == a.k - 1) s_tau = mk;
+    }
+    // kp < k cannot happen (host guarantees kp >= k)
+    __syncthreads();
+    if (threadIdx.x == 0 && a.certify) {
+        bool certified;
+        if (s_nvalid < a.kp) {
+            certified = true;  // every row of the index is already a candidate
+        } else {
+            const float tau = s_tau;                               // exact k-th best key
+            const float ckp = a.cand_key[(int64_t)q * a.kp + a.kp - 1];  // k'-th coarse key (without |q~|^2)
+            const float qn2 = a.qnorm[q];
+            const float qn = sqrtf(qn2);
+            const float eq = a.qerr[q];
+            const float nu = 4.f * (float)(a.d + 16) * 1.1920929e-7f * (qn * a.max_row_norm + qn2 + a.max_row_norm * a.max_row_norm);
+            if (l2) {
+                const float c = ckp + qn2 - nu;
+                const float L = sqrtf(fmaxf(c, 0.f)) - eq - a.max_row_err;
+                certified = L > 0.f && L * L * (1.f - 4e-7f) > tau;
+            } else {
+                // keys are negated inner products: non-candidates have <q,x> <= -ckp + slack
+                const float U = -ckp + nu + (qn + eq) * a.max_row_err + a.max_row_norm * eq;
+                certified = U < -tau;
+            }
+        }
+        if (!certified) {
+            const int slot = atomicAdd(a.fail_count, 1);
+            a.fail_list[slot] = q;
+        }
+    }
+}
+
+int launch_rerank(const RerankArgs& a, cudaStream_t st) {
+    if (a.nq <= 0) return B2F_OK;
+    if (a.kp < a.k) {
+        set_error("rerank: kp %d < k %d", a.kp, a.k);
+        return B2F_EINVAL;
+    }
+    rerank_kernel<<<a.nq, kRerankThreads, (size_t)a.kp * 8, st>>>(a);
+    B2F_CUDA(cudaGetLastError());
+    return B2F_OK;
+}
+
+}  // namespace b2f

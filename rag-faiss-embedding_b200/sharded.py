@@ -1,0 +1,176 @@
+"""Row-sharded exact search across the GPUs of one box (BASELINE config 4).
+
+One process per GPU (torch.distributed, NCCL over NVLink).  Every rank holds a contiguous range of
+the database rows in its own single-GPU IndexFlat; queries are replicated; each rank searches its
+shard (global label = shard offset + local row), the per-rank (distance, label)[nq, k] lists are
+exchanged with ONE all-gather and merged on every rank by the CUDA merge kernel (b2f_merge_topk).
+Exact top-k over a partition = merge of per-part exact top-k, so results equal the single-GPU index.
+
+The reference has no multi-process code; its file order / .mapping list stay valid because global
+labels are plain row numbers of the concatenated database.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Callable, List, Optional, Tuple
+
+import numpy as np
+
+from . import _capi as C
+from .index import METRIC_L2, IndexFlat
+
+
+def partition_rows(n: int, world: int) -> List[Tuple[int, int]]:
+    """Contiguous ranges [start, stop) per rank: rank r gets rows [r*ceil(n/G), min(n, (r+1)*ceil(n/G)))."""
+    per = -(-n // world) if n > 0 else 0
+    return [(min(n, r * per), min(n, (r + 1) * per)) for r in range(world)]
+
+
+class SegmentMap:
+    """local row -> global label for a shard filled by several add() calls (piecewise offsets)."""
+
+    def __init__(self):
+        self.local_starts: List[int] = []
+        self.global_starts: List[int] = []
+        self.nlocal = 0
+
+    def append(self, global_start: int, count: int):
+        if count <= 0:
+            return
+        if self.local_starts and self.global_starts[-1] + (self.nlocal - self.local_starts[-1]) == global_start:
+            self.nlocal += count  # contiguous with the previous segment
+            return
+        self.local_starts.append(self.nlocal)
+        self.global_starts.append(global_start)
+        self.nlocal += count
+
+    def single_offset(self) -> Optional[int]:
+        if not self.local_starts:
+            return 0
+        return self.global_starts[0] if len(self.local_starts) == 1 else None
+
+    def to_global_numpy(self, local_ids: np.ndarray) -> np.ndarray:
+        out = local_ids.astype(np.int64, copy=True)
+        if not self.local_starts:
+            return out
+        ls = np.asarray(self.local_starts, np.int64)
+        gs = np.asarray(self.global_starts, np.int64)
+        valid = out >= 0
+        seg = np.searchsorted(ls, out[valid], side="right") - 1
+        out[valid] = out[valid] - ls[seg] + gs[seg]
+        return out
+
+    def to_global_torch(self, local_ids):
+        import torch
+
+        if not self.local_starts:
+            return local_ids
+        ls = torch.tensor(self.local_starts, dtype=torch.int64, device=local_ids.device)
+        gs = torch.tensor(self.global_starts, dtype=torch.int64, device=local_ids.device)
+        seg = (torch.bucketize(local_ids.clamp(min=0), ls, right=True) - 1).clamp(min=0)
+        return torch.where(local_ids >= 0, local_ids - ls[seg] + gs[seg], local_ids)
+
+
+def merge_topk(metric: int, D_parts, I_parts):
+    """[G, nq, k] per-shard results (CUDA tensors) -> merged [nq, k] via the CUDA merge kernel."""
+    import torch
+
+    G, nq, k = D_parts.shape
+    D_parts = D_parts.contiguous()
+    I_parts = I_parts.contiguous()
+    D = torch.empty((nq, k), dtype=torch.float32, device=D_parts.device)
+    I = torch.empty((nq, k), dtype=torch.int64, device=D_parts.device)
+    stream = int(torch.cuda.current_stream(D_parts.device).cuda_stream)
+    C.check(C.load().b2f_merge_topk(int(metric), nq, k, G, D_parts.data_ptr(), I_parts.data_ptr(), D.data_ptr(),
+                                    I.data_ptr(), D_parts.device.index or 0, ctypes.c_void_p(stream)))
+    return D, I
+
+
+class ShardedIndexFlat:
+    """IndexFlat surface over a torch.distributed process group, one shard per rank.
+
+    `local_index` / `merge_fn` exist so the host logic (partitioning, label mapping, the collective)
+    can be exercised on CPU with the gloo backend in tests; the defaults are the CUDA index and the
+    CUDA merge kernel.
+    """
+
+    def __init__(self, d: int, metric: int = METRIC_L2, *, storage: Optional[int] = None,
+                 device: Optional[int] = None, group=None, local_index=None,
+                 merge_fn: Optional[Callable] = None):
+        import torch.distributed as dist
+
+        self._dist = dist
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.d = d
+        self.metric_type = metric
+        self.local = local_index if local_index is not None else IndexFlat(d, metric, storage=storage, device=device)
+        self._merge = merge_fn if merge_fn is not None else merge_topk
+        self.segments = SegmentMap()
+        self.ntotal = 0
+        self.is_trained = True
+
+    # -- ingest -----------------------------------------------------------------------------------
+    def add(self, x):
+        """x: the same [n, d] array on every rank; each rank keeps its contiguous slice."""
+        n = int(x.shape[0])
+        start, stop = partition_rows(n, self.world)[self.rank]
+        if stop > start:
+            self.local.add(x[start:stop])
+        self.segments.append(self.ntotal + start, stop - start)
+        self.ntotal += n
+
+    def add_local(self, x_local, global_start: int):
+        """This rank's rows only (already partitioned by the caller); labels start at global_start."""
+        self.local.add(x_local)
+        self.segments.append(int(global_start), int(x_local.shape[0]))
+
+    def add_synthetic(self, seed: int, nrows: int, normalize: bool = False):
+        """Every rank generates its slice of the synthetic matrix on its own device."""
+        start, stop = partition_rows(nrows, self.world)[self.rank]
+        if stop > start:
+            self.local.add_synthetic(seed, self.ntotal + start, stop - start, normalize)
+        self.segments.append(self.ntotal + start, stop - start)
+        self.ntotal += nrows
+
+    def set_total(self, ntotal: int):
+        self.ntotal = int(ntotal)
+
+    # -- search -----------------------------------------------------------------------------------
+    def search_local(self, x, k: int):
+        off = self.segments.single_offset()
+        if off is not None and hasattr(self.local, "set_search_params"):
+            self.local.set_search_params(id_offset=off)
+            return self.local.search(x, k)
+        D, I = self.local.search(x, k)
+        if isinstance(I, np.ndarray):
+            return D, self.segments.to_global_numpy(I)
+        return D, self.segments.to_global_torch(I)
+
+    def search(self, x, k: int):
+        """Replicated queries -> identical merged (D, I) on every rank."""
+        D, I = self.search_local(x, k)
+        if self.world == 1:
+            return D, I
+        import torch
+
+        was_numpy = isinstance(D, np.ndarray)
+        if was_numpy:
+            D, I = torch.from_numpy(D), torch.from_numpy(I)
+        nq, kk = D.shape
+        # concatenated-along-dim-0 form ([G*nq, k]) is accepted by both NCCL and gloo
+        Dg = torch.empty((self.world * nq, kk), dtype=D.dtype, device=D.device)
+        Ig = torch.empty((self.world * nq, kk), dtype=I.dtype, device=I.device)
+        # the one exchange step of the path: 12 * nq * k bytes per rank
+        self._dist.all_gather_into_tensor(Dg, D.contiguous(), group=self.group)
+        self._dist.all_gather_into_tensor(Ig, I.contiguous(), group=self.group)
+        Dm, Im = self._merge(self.metric_type, Dg.view(self.world, nq, kk), Ig.view(self.world, nq, kk))
+        if was_numpy and not isinstance(Dm, np.ndarray):
+            Dm, Im = Dm.cpu().numpy(), Im.cpu().numpy()
+        return Dm, Im
+
+    def reset(self):
+        self.local.reset()
+        self.segments = SegmentMap()
+        self.ntotal = 0

@@ -1,0 +1,141 @@
+"""CPU tier: the C-ABI library loads and exports exactly what include/b200flat.h declares; host-side
+logic (partitioning, label mapping, the FAISSVectorStore mirror) behaves like the reference's."""
+import ctypes
+import os
+import pickle
+import re
+
+import numpy as np
+import pytest
+
+import oracle as orc
+from tests.helpers import OracleIndex
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "b200flat.h")).read()
+    return sorted(set(re.findall(r"B2F_API\s+[\w\s\*]+?\b(b2f_\w+)\s*\(", text)))
+
+
+def test_header_symbols_exported_and_bound():
+    from rag_faiss_embedding_b200 import _capi
+
+    lib = _capi.load()
+    declared = _declared_symbols()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in b200flat.h but not exported"
+    assert sorted(_capi.PROTOTYPES) == declared
+    assert lib.b2f_version() == 1
+    assert ctypes.sizeof(_capi.SearchParams) == 32 and ctypes.sizeof(_capi.Stats) == 64
+
+
+def test_no_cpu_fallback_fails_loudly():
+    import rag_faiss_embedding_b200 as m
+
+    if m.device_count() > 0:
+        pytest.skip("a B200 is present; the failure path is for CPU-only boxes")
+    with pytest.raises(m.B200FlatError) as e:
+        m.IndexFlatL2(384)
+    assert e.value.code == -2 and "no CPU path" in str(e.value)
+    with pytest.raises(RuntimeError):
+        m.read_index(os.path.join(ROOT, "tests", "golden", "faiss_index.bin"))
+
+
+def test_faiss_shim_surface():
+    import importlib
+    import sys
+
+    shim = os.path.join(ROOT, "rag-faiss-embedding_b200", "shim")
+    sys.path.insert(0, shim)
+    try:
+        sys.modules.pop("faiss", None)
+        faiss = importlib.import_module("faiss")
+        for name in ("IndexFlatL2", "IndexFlatIP", "IndexFlat", "read_index", "write_index", "METRIC_L2",
+                     "METRIC_INNER_PRODUCT"):
+            assert hasattr(faiss, name)
+        assert faiss.METRIC_L2 == 1 and faiss.METRIC_INNER_PRODUCT == 0
+    finally:
+        sys.path.remove(shim)
+        sys.modules.pop("faiss", None)
+
+
+def test_partition_and_segments():
+    from rag_faiss_embedding_b200.sharded import SegmentMap, partition_rows
+
+    assert partition_rows(10, 4) == [(0, 3), (3, 6), (6, 9), (9, 10)]
+    assert partition_rows(2, 4) == [(0, 1), (1, 2), (2, 2), (2, 2)]
+    assert partition_rows(0, 2) == [(0, 0), (0, 0)]
+    for n in (1, 7, 100, 12345):
+        for w in (1, 2, 4, 8):
+            parts = partition_rows(n, w)
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+    seg = SegmentMap()
+    seg.append(5, 3)      # local 0..2 -> 5..7
+    seg.append(8, 2)      # contiguous: local 3..4 -> 8..9 (same segment)
+    seg.append(100, 4)    # local 5..8 -> 100..103
+    assert seg.single_offset() is None and len(seg.local_starts) == 2
+    got = seg.to_global_numpy(np.array([[0, 2, 4, 5, 8, -1]]))
+    assert got.tolist() == [[5, 7, 9, 100, 103, -1]]
+    import torch
+
+    got_t = seg.to_global_torch(torch.tensor([[0, 2, 4, 5, 8, -1]]))
+    assert got_t.tolist() == [[5, 7, 9, 100, 103, -1]]
+
+
+def test_store_mirror_host_logic(monkeypatch, tmp_path, golden):
+    """FAISSVectorStore mirror: coercions, nq forced to 1, -1 filtering, swallow-all-errors search,
+    mapping pickle next to the index, sequential ids when the mapping is missing (faiss_store.py)."""
+    from rag_faiss_embedding_b200 import store as st
+
+    written = {}
+
+    def fake_write(index, path):
+        orc.np_write_index(path, index.x, index.metric_type)
+        written["path"] = path
+
+    def fake_read(path, device=None):
+        x, metric = orc.np_read_index(path)
+        ix = OracleIndex(x.shape[1], metric)
+        ix.add(x)
+        return ix
+
+    monkeypatch.setattr(st, "IndexFlatL2", OracleIndex)
+    monkeypatch.setattr(st, "IndexFlatIP", lambda d, **kw: OracleIndex(d, orc.METRIC_INNER_PRODUCT))
+    monkeypatch.setattr(st, "write_index", fake_write)
+    monkeypatch.setattr(st, "read_index", fake_read)
+
+    path = str(tmp_path / "data" / "faiss_index.bin")
+    s = st.FAISSVectorStore(dimension=8, index_path=path)
+    x = orc.np_synth_rows(3, 0, 6, 8)
+    s.add_vectors(x[:5].tolist(), [50, 40, 30, 20, 10])   # list input is coerced to fp32
+    s.add_vectors(x[5], [60])                              # 1-D input becomes one row
+    assert s.index.ntotal == 6 and s.doc_ids == [50, 40, 30, 20, 10, 60]
+    d, ids = s.search(x[2], k=3)
+    assert ids[0] == 30 and len(ids) == 3 and d[0] == 0
+    d, ids = s.search(x[2].tolist(), k=10)                 # k > ntotal: -1 rows dropped
+    assert len(ids) == 6
+    d, ids = s.search(np.zeros(5, np.float32), k=3)        # wrong dimension: swallowed, empty result
+    assert len(ids) == 0 and d.size == 0
+    dm, idm = s.search_many(x[:2], k=2)
+    assert [r[0] for r in idm] == [50, 40] and dm.shape == (2, 2)
+    s.save_index()
+    assert os.path.exists(path) and pickle.load(open(path + ".mapping", "rb")) == s.doc_ids
+    s2 = st.FAISSVectorStore(dimension=8, index_path=path)  # auto-load in the constructor
+    assert s2.index.ntotal == 6 and s2.doc_ids == s.doc_ids
+    os.remove(path + ".mapping")
+    s2.load_index()
+    assert s2.doc_ids == list(range(6))
+    s2.reset()
+    assert s2.index.ntotal == 0 and s2.doc_ids == []
+    # the reference's own artefacts load through the same surface
+    s3 = st.FAISSVectorStore(dimension=384, index_path=golden["index_path"])
+    assert s3.doc_ids == golden["mapping"] and s3.index.ntotal == 23
+    xb, _ = orc.np_read_index(golden["index_path"])
+    case = next(c for c in golden["cases"] if c["metric"] == 1 and c["k"] == 5 and c["queries"] == "self")
+    for row in (0, 7, 22):
+        d, ids = s3.search(xb[row], k=5)
+        assert ids == [golden["mapping"][i] for i in case["ids"][row]]

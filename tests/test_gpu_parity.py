@@ -1,0 +1,322 @@
+"""GPU tier (-m gpu): the CUDA path, called through the C-ABI, against the CPU oracle and the golden
+fixtures.  Tolerances (BASELINE.json north_star): ids identical except among exact-distance ties;
+distances within 1e-5 relative (1e-4 absolute floor near zero) -- both search paths end in fp32
+exact-difference arithmetic, like faiss's fvec_L2sqr."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+FLT_MAX = np.finfo(np.float32).max
+REL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def m():
+    import rag_faiss_embedding_b200 as mod
+
+    assert mod.device_count() > 0, "no B200 visible"
+    return mod
+
+
+def _check(D, I, D_ref, I_ref, metric, rel=REL):
+    r = orc.recall_and_errors(D, I, D_ref, I_ref, metric, rel_tol=rel)
+    assert r["recall"] == 1.0, r
+    assert r["id_mismatch"] == 0, r
+    assert r["padding_ok"], r
+    assert r["max_rel_err"] <= rel, r
+    return r
+
+
+def _make(m, xb, metric, **kw):
+    ix = m.IndexFlat(xb.shape[1], metric, **kw)
+    if xb.shape[0]:
+        ix.add(xb)
+    return ix
+
+
+# ---- golden fixture: the reference's own FAISS-written index ------------------------------------------
+def test_fixture_read_search_write(m, golden, tmp_path):
+    ix = m.read_index(golden["index_path"])
+    assert (ix.d, ix.ntotal, ix.metric_type, ix.is_trained) == (384, 23, 1, True)
+    xb, _ = orc.np_read_index(golden["index_path"])
+    assert np.array_equal(ix.reconstruct_n(0, 23), xb)
+    assert np.array_equal(ix.reconstruct(7), xb[7])
+    for algo in (m.ALGO_SCAN, m.ALGO_TENSOR):
+        ix.set_search_params(algo=algo)
+        for case in golden["cases"]:
+            if case["metric"] != 1 or (algo == m.ALGO_TENSOR and case["k"] > 10):
+                continue
+            q = xb if case["queries"] == "self" else golden["perturbed"]
+            D, I = ix.search(q, case["k"])
+            _check(D, I, np.asarray(case["dists"]), np.asarray(case["ids"], np.int64), 1)
+    out = tmp_path / "roundtrip.bin"
+    m.write_index(ix, out)
+    assert open(out, "rb").read() == open(golden["index_path"], "rb").read()
+    # inner-product twin of the same rows
+    ip = _make(m, xb, 0)
+    for case in golden["cases"]:
+        if case["metric"] != 0:
+            continue
+        q = xb if case["queries"] == "self" else golden["perturbed"]
+        D, I = ip.search(q, case["k"])
+        _check(D, I, np.asarray(case["dists"]), np.asarray(case["ids"], np.int64), 0)
+    out2 = tmp_path / "ip.bin"
+    m.write_index(ip, out2)
+    assert open(out2, "rb").read()[:4] == b"IxFI"
+    back = m.read_index(out2)
+    assert back.metric_type == 0 and np.array_equal(back.reconstruct_n(), xb)
+
+
+def test_reference_wrapper_on_fixture(m, golden):
+    """The FAISSVectorStore surface (faiss_store.py) over the real index: row -> doc id mapping."""
+    s = m.FAISSVectorStore(dimension=384, index_path=golden["index_path"])
+    assert s.doc_ids == golden["mapping"]
+    xb, _ = orc.np_read_index(golden["index_path"])
+    case = next(c for c in golden["cases"] if c["metric"] == 1 and c["k"] == 5 and c["queries"] == "self")
+    for row in (0, 1, 2, 7, 22):
+        d, ids = s.search(xb[row], k=5)
+        assert ids == [golden["mapping"][i] for i in case["ids"][row]]
+        assert np.allclose(d, case["dists"][row], rtol=1e-5, atol=1e-4)
+    d, ids = s.search(xb[0], k=40)
+    assert len(ids) == 23
+
+
+# ---- K1 streaming scan vs oracle -----------------------------------------------------------------------
+@pytest.mark.parametrize("metric", [1, 0])
+@pytest.mark.parametrize("n,d,nq,k", [
+    (1, 384, 1, 1), (23, 384, 1, 5), (1000, 384, 3, 10), (5000, 768, 8, 10), (4097, 96, 5, 100),
+    (3000, 100, 2, 7), (777, 1, 4, 3), (2500, 30, 9, 128), (50000, 384, 1, 10), (20000, 64, 17, 1024),
+    (300, 1026, 2, 10),
+])
+def test_scan_vs_oracle(m, metric, n, d, nq, k):
+    xb = orc.c_synth_rows(1234, 0, n, d)
+    xq = orc.c_synth_rows(5678, 0, nq, d)
+    ix = _make(m, xb, metric).set_search_params(algo=m.ALGO_SCAN)
+    D, I = ix.search(xq, k)
+    D_ref, I_ref = orc.np_search_f64(xb, xq, k, metric)
+    _check(D, I, D_ref, I_ref, metric)
+    st = ix.stats()
+    assert st["last_algo"] == m.ALGO_SCAN and st["last_launches"] >= 3
+
+
+def test_edge_cases(m):
+    xb = orc.c_synth_rows(1, 0, 10, 8)
+    ix = _make(m, xb, 1)
+    D, I = ix.search(xb[:2], 16)           # k > ntotal
+    assert (I[:, 10:] == -1).all() and (D[:, 10:] == FLT_MAX).all() and I[:, 0].tolist() == [0, 1]
+    e = m.IndexFlatL2(8)                   # empty index
+    D, I = e.search(xb[:2], 3)
+    assert (I == -1).all() and (D == FLT_MAX).all()
+    e = m.IndexFlatIP(8)
+    D, I = e.search(xb[:2], 3)
+    assert (I == -1).all() and (D == -FLT_MAX).all()
+    dup = _make(m, np.repeat(xb[:1], 5, 0), 1)   # exact ties -> ascending label
+    D, I = dup.search(xb[:1], 3)
+    assert I.tolist() == [[0, 1, 2]] and (D == 0).all()
+    bad = xb.copy()
+    bad[3] = np.nan                        # NaN rows never enter
+    D, I = _make(m, bad, 1).search(xb[:1], 10)
+    assert 3 not in I[0].tolist() and I[0, -1] == -1
+    with pytest.raises(AssertionError):
+        ix.search(xb[:1], 0)
+    with pytest.raises(AssertionError):
+        ix.search(np.zeros((1, 9), np.float32), 1)
+    with pytest.raises(AssertionError):
+        ix.add(np.zeros((1, 9), np.float32))
+    with pytest.raises(RuntimeError):
+        m.read_index("/nonexistent/index.bin")
+    with pytest.raises(RuntimeError):
+        ix.reconstruct(10)
+    ix.reset()
+    assert ix.ntotal == 0
+    ix.add(xb[:3])
+    assert ix.ntotal == 3 and ix.search(xb[:1], 1)[1][0, 0] == 0
+    D, I = ix.search(np.zeros((0, 8), np.float32), 3)   # empty query batch
+    assert D.shape == (0, 3) and I.shape == (0, 3)
+
+
+def test_incremental_add_and_growth(m):
+    d = 48
+    xb = orc.c_synth_rows(9, 0, 5000, d)
+    ix = m.IndexFlatL2(d)
+    for a, b in ((0, 1), (1, 700), (700, 1500), (1500, 5000)):   # crosses the initial capacity
+        ix.add(xb[a:b])
+    assert ix.ntotal == 5000 and np.array_equal(ix.reconstruct_n(), xb)
+    xq = orc.c_synth_rows(10, 0, 4, d)
+    D, I = ix.search(xq, 10)
+    _check(D, I, *orc.np_search_f64(xb, xq, 10, 1), 1)
+
+
+# ---- K2 tensor path (tcgen05 + fused top-k + exact re-rank + certification) vs oracle --------------------
+@pytest.mark.parametrize("metric", [1, 0])
+@pytest.mark.parametrize("n,d,nq,k", [
+    (300, 384, 1, 10), (5000, 384, 33, 10), (20000, 384, 128, 10), (100000, 384, 200, 10),
+    (7000, 768, 64, 10), (9000, 100, 130, 5), (70000, 64, 1024, 10), (4000, 384, 16, 20),
+    (256, 384, 9, 1), (257, 128, 300, 10),
+])
+def test_tensor_vs_oracle(m, metric, n, d, nq, k):
+    xb = orc.c_synth_rows(1234, 0, n, d)
+    xq = orc.c_synth_rows(5678, 0, nq, d)
+    ix = _make(m, xb, metric).set_search_params(algo=m.ALGO_TENSOR)
+    D, I = ix.search(xq, k)
+    D_ref, I_ref = orc.np_search_f64(xb, xq, k, metric)
+    _check(D, I, D_ref, I_ref, metric)
+    st = ix.stats()
+    assert st["last_algo"] == m.ALGO_TENSOR and st["last_kprime"] in (32, 64)
+
+
+def test_tensor_hard_inputs(m):
+    """Near-duplicates and mean-shifted rows (the fixture's distribution: norm ~7.7, tiny relative gaps)
+    stress the bf16 coarse pass; certification + exact fallback must keep results exact."""
+    rng = np.random.default_rng(7)
+    d, n = 384, 30000
+    base = (rng.standard_normal((n, d)) * 0.25 + 0.4).astype(np.float32)
+    base[1000:1100] = base[999] + rng.standard_normal((100, d)).astype(np.float32) * 1e-3  # a tight cluster
+    xq = np.concatenate([base[995:1005] + 1e-4, (rng.standard_normal((30, d)) * 0.25 + 0.4).astype(np.float32)])
+    for metric in (1, 0):
+        ix = _make(m, base, metric).set_search_params(algo=m.ALGO_TENSOR)
+        D, I = ix.search(xq, 10)
+        _check(D, I, *orc.np_search_f64(base, xq, 10, metric), metric)
+    # with certification off the same call may miss, but must still return sorted, valid rows
+    ix.set_search_params(certify=False)
+    D, I = ix.search(xq, 10)
+    assert (I >= 0).all() and (np.diff(D, axis=1) <= 1e-6).all()
+
+
+def test_auto_dispatch(m):
+    xb = orc.c_synth_rows(1, 0, 4000, 128)
+    ix = _make(m, xb, 1)
+    ix.search(orc.c_synth_rows(2, 0, 4, 128), 10)
+    assert ix.stats()["last_algo"] == m.ALGO_SCAN
+    ix.search(orc.c_synth_rows(2, 0, 64, 128), 10)
+    assert ix.stats()["last_algo"] == m.ALGO_TENSOR
+    D, I = ix.search(orc.c_synth_rows(2, 0, 64, 128), 200)   # k' > 64: falls back to the exact scan
+    assert ix.stats()["last_algo"] == m.ALGO_SCAN
+    _check(D, I, *orc.np_search_f64(xb, orc.c_synth_rows(2, 0, 64, 128), 200, 1), 1)
+
+
+# ---- bf16 storage: the oracle runs on the rounded rows -------------------------------------------------
+@pytest.mark.parametrize("algo_name", ["scan", "tensor"])
+def test_bf16_storage(m, algo_name):
+    import torch
+
+    n, d, nq, k = 20000, 384, 40, 10
+    xb = orc.c_synth_rows(1234, 0, n, d)
+    xb_r = torch.from_numpy(xb).to(torch.bfloat16).to(torch.float32).numpy()
+    xq = orc.c_synth_rows(5678, 0, nq, d)
+    ix = m.IndexFlat(d, 1, storage=m.STORE_BF16)
+    ix.add(xb)
+    assert np.array_equal(ix.reconstruct_n(0, 100), xb_r[:100])
+    ix.set_search_params(algo=m.ALGO_SCAN if algo_name == "scan" else m.ALGO_TENSOR)
+    D, I = ix.search(xq, k)
+    _check(D, I, *orc.np_search_f64(xb_r, xq, k, 1), 1)
+
+
+# ---- torch tensor handoff, pooling kernel, synthetic generator, merge kernel ---------------------------
+def test_torch_device_pointers(m):
+    import torch
+
+    d = 384
+    xb = orc.c_synth_rows(1234, 0, 3000, d)
+    xq = orc.c_synth_rows(5678, 0, 20, d)
+    ix = m.IndexFlatL2(d)
+    ix.add(torch.from_numpy(xb).cuda())
+    Dt, It = ix.search(torch.from_numpy(xq).cuda(), 10)
+    assert Dt.is_cuda and It.dtype == torch.int64
+    torch.cuda.synchronize()
+    _check(Dt.cpu().numpy(), It.cpu().numpy(), *orc.np_search_f64(xb, xq, 10, 1), 1)
+
+
+def test_pool_normalize_and_add_pooled(m):
+    import torch
+
+    from rag_faiss_embedding_b200.encoder import pool_normalize
+
+    torch.manual_seed(0)
+    B, T, d = 37, 19, 384
+    h = torch.randn(B, T, d, device="cuda") * 2 + 0.5
+    lens = torch.randint(1, T + 1, (B,), device="cuda")
+    mask = (torch.arange(T, device="cuda")[None, :] < lens[:, None]).to(torch.int64)
+    cls = pool_normalize(h, mask, "cls", False)
+    assert torch.equal(cls, h[:, 0])                      # reference semantics: raw CLS token, bit exact
+    mean_ref = (h * mask[..., None]).sum(1) / mask.sum(1, keepdim=True).clamp(min=1e-9)
+    mean = pool_normalize(h, mask, "mean", False)
+    assert torch.allclose(mean, mean_ref, rtol=1e-5, atol=1e-6)
+    nrm = pool_normalize(h, mask, "mean", True)
+    assert torch.allclose(nrm, torch.nn.functional.normalize(mean_ref, dim=1), rtol=1e-5, atol=1e-6)
+    ix = m.IndexFlatIP(d)
+    ix.add_pooled(h, mask, pool="mean", normalize=True)
+    ix.add_pooled(h, None, pool="cls", normalize=False)
+    torch.cuda.synchronize()
+    assert ix.ntotal == 2 * B
+    rows = ix.reconstruct_n()
+    assert np.allclose(rows[:B], nrm.cpu().numpy(), rtol=1e-6, atol=1e-7)
+    assert np.array_equal(rows[B:], h[:, 0].cpu().numpy())
+    D, I = ix.search(nrm.cpu().numpy()[:5], 1)
+    assert I[:, 0].tolist() == [0, 1, 2, 3, 4] or (D[:, 0] >= 1 - 1e-4).all()
+
+
+def test_synth_bit_identical(m):
+    from rag_faiss_embedding_b200.encoder import synth_rows
+
+    for norm in (False, True):
+        a = synth_rows(1234, 999_983, 257, 384, norm).cpu().numpy()
+        b = orc.c_synth_rows(1234, 999_983, 257, 384, norm)
+        assert np.array_equal(a, b)
+    ix = m.IndexFlatL2(96)
+    ix.add_synthetic(77, 5, 1000)
+    assert np.array_equal(ix.reconstruct_n(), orc.c_synth_rows(77, 5, 1000, 96))
+
+
+def test_merge_topk_kernel(m):
+    import torch
+
+    from tests.helpers import np_merge
+
+    rng = np.random.default_rng(3)
+    for metric in (1, 0):
+        G, nq, k = 8, 50, 10
+        D = np.sort(rng.random((G, nq, k)).astype(np.float32), axis=2)
+        if metric == 0:
+            D = D[:, :, ::-1].copy()
+        I = rng.permutation(G * nq * k).reshape(G, nq, k).astype(np.int64)
+        D[3, :, 7:] = FLT_MAX if metric == 1 else -FLT_MAX   # a short shard
+        I[3, :, 7:] = -1
+        D[5] = D[2]                                           # exact ties across shards -> lower label first
+        Dm, Im = m.merge_topk(metric, torch.from_numpy(D).cuda(), torch.from_numpy(I).cuda())
+        D_ref, I_ref = np_merge(metric, D, I)
+        assert np.array_equal(Im.cpu().numpy(), I_ref) and np.array_equal(Dm.cpu().numpy(), D_ref)
+
+
+# ---- full-size properties at the BASELINE config (1M x 384, fp32, L2, k=10) -----------------------------
+def test_full_size_properties(m):
+    n, d, k = 1_000_000, 384, 10
+    ix = m.IndexFlatL2(d)
+    ix.add_synthetic(1234, 0, n)
+    assert ix.ntotal == n
+    # self-queries: every row's nearest neighbour is itself at distance exactly 0 (exact-difference form)
+    rows = np.array([0, 1, 255, 256, 499_999, 777_777, 999_999])
+    q_self = np.stack([orc.c_synth_rows(1234, int(r), 1, d)[0] for r in rows])
+    for algo in (m.ALGO_SCAN, m.ALGO_TENSOR):
+        D, I = ix.set_search_params(algo=algo).search(q_self, k)
+        assert I[:, 0].tolist() == rows.tolist() and (D[:, 0] == 0).all()
+        assert (np.diff(D, axis=1) >= 0).all()
+    # sampled parity against the oracle's own exhaustive scan (8 queries x 1M rows on the host)
+    xb = orc.c_synth_rows(1234, 0, n, d)
+    xq = orc.c_synth_rows(5678, 0, 1024, d)
+    D_ref, I_ref = orc.c_search(xb, xq[:8], k, 1, algo=1)
+    D8, I8 = ix.set_search_params(algo=m.ALGO_SCAN).search(xq[:8], k)
+    _check(D8, I8, D_ref, I_ref, 1)
+    # the two GPU paths must agree with each other on the whole 1024-query batch
+    Dt, It = ix.set_search_params(algo=m.ALGO_TENSOR).search(xq, k)
+    _check(Dt[:8], It[:8], D_ref, I_ref, 1)
+    Ds, Is = ix.set_search_params(algo=m.ALGO_SCAN).search(xq[:64], k)
+    _check(Dt[:64], It[:64], Ds, Is, 1)
+    # idempotence and batch-independence: a query's answer does not depend on its batch
+    D1, I1 = ix.set_search_params(algo=m.ALGO_TENSOR).search(xq[100:101], k)
+    assert np.array_equal(I1[0], It[100]) and np.allclose(D1[0], Dt[100], rtol=1e-6)
