@@ -348,7 +348,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": wl["label"], "rows_total": n_global, "rows_per_gpu": rows_local, "d": d, "nq": nq, "k": k,
                        "storage": wl["storage"], "algo": {1: "scan", 2: "tensor"}.get(used_algo, "?"),
-                       "kprime": st["last_kprime"], "fallback_queries": st["fallback_queries"],
+                       "kprime": st["last_kprime"], "fallback_queries": st["fallback_queries"], "overflow_queries": st["overflow_queries"],
                        "l2_policy": "inputs larger than L2 (bf16 scan copy %.0f MB per GPU, L2 126 MB)" % (rows_local * dpad * 2 / 1e6),
                        "sharding": "rows, contiguous ranges; one all-gather + CUDA merge per step" if world > 1 else "single GPU"},
             "roofline": roof,

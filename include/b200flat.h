@@ -93,6 +93,7 @@ typedef struct b2f_stats {
     int32_t last_launches;     /* kernels launched by the last search */
     int64_t bytes_rows;        /* device bytes held: authoritative rows */
     int64_t bytes_scan;        /* device bytes held: bf16 scan copy + norms */
+    int64_t overflow_queries;  /* subset of fallback_queries caused by a candidate-list overflow */
 } b2f_stats;
 
 /* ---- lifecycle -------------------------------------------------------------------------------

@@ -48,6 +48,7 @@ class Stats(ctypes.Structure):
         ("last_launches", ctypes.c_int32),
         ("bytes_rows", ctypes.c_int64),
         ("bytes_scan", ctypes.c_int64),
+        ("overflow_queries", ctypes.c_int64),
     ]
 
     def as_dict(self):

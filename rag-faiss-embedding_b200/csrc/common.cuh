@@ -207,8 +207,9 @@ struct RerankArgs {
     int certify;
     float* out_key;                 // [nq, k] exact keys
     int32_t* out_id;                // [nq, k]
+    const int32_t* overflow;        // optional [nq]: 1 = candidate list overflowed (treated as uncertified)
     int32_t* fail_list;             // queries that could not be certified
-    int32_t* fail_count;
+    int32_t* fail_count;            // [2]: uncertified queries, of which list overflows
 };
 int launch_rerank(const RerankArgs& a, cudaStream_t st);
 
@@ -216,12 +217,23 @@ int launch_rerank(const RerankArgs& a, cudaStream_t st);
 struct TensorScanPlan {
     int nq_tiles;      // ceil(nq / 128)
     int nsplits;       // database streams per query tile
-    int kp;            // candidates kept per (query, stream)
-    size_t smem_bytes;
+    int kp;            // candidates kept per query
+    int list_mode;     // 1: shared-threshold candidate lists (K3b merge), 0: per-thread heaps (K3 merge)
+    int list_j;        // rows each split vouches for
+    int list_g;        // splits consulted for the shared threshold (g * j >= kp)
+    int list_cap;      // entries per (query, split) list
+};
+struct TensorScanLists {  // LIST-mode scratch (device)
+    float* shared_thr;    // [nq_pad][nsplits]
+    void* cand;           // [nq_pad * nsplits][list_cap] x 8 bytes
+    int32_t* counts;      // [nq_pad * nsplits]
 };
 int plan_tensor_scan(int nq, int64_t n, int d, int kp, TensorScanPlan* plan);
 int launch_tensor_scan(const __nv_bfloat16* scan, int64_t dpad, const float* norms, int64_t n, int metric,
                        const __nv_bfloat16* qb, int nq, int nq_pad, const TensorScanPlan& plan, float* pk,
-                       int32_t* pi, cudaStream_t st);
+                       int32_t* pi, const TensorScanLists& lists, cudaStream_t st);
+// K3b: per query, the kp best of the variable-length lists -> ck/ci [nq][kp]; ovf[q]=1 on list overflow
+int launch_merge_lists(const TensorScanLists& lists, int nq, const TensorScanPlan& plan, float* ck, int32_t* ci,
+                       int32_t* ovf, cudaStream_t st);
 
 }  // namespace b2f

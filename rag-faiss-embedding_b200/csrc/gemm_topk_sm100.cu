@@ -12,11 +12,17 @@
 //            smem stage / publishes the accumulator
 //   warp 2   TMEM allocator (512 columns = two 128x256 fp32 accumulators, double buffered)
 //   warp 3   bias loader: |x~|^2 of the 256 rows of the tile (+inf for rows past the end) -> smem
-//   warps 4-7  epilogue: tcgen05.ld 32 columns at a time; thread t owns query t of the tile, so the
-//            running top-k' is thread-private: key = bias[col] - 2*acc (L2) or -acc (IP) is compared
-//            with a register threshold; the rare survivor replaces the root of the thread's max-heap
-//            (shared memory, [slot][thread] layout => conflict free).  At the end each heap is sorted
-//            and written as the (query, split) partial list.
+//   warps 4-7  epilogue: tcgen05.ld 32 columns at a time (double buffered); thread t owns query t of
+//            the tile: key = bias[col] - 2*acc (L2) or -acc (IP) is compared with a register threshold
+//            and the rare survivor is kept.  Two selection modes:
+//            LIST (nsplits >= k'/8): survivors are appended to the thread's candidate list in global
+//              memory (fire-and-forget stores).  The threshold is SHARED across the CTAs that stream
+//              different database splits for the same query: every split publishes its j-th best key
+//              so far (j = ceil(k'/g)); T* = max over g splits of those values is an upper bound of
+//              the global k'-th best (g*j >= k' rows are known to be <= T*), and it is far tighter
+//              than any single split's own k'-th best, so ~5x fewer rows survive the filter.
+//            HEAP (few splits, long streams): thread-private max-heap of k' in shared memory
+//              ([slot][thread] layout => conflict free), threshold = heap root.
 //
 // Work split: grid = nq_tiles x nsplits (<= 148 CTAs, one per SM); CTA (qt, s) streams database tiles
 // [s*NT/nsplits, (s+1)*NT/nsplits) against query tile qt.  CTAs that share a split walk the same
@@ -36,7 +42,10 @@ constexpr int BM = 128;        // queries per tile  (UMMA M)
 constexpr int BN = 256;        // database rows per tile (UMMA N)
 constexpr int BK = 64;         // bf16 elements per stage along d: 128 bytes = one swizzle atom
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 3;
+constexpr int STAGES_HEAP = 3;
+constexpr int STAGES_LIST = 4;
+constexpr int LIST_CAP = 128;     // entries per (query, split) candidate list
+constexpr int JSLOTS = 8;         // register slots for the split-local j-th best (j <= 8)
 constexpr int A_BYTES = BM * BK * 2;  // 16 KB
 constexpr int B_BYTES = BN * BK * 2;  // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -120,17 +129,26 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-template <int KP>
+template <int KP, int NST>
 struct Smem {
     static constexpr size_t stages_off = 0;
-    static constexpr size_t heapk_off = (size_t)STAGES * STAGE_BYTES;
+    static constexpr size_t heapk_off = (size_t)NST * STAGE_BYTES;
     static constexpr size_t heapi_off = heapk_off + (size_t)EPI_THREADS * KP * 4;
     static constexpr size_t bias_off = heapi_off + (size_t)EPI_THREADS * KP * 4;
     static constexpr size_t bar_off = bias_off + 2 * BN * 4;
-    static constexpr int nbars = 2 * STAGES + 6;
+    static constexpr int nbars = 2 * NST + 6;
     static constexpr size_t tmem_off = bar_off + nbars * 8;
     static constexpr size_t total = tmem_off + 16;
     static constexpr size_t alloc = total + 1024;  // slack for manual 1024-byte alignment
+};
+
+// LIST-mode arguments (all device pointers)
+struct ListArgs {
+    float* shared_thr;   // [nq_pad][nsplits]  each split's published j-th best key (init: huge)
+    uint2* cand;         // [nq_pad * nsplits][LIST_CAP]  (key bits, row id)
+    int32_t* counts;     // [nq_pad * nsplits]  entries appended (may exceed LIST_CAP => overflow)
+    int j;               // rows each split vouches for
+    int g;               // splits consulted: g * j >= k'
 };
 
 // thread-private max-heap in shared memory, element j of thread t at [j * 128 + t].
@@ -170,12 +188,22 @@ __device__ __noinline__ float heap_push(float* hk, int32_t* hi, int tid, float k
     return hk[tid];
 }
 
-template <int KP, bool L2>
+// Order-preserving float <-> uint32 map (for the 64-bit (key,id) composites of the list merge)
+__device__ __forceinline__ uint32_t enc_key(float f) {
+    const uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float dec_key(uint32_t e) {
+    return __uint_as_float((e & 0x80000000u) ? (e & 0x7fffffffu) : ~e);
+}
+
+template <int KP, bool L2, bool LIST>
 __global__ void __launch_bounds__(THREADS, 1)
 tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
                    const float* __restrict__ norms, int64_t n, int nq, int kblocks, int nq_tiles, int nsplits,
-                   float* __restrict__ pk, int32_t* __restrict__ pi) {
-    using L = Smem<KP>;
+                   float* __restrict__ pk, int32_t* __restrict__ pi, ListArgs la) {
+    constexpr int STAGES = LIST ? STAGES_LIST : STAGES_HEAP;
+    using L = Smem<LIST ? 0 : KP, STAGES>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     float* heap_k = reinterpret_cast<float*>(smem + L::heapk_off);
@@ -298,51 +326,147 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         const int wq = warp & 3;                      // TMEM lane quarter this warp may access
         const int qrow = qt * BM + tid;
         const bool active = qrow < nq;
-        for (int j = 0; j < KP; j++) {
-            heap_k[j * EPI_THREADS + tid] = FLT_MAX;
-            heap_i[j * EPI_THREADS + tid] = -1;
-        }
-        float thr = FLT_MAX;
-        for (int t = 0; t < my_tiles; t++) {
-            const int acc = t & 1;
-            const uint32_t acc_phase = (t >> 1) & 1;
-            mbar_wait(&bias_full[acc], acc_phase);
-            mbar_wait(&tmem_full[acc], acc_phase);
-            tc_fence_after();
-            const int32_t row0 = (int32_t)((t_begin + t) * BN);
-            const float* tb = bias + acc * BN;
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; c++) {
-                uint32_t r[32];
-                tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * BN + c * 32), r);
-                tmem_ld_wait();
-                if (active) {
+        const uint32_t lane_taddr = tmem_base + ((uint32_t)(wq * 32) << 16);
+
+        if constexpr (LIST) {
+            // ---- LIST mode: shared cross-split threshold + append-only candidate lists -----------------
+            const float kInf = __int_as_float(0x7f800000);
+            float best[JSLOTS];  // ascending; the first JSLOTS - j slots are pinned at -inf, so best[7] = j-th best
 #pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        const float s = __uint_as_float(r[j]);
-                        const float key = L2 ? fmaf(-2.f, s, tb[c * 32 + j]) : tb[c * 32 + j] - s;
-                        if (key < thr) thr = heap_push<KP>(heap_k, heap_i, tid, key, row0 + c * 32 + j);
+            for (int i = 0; i < JSLOTS; i++) best[i] = (i < JSLOTS - la.j) ? -kInf : kInf;
+            float thr = 3.0e38f, pub = kInf;  // refreshed before the first compare; never +inf (padding rows have key +inf)
+            int cnt = 0;
+            uint2* mylist = la.cand + ((int64_t)(active ? qrow : 0) * nsplits + split) * LIST_CAP;
+            // shared thresholds are laid out [split][query] so that a warp's loads for one split coalesce
+            float* gq = la.shared_thr + (active ? qrow : 0);
+            const int64_t gstride = (int64_t)nq_tiles * BM;
+            auto refresh = [&]() {
+                if (best[JSLOTS - 1] < pub) {
+                    pub = best[JSLOTS - 1];
+                    __stcg(gq + (int64_t)split * gstride, pub);
+                }
+                float t = -kInf;
+                for (int i0 = 0; i0 < la.g; i0 += 8) {  // 8 independent L2 loads in flight
+                    float v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        int s2 = split + i0 + u;
+                        if (s2 >= nsplits) s2 -= nsplits;
+                        v[u] = (i0 + u < la.g) ? __ldcg(gq + (int64_t)s2 * gstride) : -kInf;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; u++) t = fmaxf(t, v[u]);
+                }
+                thr = t;
+            };
+            for (int t = 0; t < my_tiles; t++) {
+                const int acc = t & 1;
+                const uint32_t acc_phase = (t >> 1) & 1;
+                mbar_wait(&bias_full[acc], acc_phase);
+                mbar_wait(&tmem_full[acc], acc_phase);
+                tc_fence_after();
+                const int32_t row0 = (int32_t)((t_begin + t) * BN);
+                const float* tb = bias + acc * BN;
+                const uint32_t tile_taddr = lane_taddr + (uint32_t)(acc * BN);
+                uint32_t r[2][32];
+                tmem_ld32(tile_taddr, r[0]);
+#pragma unroll
+                for (int c = 0; c < BN / 32; c++) {
+                    tmem_ld_wait();
+                    if (c + 1 < BN / 32) tmem_ld32(tile_taddr + (uint32_t)((c + 1) * 32), r[(c + 1) & 1]);
+                    if (active) {
+                        if (t < 2 || c == 0) refresh();  // every chunk while the threshold is still settling
+                        if (t == 0 && c == 1) {
+                            // Every split has now seen 32 rows and published.  CTAs start a few microseconds
+                            // apart; wait (bounded -- never a hard dependency) for the slowest of the g
+                            // splits we consult instead of appending blindly into the list meanwhile.
+                            for (int spin = 0; spin < 64 && thr > 1.0e38f; spin++) {
+                                __nanosleep(256);
+                                refresh();
+                            }
+                        }
+                        uint32_t mask = 0;
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            const float sdot = __uint_as_float(r[c & 1][j]);
+                            const float key = L2 ? fmaf(-2.f, sdot, tb[c * 32 + j]) : tb[c * 32 + j] - sdot;
+                            if (key <= thr) mask |= 1u << j;
+                        }
+                        if (mask) {
+#pragma unroll
+                            for (int j = 0; j < 32; j++) {
+                                if (mask & (1u << j)) {
+                                    const float sdot = __uint_as_float(r[c & 1][j]);
+                                    const float key = L2 ? fmaf(-2.f, sdot, tb[c * 32 + j]) : tb[c * 32 + j] - sdot;
+                                    if (cnt < LIST_CAP) mylist[cnt] = make_uint2(__float_as_uint(key), (uint32_t)(row0 + c * 32 + j));
+                                    cnt++;
+                                    if (key < best[JSLOTS - 1]) {
+                                        best[JSLOTS - 1] = key;
+#pragma unroll
+                                        for (int i = JSLOTS - 1; i > 0; i--) {
+                                            const float lo = fminf(best[i - 1], best[i]), hi = fmaxf(best[i - 1], best[i]);
+                                            best[i - 1] = lo;
+                                            best[i] = hi;
+                                        }
+                                    }
+                                }
+                            }
+                        }
                     }
                 }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[acc]);
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-        }
-        // heap sort (ascending) and write the partial list of (query, split)
-        if (active) {
-            for (int m = KP - 1; m > 0; m--) {
-                const float lk_ = heap_k[m * EPI_THREADS + tid];
-                const int32_t li_ = heap_i[m * EPI_THREADS + tid];
-                heap_k[m * EPI_THREADS + tid] = heap_k[tid];
-                heap_i[m * EPI_THREADS + tid] = heap_i[tid];
-                heap_sift_down_n<KP>(heap_k, heap_i, tid, m, lk_, li_);
-            }
-            float* ok = pk + ((int64_t)qrow * nsplits + split) * KP;
-            int32_t* oi = pi + ((int64_t)qrow * nsplits + split) * KP;
+            if (active) la.counts[(int64_t)qrow * nsplits + split] = cnt;
+        } else {
+            // ---- HEAP mode: thread-private max-heap of k' in shared memory ------------------------------
             for (int j = 0; j < KP; j++) {
-                ok[j] = heap_k[j * EPI_THREADS + tid];
-                oi[j] = heap_i[j * EPI_THREADS + tid];
+                heap_k[j * EPI_THREADS + tid] = FLT_MAX;
+                heap_i[j * EPI_THREADS + tid] = -1;
+            }
+            float thr = FLT_MAX;
+            for (int t = 0; t < my_tiles; t++) {
+                const int acc = t & 1;
+                const uint32_t acc_phase = (t >> 1) & 1;
+                mbar_wait(&bias_full[acc], acc_phase);
+                mbar_wait(&tmem_full[acc], acc_phase);
+                tc_fence_after();
+                const int32_t row0 = (int32_t)((t_begin + t) * BN);
+                const float* tb = bias + acc * BN;
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; c++) {
+                    uint32_t r[32];
+                    tmem_ld32(lane_taddr + (uint32_t)(acc * BN + c * 32), r);
+                    tmem_ld_wait();
+                    if (active) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            const float sdot = __uint_as_float(r[j]);
+                            const float key = L2 ? fmaf(-2.f, sdot, tb[c * 32 + j]) : tb[c * 32 + j] - sdot;
+                            if (key < thr) thr = heap_push<KP>(heap_k, heap_i, tid, key, row0 + c * 32 + j);
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            }
+            // heap sort (ascending) and write the partial list of (query, split)
+            if (active) {
+                for (int m = KP - 1; m > 0; m--) {
+                    const float lk_ = heap_k[m * EPI_THREADS + tid];
+                    const int32_t li_ = heap_i[m * EPI_THREADS + tid];
+                    heap_k[m * EPI_THREADS + tid] = heap_k[tid];
+                    heap_i[m * EPI_THREADS + tid] = heap_i[tid];
+                    heap_sift_down_n<KP>(heap_k, heap_i, tid, m, lk_, li_);
+                }
+                float* ok = pk + ((int64_t)qrow * nsplits + split) * KP;
+                int32_t* oi = pi + ((int64_t)qrow * nsplits + split) * KP;
+                for (int j = 0; j < KP; j++) {
+                    ok[j] = heap_k[j * EPI_THREADS + tid];
+                    oi[j] = heap_i[j * EPI_THREADS + tid];
+                }
             }
         }
     }
@@ -352,6 +476,97 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
     }
+}
+
+// ---- K3b: per query, select the k' best of the S variable-length candidate lists ----------------------
+// One CTA per query.  Candidates become 64-bit composites (order-preserving key bits << 32 | row id);
+// the k'-th smallest composite is found by bisection on the 64-bit value (64 counting passes over
+// shared memory), the <= k' survivors are rank-sorted.  Output: ck/ci [nq][kp] ascending, padded with
+// (FLT_MAX,-1).  ovf[q] = 1 when a list overflowed (the query is then re-run by the exact scan).
+constexpr int MERGE_THREADS = 256;
+constexpr int MERGE_MAX = 12288;  // composites held in shared memory (96 KB)
+
+__global__ void __launch_bounds__(MERGE_THREADS)
+merge_lists_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ counts, int nsplits, int kp,
+                   float* __restrict__ ck, int32_t* __restrict__ ci, int32_t* __restrict__ ovf) {
+    extern __shared__ __align__(16) unsigned long long comp[];  // [MERGE_MAX] + survivors [kp]
+    __shared__ int s_off[kNumSMs + 2];
+    __shared__ int s_count;
+    __shared__ int s_nsurv;
+    __shared__ int s_ovf;
+    unsigned long long* surv = comp + MERGE_MAX;
+    const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        int tot = 0, o = 0;
+        for (int s = 0; s < nsplits; s++) {
+            int c = counts[(int64_t)q * nsplits + s];
+            if (c > LIST_CAP) {
+                c = LIST_CAP;
+                o = 1;
+            }
+            s_off[s] = tot;
+            tot += c;
+            if (tot > MERGE_MAX) {
+                tot = MERGE_MAX;
+                o = 1;
+            }
+        }
+        s_off[nsplits] = tot;
+        s_ovf = o;
+        s_nsurv = 0;
+    }
+    __syncthreads();
+    const int M = s_off[nsplits];
+    for (int s = warp; s < nsplits; s += MERGE_THREADS / 32) {
+        const int o = s_off[s], c = s_off[s + 1] - o;
+        const uint2* src = cand + ((int64_t)q * nsplits + s) * LIST_CAP;
+        for (int i = lane; i < c; i += 32) {
+            const uint2 e = src[i];
+            comp[o + i] = ((unsigned long long)enc_key(__uint_as_float(e.x)) << 32) | (unsigned long long)e.y;
+        }
+    }
+    __syncthreads();
+    unsigned long long T = ~0ull;
+    if (M > kp) {
+        unsigned long long lo = 0, hi = ~0ull;
+        while (lo < hi) {
+            const unsigned long long mid = lo + ((hi - lo) >> 1);
+            if (tid == 0) s_count = 0;
+            __syncthreads();
+            int c = 0;
+            for (int i = tid; i < M; i += MERGE_THREADS) c += comp[i] <= mid ? 1 : 0;
+            c = __reduce_add_sync(kFull, c);
+            if (lane == 0 && c) atomicAdd(&s_count, c);
+            __syncthreads();
+            const int total = s_count;
+            __syncthreads();
+            if (total >= kp) hi = mid;
+            else lo = mid + 1;
+        }
+        T = lo;
+    }
+    for (int i = tid; i < M; i += MERGE_THREADS) {
+        const unsigned long long v = comp[i];
+        if (v <= T) {
+            const int slot = atomicAdd(&s_nsurv, 1);
+            if (slot < kp) surv[slot] = v;
+        }
+    }
+    __syncthreads();
+    const int ns = s_nsurv < kp ? s_nsurv : kp;
+    for (int t = tid; t < kp; t += MERGE_THREADS) {
+        if (t < ns) {
+            const unsigned long long mine = surv[t];
+            int rank = 0;
+            for (int j = 0; j < ns; j++) rank += surv[j] < mine ? 1 : 0;
+            ck[(int64_t)q * kp + rank] = dec_key((uint32_t)(mine >> 32));
+            ci[(int64_t)q * kp + rank] = (int32_t)(uint32_t)(mine & 0xffffffffu);
+        } else {
+            ck[(int64_t)q * kp + t] = FLT_MAX;
+            ci[(int64_t)q * kp + t] = -1;
+        }
+    }
+    if (tid == 0) ovf[q] = s_ovf;
 }
 
 // ---- host side --------------------------------------------------------------------------------------
@@ -391,17 +606,18 @@ static int make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t
     return B2F_OK;
 }
 
-template <int KP, bool L2>
+template <int KP, bool L2, bool LIST>
 static int launch_k2(const CUtensorMap& mq, const CUtensorMap& mx, const float* norms, int64_t n, int nq, int kblocks,
-                     const TensorScanPlan& plan, float* pk, int32_t* pi, cudaStream_t st) {
-    auto kern = tensor_scan_kernel<KP, L2>;
+                     const TensorScanPlan& plan, float* pk, int32_t* pi, const ListArgs& la, cudaStream_t st) {
+    auto kern = tensor_scan_kernel<KP, L2, LIST>;
+    constexpr size_t smem = Smem<LIST ? 0 : KP, LIST ? STAGES_LIST : STAGES_HEAP>::alloc;
     static bool configured = false;
     if (!configured) {
-        B2F_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<KP>::alloc));
+        B2F_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    kern<<<plan.nq_tiles * plan.nsplits, THREADS, Smem<KP>::alloc, st>>>(mq, mx, norms, n, nq, kblocks, plan.nq_tiles,
-                                                                        plan.nsplits, pk, pi);
+    kern<<<plan.nq_tiles * plan.nsplits, THREADS, smem, st>>>(mq, mx, norms, n, nq, kblocks, plan.nq_tiles, plan.nsplits, pk,
+                                                              pi, la);
     B2F_CUDA(cudaGetLastError());
     return B2F_OK;
 }
@@ -419,26 +635,68 @@ int plan_tensor_scan(int nq, int64_t n, int d, int kp, TensorScanPlan* plan) {
     if (ns < 1) ns = 1;
     if (ns > ntiles) ns = (int)ntiles;
     plan->nsplits = ns;
-    plan->smem_bytes = kp == 32 ? k2::Smem<32>::alloc : k2::Smem<64>::alloc;
+    // LIST mode needs every split resident at once (one wave), j = ceil(kp / nsplits) <= 8 rows vouched
+    // per split, and at least two tiles per split so that every split can vouch for its j rows early.
+    int j = (kp + ns - 1) / ns;
+    plan->list_mode = 0;
+    if (plan->nq_tiles * ns <= kNumSMs) {
+        int ns_list = ns;
+        if (ntiles < 2 * (int64_t)ns_list) ns_list = (int)(ntiles / 2);
+        if (ns_list >= 2 && (kp + ns_list - 1) / ns_list <= k2::JSLOTS) {
+            plan->list_mode = 1;
+            plan->nsplits = ns = ns_list;
+            j = (kp + ns - 1) / ns;
+        }
+    }
+    plan->list_j = j;
+    plan->list_g = (kp + j - 1) / j;
+    plan->list_cap = k2::LIST_CAP;
     return B2F_OK;
 }
 
 int launch_tensor_scan(const __nv_bfloat16* scan, int64_t dpad, const float* norms, int64_t n, int metric,
                        const __nv_bfloat16* qb, int nq, int nq_pad, const TensorScanPlan& plan, float* pk, int32_t* pi,
-                       cudaStream_t st) {
+                       const TensorScanLists& lists, cudaStream_t st) {
     CUtensorMap mq, mx;
     B2F_TRY(k2::make_map(&mq, qb, (uint64_t)dpad, (uint64_t)nq_pad, (uint64_t)dpad, k2::BM));
     B2F_TRY(k2::make_map(&mx, scan, (uint64_t)dpad, (uint64_t)n, (uint64_t)dpad, k2::BN));
     const int kblocks = (int)(dpad / k2::BK);
     const bool l2 = metric == B2F_METRIC_L2;
+    k2::ListArgs la{};
+    if (plan.list_mode) {
+        la.shared_thr = lists.shared_thr;
+        la.cand = reinterpret_cast<uint2*>(lists.cand);
+        la.counts = lists.counts;
+        la.j = plan.list_j;
+        la.g = plan.list_g;
+        // "no information yet": 0x7f7f7f7f = 3.39e38, above every admissible key
+        B2F_CUDA(cudaMemsetAsync(lists.shared_thr, 0x7f, (size_t)nq_pad * plan.nsplits * sizeof(float), st));  // [split][query]
+        return l2 ? k2::launch_k2<0, true, true>(mq, mx, norms, n, nq, kblocks, plan, pk, pi, la, st)
+                  : k2::launch_k2<0, false, true>(mq, mx, norms, n, nq, kblocks, plan, pk, pi, la, st);
+    }
     if (plan.kp == 32)
-        return l2 ? k2::launch_k2<32, true>(mq, mx, norms, n, nq, kblocks, plan, pk, pi, st)
-                  : k2::launch_k2<32, false>(mq, mx, norms, n, nq, kblocks, plan, pk, pi, st);
+        return l2 ? k2::launch_k2<32, true, false>(mq, mx, norms, n, nq, kblocks, plan, pk, pi, la, st)
+                  : k2::launch_k2<32, false, false>(mq, mx, norms, n, nq, kblocks, plan, pk, pi, la, st);
     if (plan.kp == 64)
-        return l2 ? k2::launch_k2<64, true>(mq, mx, norms, n, nq, kblocks, plan, pk, pi, st)
-                  : k2::launch_k2<64, false>(mq, mx, norms, n, nq, kblocks, plan, pk, pi, st);
+        return l2 ? k2::launch_k2<64, true, false>(mq, mx, norms, n, nq, kblocks, plan, pk, pi, la, st)
+                  : k2::launch_k2<64, false, false>(mq, mx, norms, n, nq, kblocks, plan, pk, pi, la, st);
     set_error("tensor scan: k' = %d not supported", plan.kp);
     return B2F_EINVAL;
+}
+
+int launch_merge_lists(const TensorScanLists& lists, int nq, const TensorScanPlan& plan, float* ck, int32_t* ci,
+                       int32_t* ovf, cudaStream_t st) {
+    if (nq <= 0) return B2F_OK;
+    const size_t smem = (size_t)(k2::MERGE_MAX + plan.kp) * 8;
+    static bool configured = false;
+    if (!configured) {
+        B2F_CUDA(cudaFuncSetAttribute(k2::merge_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem + 1024));
+        configured = true;
+    }
+    k2::merge_lists_kernel<<<nq, k2::MERGE_THREADS, smem, st>>>(reinterpret_cast<const uint2*>(lists.cand), lists.counts,
+                                                               plan.nsplits, plan.kp, ck, ci, ovf);
+    B2F_CUDA(cudaGetLastError());
+    return B2F_OK;
 }
 
 }  // namespace b2f

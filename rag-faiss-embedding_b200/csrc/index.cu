@@ -578,7 +578,13 @@ int b2f_index_search(b2f_index* ix, int64_t nq64, const float* q, int64_t k64, f
     if (algo == B2F_ALGO_TENSOR) {
         const size_t nq_pad = (size_t)plan.nq_tiles * 128;
         need += align_up(nq_pad * ix->dpad * 2, 256) + 2 * align_up(nq_pad * 4, 256);
-        need += 2 * align_up(nq_pad * plan.nsplits * kp * 4, 256);  // partial lists
+        if (plan.list_mode) {
+            need += align_up(nq_pad * plan.nsplits * 4, 256) * 2;                       // shared thresholds + counts
+            need += align_up(nq_pad * plan.nsplits * (size_t)plan.list_cap * 8, 256);   // candidate lists
+            need += align_up((size_t)nq * 4, 256);                                      // overflow flags
+        } else {
+            need += 2 * align_up(nq_pad * plan.nsplits * kp * 4, 256);  // partial lists
+        }
         need += 2 * align_up((size_t)nq * kp * 4, 256);             // merged coarse
         need += 2 * align_up((size_t)nq * k * 4, 256);              // exact
         need += align_up((size_t)nq * 4, 256) + 256;                // fail list + count
@@ -616,22 +622,36 @@ int b2f_index_search(b2f_index* ix, int64_t nq64, const float* q, int64_t k64, f
         __nv_bfloat16* qb = bump.take<__nv_bfloat16>((size_t)nq_pad * ix->dpad);
         float* qnorm = bump.take<float>(nq_pad);
         float* qerr = bump.take<float>(nq_pad);
-        float* pk = bump.take<float>((size_t)nq_pad * plan.nsplits * kp);
-        int32_t* pi = bump.take<int32_t>((size_t)nq_pad * plan.nsplits * kp);
+        float* pk = nullptr;
+        int32_t* pi = nullptr;
+        TensorScanLists lists{};
+        int32_t* ovf = nullptr;
+        if (plan.list_mode) {
+            lists.shared_thr = bump.take<float>((size_t)nq_pad * plan.nsplits);
+            lists.counts = bump.take<int32_t>((size_t)nq_pad * plan.nsplits);
+            lists.cand = bump.take<uint2>((size_t)nq_pad * plan.nsplits * plan.list_cap);
+            ovf = bump.take<int32_t>(nq);
+        } else {
+            pk = bump.take<float>((size_t)nq_pad * plan.nsplits * kp);
+            pi = bump.take<int32_t>((size_t)nq_pad * plan.nsplits * kp);
+        }
         float* ck = bump.take<float>((size_t)nq * kp);
         int32_t* ci = bump.take<int32_t>((size_t)nq * kp);
         float* xk = bump.take<float>((size_t)nq * k);
         int32_t* xi = bump.take<int32_t>((size_t)nq * k);
         int32_t* fail_list = bump.take<int32_t>(nq);
-        int32_t* fail_count = bump.take<int32_t>(1);
+        int32_t* fail_count = bump.take<int32_t>(2);
         B2F_TRY(refresh_host_stats(ix, st));
-        B2F_CUDA(cudaMemsetAsync(fail_count, 0, 4, st));
+        B2F_CUDA(cudaMemsetAsync(fail_count, 0, 8, st));
         B2F_TRY(launch_prep_queries(qd, nq, nq_pad, ix->d, qb, ix->dpad, qnorm, qerr, st));
         if (profile) B2F_CUDA(cudaEventRecord(get_event(ix, ev_main), st));
-        B2F_TRY(launch_tensor_scan(ix->scan, ix->dpad, ix->norms, ix->ntotal, ix->metric, qb, nq, nq_pad, plan, pk, pi, st));
+        B2F_TRY(launch_tensor_scan(ix->scan, ix->dpad, ix->norms, ix->ntotal, ix->metric, qb, nq, nq_pad, plan, pk, pi, lists, st));
         if (profile) B2F_CUDA(cudaEventRecord(get_event(ix, ev_main + 1), st));
         n_main = 1;
-        B2F_TRY(launch_merge_parts(pk, pi, nq, plan.nsplits, kp, kp, ck, ci, st));
+        if (plan.list_mode)
+            B2F_TRY(launch_merge_lists(lists, nq, plan, ck, ci, ovf, st));
+        else
+            B2F_TRY(launch_merge_parts(pk, pi, nq, plan.nsplits, kp, kp, ck, ci, st));
         RerankArgs ra{};
         ra.rows_f32 = ix->storage == B2F_STORE_F32 ? ix->rows_f32 : nullptr;
         ra.rows_bf16 = ix->scan;
@@ -650,6 +670,7 @@ int b2f_index_search(b2f_index* ix, int64_t nq64, const float* q, int64_t k64, f
         ra.max_row_norm = sqrtf(ix->host_stats[0]);
         ra.max_row_err = ix->storage == B2F_STORE_F32 ? sqrtf(ix->host_stats[1]) : 0.f;
         ra.certify = certify;
+        ra.overflow = ovf;
         ra.out_key = xk;
         ra.out_id = xi;
         ra.fail_list = fail_list;
@@ -658,12 +679,13 @@ int b2f_index_search(b2f_index* ix, int64_t nq64, const float* q, int64_t k64, f
         B2F_TRY(launch_finalize(xk, xi, nq, k, k, ix->metric, P.id_offset, nullptr, Dd, Id, st));
         ix->st.launches += 5;
         ix->st.last_launches += 5;
-        if (certify) {
+        if (certify || plan.list_mode) {
             B2F_TRY(ensure_pinned(ix, 4096));
             int32_t* hcount = reinterpret_cast<int32_t*>(ix->pinned);
-            B2F_CUDA(cudaMemcpyAsync(hcount, fail_count, 4, cudaMemcpyDeviceToHost, st));
+            B2F_CUDA(cudaMemcpyAsync(hcount, fail_count, 8, cudaMemcpyDeviceToHost, st));
             B2F_CUDA(cudaStreamSynchronize(st));
-            const int nfail = *hcount;
+            const int nfail = hcount[0];
+            ix->st.overflow_queries += hcount[1];
             if (nfail > 0) {
                 ix->st.fallback_queries += nfail;
                 int dummy = 0;

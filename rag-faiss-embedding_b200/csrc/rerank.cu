@@ -90,9 +90,12 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankArgs a) {
     }
     // kp < k cannot happen (host guarantees kp >= k)
     __syncthreads();
-    if (threadIdx.x == 0 && a.certify) {
+    const bool overflowed = a.overflow && a.overflow[q];
+    if (threadIdx.x == 0 && (a.certify || overflowed)) {
         bool certified;
-        if (s_nvalid < a.kp) {
+        if (overflowed) {
+            certified = false;  // some candidates were dropped: only the exact scan can answer
+        } else if (s_nvalid < a.kp) {
             certified = true;  // every row of the index is already a candidate
         } else {
             const float tau = s_tau;                               // exact k-th best key
@@ -114,6 +117,7 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankArgs a) {
         if (!certified) {
             const int slot = atomicAdd(a.fail_count, 1);
             a.fail_list[slot] = q;
+            if (overflowed) atomicAdd(a.fail_count + 1, 1);
         }
     }
 }

@@ -188,6 +188,24 @@ def test_tensor_hard_inputs(m):
     assert (I >= 0).all() and (np.diff(D, axis=1) <= 1e-6).all()
 
 
+def test_tensor_list_overflow_falls_back(m):
+    """Adversarial order: every later row is closer to the queries than all earlier ones, so every row
+    passes the running threshold and the per-(query, split) candidate lists overflow.  The overflow
+    must be detected and those queries answered by the exact scan."""
+    rng = np.random.default_rng(11)
+    n, d, nq, k = 40000, 128, 20, 10
+    q0 = rng.standard_normal(d).astype(np.float32)
+    dirs = rng.standard_normal((n, d)).astype(np.float32)
+    dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    radius = np.linspace(30.0, 1.0, n, dtype=np.float32)[:, None]     # strictly shrinking distance to q0
+    xb = (q0[None, :] + dirs * radius).astype(np.float32)
+    xq = (q0[None, :] + rng.standard_normal((nq, d)).astype(np.float32) * 1e-3).astype(np.float32)
+    ix = _make(m, xb, 1).set_search_params(algo=m.ALGO_TENSOR)
+    D, I = ix.search(xq, k)
+    _check(D, I, *orc.np_search_f64(xb, xq, k, 1), 1)
+    assert ix.stats()["fallback_queries"] > 0
+
+
 def test_auto_dispatch(m):
     xb = orc.c_synth_rows(1, 0, 4000, 128)
     ix = _make(m, xb, 1)

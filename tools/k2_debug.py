@@ -49,7 +49,7 @@ def main():
             ix.set_search_params(certify=True)
             D, I = ix.search(xq, k)
             r2 = orc.recall_and_errors(D, I, D_ref, I_ref, metric)
-            print(f"   certified: recall={r2['recall']:.4f} idmis={r2['id_mismatch']} fallback_queries={ix.stats()['fallback_queries']}",
+            print(f"   certified: recall={r2['recall']:.4f} idmis={r2['id_mismatch']} fallback_queries={ix.stats()['fallback_queries']} overflow={ix.stats()['overflow_queries']}",
                   flush=True)
 
 
