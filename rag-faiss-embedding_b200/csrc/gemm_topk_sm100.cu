@@ -125,6 +125,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
+    uint32_t v;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
+    return v;
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -328,6 +333,22 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         const bool active = qrow < nq;
         const uint32_t lane_taddr = tmem_base + ((uint32_t)(wq * 32) << 16);
 
+        // Hot loop (both modes): 32 accumulator columns per tcgen05.ld, double buffered; per value one
+        // FFMA + one compare + one predicated OR into a bit mask.  Survivors are rare, so the cold path
+        // is a warp-uniform loop over the union of the lanes' masks that re-reads the one column with
+        // tcgen05.ld.x1 -- nothing is unrolled 32x, which keeps the whole epilogue inside the
+        // instruction cache (ncu: the unrolled version stalled 46% of issue slots on no_instruction).
+        auto chunk_mask = [&](const uint32_t (&r)[32], const float* tbc, float thr) -> uint32_t {
+            uint32_t mask = 0;
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                const float sdot = __uint_as_float(r[j]);
+                const float key = L2 ? fmaf(-2.f, sdot, tbc[j]) : tbc[j] - sdot;
+                if (LIST ? (key <= thr) : (key < thr)) mask |= 1u << j;
+            }
+            return mask;
+        };
+
         if constexpr (LIST) {
             // ---- LIST mode: shared cross-split threshold + append-only candidate lists -----------------
             const float kInf = __int_as_float(0x7f800000);
@@ -346,18 +367,60 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                     __stcg(gq + (int64_t)split * gstride, pub);
                 }
                 float t = -kInf;
-                for (int i0 = 0; i0 < la.g; i0 += 8) {  // 8 independent L2 loads in flight
-                    float v[8];
+#pragma unroll 1
+                for (int i0 = 0; i0 < la.g; i0 += 16) {  // 16 independent L2 loads in flight
+                    float v[16];
 #pragma unroll
-                    for (int u = 0; u < 8; u++) {
+                    for (int u = 0; u < 16; u++) {
                         int s2 = split + i0 + u;
                         if (s2 >= nsplits) s2 -= nsplits;
                         v[u] = (i0 + u < la.g) ? __ldcg(gq + (int64_t)s2 * gstride) : -kInf;
                     }
 #pragma unroll
-                    for (int u = 0; u < 8; u++) t = fmaxf(t, v[u]);
+                    for (int u = 0; u < 16; u++) t = fmaxf(t, v[u]);
                 }
                 thr = t;
+            };
+            auto process = [&](const uint32_t (&r)[32], int t, int c, uint32_t chunk_taddr, const float* tbc, int32_t rowc) {
+                // refresh schedule: thresholds move like 1/rows_seen, so consult the other splits often
+                // at the start and rarely later
+                const bool do_refresh = t == 0 || (t == 1 && (c & 1) == 0) ||
+                                        (c == 0 && (t < 8 || (t < 32 && (t & 3) == 0) || (t & 15) == 0));
+                if (active && do_refresh) {
+                    refresh();
+                    if (t == 0 && c == 1) {
+                        // Every split has now seen 32 rows and published.  CTAs start a few microseconds
+                        // apart; wait (bounded -- never a hard dependency) for the slowest of the g splits
+                        // we consult instead of appending blindly into the list meanwhile.
+                        for (int spin = 0; spin < 64 && thr > 1.0e38f; spin++) {
+                            __nanosleep(256);
+                            refresh();
+                        }
+                    }
+                }
+                const uint32_t mask = active ? chunk_mask(r, tbc, thr) : 0u;
+                uint32_t um = __reduce_or_sync(kFull, mask);
+                while (um) {
+                    const int j = __ffs(um) - 1;
+                    um &= um - 1;
+                    const uint32_t v = tmem_ld1(chunk_taddr + (uint32_t)j);
+                    tmem_ld_wait();
+                    if (mask & (1u << j)) {
+                        const float sdot = __uint_as_float(v);
+                        const float key = L2 ? fmaf(-2.f, sdot, tbc[j]) : tbc[j] - sdot;
+                        if (cnt < LIST_CAP) mylist[cnt] = make_uint2(__float_as_uint(key), (uint32_t)(rowc + j));
+                        cnt++;
+                        if (key < best[JSLOTS - 1]) {
+                            best[JSLOTS - 1] = key;
+#pragma unroll
+                            for (int i = JSLOTS - 1; i > 0; i--) {
+                                const float lo = fminf(best[i - 1], best[i]), hi = fmaxf(best[i - 1], best[i]);
+                                best[i - 1] = lo;
+                                best[i] = hi;
+                            }
+                        }
+                    }
+                }
             };
             for (int t = 0; t < my_tiles; t++) {
                 const int acc = t & 1;
@@ -368,51 +431,16 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 const int32_t row0 = (int32_t)((t_begin + t) * BN);
                 const float* tb = bias + acc * BN;
                 const uint32_t tile_taddr = lane_taddr + (uint32_t)(acc * BN);
-                uint32_t r[2][32];
-                tmem_ld32(tile_taddr, r[0]);
-#pragma unroll
-                for (int c = 0; c < BN / 32; c++) {
+                uint32_t ra[32], rb[32];
+                tmem_ld32(tile_taddr, ra);
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; c += 2) {
                     tmem_ld_wait();
-                    if (c + 1 < BN / 32) tmem_ld32(tile_taddr + (uint32_t)((c + 1) * 32), r[(c + 1) & 1]);
-                    if (active) {
-                        if (t < 2 || c == 0) refresh();  // every chunk while the threshold is still settling
-                        if (t == 0 && c == 1) {
-                            // Every split has now seen 32 rows and published.  CTAs start a few microseconds
-                            // apart; wait (bounded -- never a hard dependency) for the slowest of the g
-                            // splits we consult instead of appending blindly into the list meanwhile.
-                            for (int spin = 0; spin < 64 && thr > 1.0e38f; spin++) {
-                                __nanosleep(256);
-                                refresh();
-                            }
-                        }
-                        uint32_t mask = 0;
-#pragma unroll
-                        for (int j = 0; j < 32; j++) {
-                            const float sdot = __uint_as_float(r[c & 1][j]);
-                            const float key = L2 ? fmaf(-2.f, sdot, tb[c * 32 + j]) : tb[c * 32 + j] - sdot;
-                            if (key <= thr) mask |= 1u << j;
-                        }
-                        if (mask) {
-#pragma unroll
-                            for (int j = 0; j < 32; j++) {
-                                if (mask & (1u << j)) {
-                                    const float sdot = __uint_as_float(r[c & 1][j]);
-                                    const float key = L2 ? fmaf(-2.f, sdot, tb[c * 32 + j]) : tb[c * 32 + j] - sdot;
-                                    if (cnt < LIST_CAP) mylist[cnt] = make_uint2(__float_as_uint(key), (uint32_t)(row0 + c * 32 + j));
-                                    cnt++;
-                                    if (key < best[JSLOTS - 1]) {
-                                        best[JSLOTS - 1] = key;
-#pragma unroll
-                                        for (int i = JSLOTS - 1; i > 0; i--) {
-                                            const float lo = fminf(best[i - 1], best[i]), hi = fmaxf(best[i - 1], best[i]);
-                                            best[i - 1] = lo;
-                                            best[i] = hi;
-                                        }
-                                    }
-                                }
-                            }
-                        }
-                    }
+                    tmem_ld32(tile_taddr + (uint32_t)((c + 1) * 32), rb);
+                    process(ra, t, c, tile_taddr + (uint32_t)(c * 32), tb + c * 32, row0 + c * 32);
+                    tmem_ld_wait();
+                    if (c + 2 < BN / 32) tmem_ld32(tile_taddr + (uint32_t)((c + 2) * 32), ra);
+                    process(rb, t, c + 1, tile_taddr + (uint32_t)((c + 1) * 32), tb + (c + 1) * 32, row0 + (c + 1) * 32);
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -434,16 +462,24 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 tc_fence_after();
                 const int32_t row0 = (int32_t)((t_begin + t) * BN);
                 const float* tb = bias + acc * BN;
+                const uint32_t tile_taddr = lane_taddr + (uint32_t)(acc * BN);
 #pragma unroll 1
                 for (int c = 0; c < BN / 32; c++) {
                     uint32_t r[32];
-                    tmem_ld32(lane_taddr + (uint32_t)(acc * BN + c * 32), r);
+                    tmem_ld32(tile_taddr + (uint32_t)(c * 32), r);
                     tmem_ld_wait();
-                    if (active) {
-#pragma unroll
-                        for (int j = 0; j < 32; j++) {
-                            const float sdot = __uint_as_float(r[j]);
-                            const float key = L2 ? fmaf(-2.f, sdot, tb[c * 32 + j]) : tb[c * 32 + j] - sdot;
+                    const float* tbc = tb + c * 32;
+                    const uint32_t mask = active ? chunk_mask(r, tbc, thr) : 0u;
+                    uint32_t um = __reduce_or_sync(kFull, mask);
+                    while (um) {
+                        const int j = __ffs(um) - 1;
+                        um &= um - 1;
+                        const uint32_t v = tmem_ld1(tile_taddr + (uint32_t)(c * 32 + j));
+                        tmem_ld_wait();
+                        if (mask & (1u << j)) {
+                            const float sdot = __uint_as_float(v);
+                            const float key = L2 ? fmaf(-2.f, sdot, tbc[j]) : tbc[j] - sdot;
+                            // the mask was computed with the threshold of the chunk start: re-test
                             if (key < thr) thr = heap_push<KP>(heap_k, heap_i, tid, key, row0 + c * 32 + j);
                         }
                     }
@@ -479,46 +515,68 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 }
 
 // ---- K3b: per query, select the k' best of the S variable-length candidate lists ----------------------
-// One CTA per query.  Candidates become 64-bit composites (order-preserving key bits << 32 | row id);
-// the k'-th smallest composite is found by bisection on the 64-bit value (64 counting passes over
-// shared memory), the <= k' survivors are rank-sorted.  Output: ck/ci [nq][kp] ascending, padded with
-// (FLT_MAX,-1).  ovf[q] = 1 when a list overflowed (the query is then re-run by the exact scan).
-constexpr int MERGE_THREADS = 256;
-constexpr int MERGE_MAX = 12288;  // composites held in shared memory (96 KB)
+// One CTA per query.  Candidates become 64-bit composites (order-preserving key bits << 32 | row id) in
+// shared memory; the k'-th smallest is found by bisection (one __syncthreads per step: first over the 32
+// key bits, then -- only when equal keys straddle the cut -- over the 32 id bits), the k' survivors are
+// rank-sorted.  Output: ck/ci [nq][kp] ascending, padded with (FLT_MAX,-1).  ovf[q] = 1 when a list
+// overflowed (the query is then re-run by the exact scan).
+constexpr int MERGE_THREADS = 128;
+constexpr int MERGE_MAX = 12288;  // composites held in shared memory (96 KB) at most
+
+__device__ __forceinline__ int block_count_le(const unsigned long long* comp, int M, unsigned long long bound, int* s_cnt,
+                                              int it, int tid, int lane) {
+    if (tid == 0) s_cnt[(it + 1) % 3] = 0;  // for the next step
+    int c = 0;
+    for (int i = tid; i < M; i += MERGE_THREADS) c += comp[i] <= bound ? 1 : 0;
+    c = __reduce_add_sync(kFull, c);
+    if (lane == 0 && c) atomicAdd(&s_cnt[it % 3], c);
+    __syncthreads();
+    return s_cnt[it % 3];
+}
 
 __global__ void __launch_bounds__(MERGE_THREADS)
-merge_lists_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ counts, int nsplits, int kp,
+merge_lists_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ counts, int nsplits, int kp, int cap_entries,
                    float* __restrict__ ck, int32_t* __restrict__ ci, int32_t* __restrict__ ovf) {
-    extern __shared__ __align__(16) unsigned long long comp[];  // [MERGE_MAX] + survivors [kp]
+    extern __shared__ __align__(16) unsigned long long comp[];  // [cap_entries] + survivors [kp]
     __shared__ int s_off[kNumSMs + 2];
-    __shared__ int s_count;
+    __shared__ int s_cnt[3];
     __shared__ int s_nsurv;
     __shared__ int s_ovf;
-    unsigned long long* surv = comp + MERGE_MAX;
+    unsigned long long* surv = comp + cap_entries;
     const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) {
-        int tot = 0, o = 0;
-        for (int s = 0; s < nsplits; s++) {
-            int c = counts[(int64_t)q * nsplits + s];
+    if (warp == 0) {
+        // exclusive prefix sum of the (clamped) list lengths, 32 splits at a time
+        int run = 0, o = 0;
+        for (int s0 = 0; s0 < nsplits; s0 += 32) {
+            const int s = s0 + lane;
+            int c = s < nsplits ? counts[(int64_t)q * nsplits + s] : 0;
             if (c > LIST_CAP) {
                 c = LIST_CAP;
                 o = 1;
             }
-            s_off[s] = tot;
-            tot += c;
-            if (tot > MERGE_MAX) {
-                tot = MERGE_MAX;
-                o = 1;
+            int incl = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int up = __shfl_up_sync(kFull, incl, d);
+                if (lane >= d) incl += up;
             }
+            if (s < nsplits) s_off[s] = run + incl - c;
+            run += __shfl_sync(kFull, incl, 31);
         }
-        s_off[nsplits] = tot;
-        s_ovf = o;
-        s_nsurv = 0;
+        o = __reduce_or_sync(kFull, o);
+        if (lane == 0) {
+            s_off[nsplits] = run;
+            s_ovf = (o || run > cap_entries) ? 1 : 0;
+            s_nsurv = 0;
+            s_cnt[0] = 0;
+        }
     }
     __syncthreads();
-    const int M = s_off[nsplits];
+    const int M = s_off[nsplits] < cap_entries ? s_off[nsplits] : cap_entries;
     for (int s = warp; s < nsplits; s += MERGE_THREADS / 32) {
-        const int o = s_off[s], c = s_off[s + 1] - o;
+        const int o = s_off[s];
+        int c = s_off[s + 1] - o;
+        if (o + c > M) c = M - o > 0 ? M - o : 0;
         const uint2* src = cand + ((int64_t)q * nsplits + s) * LIST_CAP;
         for (int i = lane; i < c; i += 32) {
             const uint2 e = src[i];
@@ -528,22 +586,28 @@ merge_lists_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ c
     __syncthreads();
     unsigned long long T = ~0ull;
     if (M > kp) {
-        unsigned long long lo = 0, hi = ~0ull;
+        int it = 0;
+        // smallest 32-bit key K with count(key <= K) >= kp
+        unsigned int lo = 0, hi = 0xffffffffu;
         while (lo < hi) {
-            const unsigned long long mid = lo + ((hi - lo) >> 1);
-            if (tid == 0) s_count = 0;
-            __syncthreads();
-            int c = 0;
-            for (int i = tid; i < M; i += MERGE_THREADS) c += comp[i] <= mid ? 1 : 0;
-            c = __reduce_add_sync(kFull, c);
-            if (lane == 0 && c) atomicAdd(&s_count, c);
-            __syncthreads();
-            const int total = s_count;
-            __syncthreads();
+            const unsigned int mid = lo + ((hi - lo) >> 1);
+            const int total = block_count_le(comp, M, ((unsigned long long)mid << 32) | 0xffffffffull, s_cnt, it++, tid, lane);
             if (total >= kp) hi = mid;
             else lo = mid + 1;
         }
-        T = lo;
+        const unsigned long long kbits = (unsigned long long)lo << 32;
+        T = kbits | 0xffffffffull;
+        if (block_count_le(comp, M, T, s_cnt, it++, tid, lane) > kp) {
+            // equal keys straddle the cut: take the lowest ids among them
+            unsigned int ilo = 0, ihi = 0xffffffffu;
+            while (ilo < ihi) {
+                const unsigned int mid = ilo + ((ihi - ilo) >> 1);
+                const int total = block_count_le(comp, M, kbits | mid, s_cnt, it++, tid, lane);
+                if (total >= kp) ihi = mid;
+                else ilo = mid + 1;
+            }
+            T = kbits | ilo;
+        }
     }
     for (int i = tid; i < M; i += MERGE_THREADS) {
         const unsigned long long v = comp[i];
@@ -687,14 +751,17 @@ int launch_tensor_scan(const __nv_bfloat16* scan, int64_t dpad, const float* nor
 int launch_merge_lists(const TensorScanLists& lists, int nq, const TensorScanPlan& plan, float* ck, int32_t* ci,
                        int32_t* ovf, cudaStream_t st) {
     if (nq <= 0) return B2F_OK;
-    const size_t smem = (size_t)(k2::MERGE_MAX + plan.kp) * 8;
-    static bool configured = false;
-    if (!configured) {
-        B2F_CUDA(cudaFuncSetAttribute(k2::merge_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem + 1024));
-        configured = true;
+    int cap_entries = plan.nsplits * k2::LIST_CAP;
+    if (cap_entries > k2::MERGE_MAX) cap_entries = k2::MERGE_MAX;
+    const size_t smem = (size_t)(cap_entries + plan.kp) * 8;
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        B2F_CUDA(cudaFuncSetAttribute(k2::merge_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)((k2::MERGE_MAX + 64) * 8)));
+        configured = (size_t)(k2::MERGE_MAX + 64) * 8;
     }
     k2::merge_lists_kernel<<<nq, k2::MERGE_THREADS, smem, st>>>(reinterpret_cast<const uint2*>(lists.cand), lists.counts,
-                                                               plan.nsplits, plan.kp, ck, ci, ovf);
+                                                               plan.nsplits, plan.kp, cap_entries, ck, ci, ovf);
     B2F_CUDA(cudaGetLastError());
     return B2F_OK;
 }
