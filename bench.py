@@ -38,6 +38,14 @@ WORKLOADS = {
                label="synthetic 1Mx384 fp32 flat L2, 1024 queries, k=10 (BASELINE configs[1])"),
     "c2_nq1": dict(n=1_000_000, d=384, nq=1, k=10, metric=1, normalize=False, storage="fp32",
                    label="synthetic 1Mx384 fp32 flat L2, 1 query, k=10 (small-batch series)"),
+    "c2_nq4": dict(n=1_000_000, d=384, nq=4, k=10, metric=1, normalize=False, storage="fp32",
+                   label="synthetic 1Mx384 fp32 flat L2, 4 queries, k=10 (small-batch series)"),
+    "c2_nq8": dict(n=1_000_000, d=384, nq=8, k=10, metric=1, normalize=False, storage="fp32",
+                   label="synthetic 1Mx384 fp32 flat L2, 8 queries, k=10 (small-batch series)"),
+    "c2_nq128": dict(n=1_000_000, d=384, nq=128, k=10, metric=1, normalize=False, storage="fp32",
+                     label="synthetic 1Mx384 fp32 flat L2, 128 queries, k=10 (small-batch series)"),
+    "c2_nq4096": dict(n=1_000_000, d=384, nq=4096, k=10, metric=1, normalize=False, storage="fp32",
+                      label="synthetic 1Mx384 fp32 flat L2, 4096 queries, k=10 (large-batch series)"),
     "c2_nq32": dict(n=1_000_000, d=384, nq=32, k=10, metric=1, normalize=False, storage="fp32",
                     label="synthetic 1Mx384 fp32 flat L2, 32 queries, k=10 (small-batch series)"),
     "c4shard": dict(n=12_500_000, d=384, nq=4096, k=10, metric=1, normalize=False, storage="bf16",
@@ -348,7 +356,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": wl["label"], "rows_total": n_global, "rows_per_gpu": rows_local, "d": d, "nq": nq, "k": k,
                        "storage": wl["storage"], "algo": {1: "scan", 2: "tensor"}.get(used_algo, "?"),
-                       "kprime": st["last_kprime"], "fallback_queries": st["fallback_queries"], "overflow_queries": st["overflow_queries"],
+                       "kprime": st["last_kprime"], "fallback_queries": st["fallback_queries"], "overflow_queries": st["overflow_queries"], "filter_survivors_per_query": round(st["last_list_entries"] / max(nq, 1), 1),
                        "l2_policy": "inputs larger than L2 (bf16 scan copy %.0f MB per GPU, L2 126 MB)" % (rows_local * dpad * 2 / 1e6),
                        "sharding": "rows, contiguous ranges; one all-gather + CUDA merge per step" if world > 1 else "single GPU"},
             "roofline": roof,

@@ -94,6 +94,7 @@ typedef struct b2f_stats {
     int64_t bytes_rows;        /* device bytes held: authoritative rows */
     int64_t bytes_scan;        /* device bytes held: bf16 scan copy + norms */
     int64_t overflow_queries;  /* subset of fallback_queries caused by a candidate-list overflow */
+    int64_t last_list_entries; /* rows that survived the fused threshold filter in the last tensor-path search */
 } b2f_stats;
 
 /* ---- lifecycle -------------------------------------------------------------------------------

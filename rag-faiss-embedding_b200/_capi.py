@@ -49,6 +49,7 @@ class Stats(ctypes.Structure):
         ("bytes_rows", ctypes.c_int64),
         ("bytes_scan", ctypes.c_int64),
         ("overflow_queries", ctypes.c_int64),
+        ("last_list_entries", ctypes.c_int64),
     ]
 
     def as_dict(self):

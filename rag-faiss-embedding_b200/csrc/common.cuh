@@ -234,6 +234,6 @@ int launch_tensor_scan(const __nv_bfloat16* scan, int64_t dpad, const float* nor
                        int32_t* pi, const TensorScanLists& lists, cudaStream_t st);
 // K3b: per query, the kp best of the variable-length lists -> ck/ci [nq][kp]; ovf[q]=1 on list overflow
 int launch_merge_lists(const TensorScanLists& lists, int nq, const TensorScanPlan& plan, float* ck, int32_t* ci,
-                       int32_t* ovf, cudaStream_t st);
+                       int32_t* ovf, unsigned long long* total_entries, cudaStream_t st);
 
 }  // namespace b2f

@@ -44,7 +44,9 @@ constexpr int BK = 64;         // bf16 elements per stage along d: 128 bytes = o
 constexpr int UMMA_K = 16;
 constexpr int STAGES_HEAP = 3;
 constexpr int STAGES_LIST = 4;
-constexpr int LIST_CAP = 128;     // entries per (query, split) candidate list
+constexpr int STAGES_QRES = 4;    // Q-resident variant: stages hold database blocks only (32 KB each)
+constexpr int QRES_MAX_KB = 6;    // query tile kept resident in smem when dpad <= 384 (6 x 16 KB)
+constexpr int LIST_CAP_MIN = 128;  // entries per (query, split) candidate list: 128 / 256 / 512 by stream length
 constexpr int JSLOTS = 8;         // register slots for the split-local j-th best (j <= 8)
 constexpr int A_BYTES = BM * BK * 2;  // 16 KB
 constexpr int B_BYTES = BN * BK * 2;  // 32 KB
@@ -134,26 +136,29 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-template <int KP, int NST>
+template <int KP, int NST, int QKB = 0>
 struct Smem {
-    static constexpr size_t stages_off = 0;
-    static constexpr size_t heapk_off = (size_t)NST * STAGE_BYTES;
+    static constexpr size_t q_off = 0;                                   // resident query tile: QKB x 16 KB
+    static constexpr size_t stage_bytes = QKB ? (size_t)B_BYTES : (size_t)STAGE_BYTES;
+    static constexpr size_t stages_off = (size_t)QKB * A_BYTES;
+    static constexpr size_t heapk_off = stages_off + (size_t)NST * stage_bytes;
     static constexpr size_t heapi_off = heapk_off + (size_t)EPI_THREADS * KP * 4;
     static constexpr size_t bias_off = heapi_off + (size_t)EPI_THREADS * KP * 4;
     static constexpr size_t bar_off = bias_off + 2 * BN * 4;
-    static constexpr int nbars = 2 * NST + 6;
+    static constexpr int nbars = 2 * NST + 7;
     static constexpr size_t tmem_off = bar_off + nbars * 8;
     static constexpr size_t total = tmem_off + 16;
-    static constexpr size_t alloc = total + 1024;  // slack for manual 1024-byte alignment
+    static constexpr size_t alloc = total;  // the dynamic smem base is declared __align__(1024)
 };
 
 // LIST-mode arguments (all device pointers)
 struct ListArgs {
     float* shared_thr;   // [nq_pad][nsplits]  each split's published j-th best key (init: huge)
-    uint2* cand;         // [nq_pad * nsplits][LIST_CAP]  (key bits, row id)
-    int32_t* counts;     // [nq_pad * nsplits]  entries appended (may exceed LIST_CAP => overflow)
+    uint2* cand;         // [nq_pad * nsplits][cap]  (key bits, row id)
+    int32_t* counts;     // [nq_pad * nsplits]  entries appended (may exceed cap => overflow)
     int j;               // rows each split vouches for
     int g;               // splits consulted: g * j >= k'
+    int cap;             // entries per list
 };
 
 // thread-private max-heap in shared memory, element j of thread t at [j * 128 + t].
@@ -202,15 +207,17 @@ __device__ __forceinline__ float dec_key(uint32_t e) {
     return __uint_as_float((e & 0x80000000u) ? (e & 0x7fffffffu) : ~e);
 }
 
-template <int KP, bool L2, bool LIST>
+template <int KP, bool L2, bool LIST, bool QRES>
 __global__ void __launch_bounds__(THREADS, 1)
 tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
                    const float* __restrict__ norms, int64_t n, int nq, int kblocks, int nq_tiles, int nsplits,
                    float* __restrict__ pk, int32_t* __restrict__ pi, ListArgs la) {
-    constexpr int STAGES = LIST ? STAGES_LIST : STAGES_HEAP;
-    using L = Smem<LIST ? 0 : KP, STAGES>;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    static_assert(!QRES || LIST, "the Q-resident variant exists for LIST mode only");
+    constexpr int STAGES = QRES ? STAGES_QRES : (LIST ? STAGES_LIST : STAGES_HEAP);
+    using L = Smem<LIST ? 0 : KP, STAGES, QRES ? QRES_MAX_KB : 0>;
+    constexpr uint32_t kStageBytes = (uint32_t)L::stage_bytes;
+    extern __shared__ __align__(1024) uint8_t smem[];  // SWIZZLE_128B tiles need 1024-byte alignment
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
     float* heap_k = reinterpret_cast<float*>(smem + L::heapk_off);
     int32_t* heap_i = reinterpret_cast<int32_t*>(smem + L::heapi_off);
     float* bias = reinterpret_cast<float*>(smem + L::bias_off);
@@ -220,6 +227,7 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     uint64_t* tmem_full = bars + 2 * STAGES;       // [2]       MMA -> epilogue
     uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // [2]       epilogue -> MMA, bias loader
     uint64_t* bias_full = bars + 2 * STAGES + 4;   // [2]       bias loader -> epilogue
+    uint64_t* q_full = bars + 2 * STAGES + 6;      // [1]       resident query tile landed (QRES)
     uint32_t* tmem_base_holder = reinterpret_cast<uint32_t*>(smem + L::tmem_off);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -242,6 +250,7 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             mbar_init(&tmem_empty[a], 4);  // one arrive per epilogue warp
             mbar_init(&bias_full[a], 1);
         }
+        mbar_init(q_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -260,14 +269,19 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            if constexpr (QRES) {
+                // the whole query tile (all k-blocks) is loaded once and stays in shared memory
+                mbar_expect_tx(q_full, (uint32_t)(kblocks * A_BYTES));
+                for (int kb = 0; kb < kblocks; kb++) tma_load_2d(smem + L::q_off + (size_t)kb * A_BYTES, &map_q, kb * BK, qt * BM, q_full);
+            }
             for (int t = 0; t < my_tiles; t++) {
                 const int row0 = (int)((t_begin + t) * BN);
                 for (int kb = 0; kb < kblocks; kb++) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    uint8_t* sa = smem + (size_t)stage * STAGE_BYTES;
-                    mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-                    tma_load_2d(sa, &map_q, kb * BK, qt * BM, &full_bar[stage]);
-                    tma_load_2d(sa + A_BYTES, &map_x, kb * BK, row0, &full_bar[stage]);
+                    uint8_t* sa = smem + L::stages_off + (size_t)stage * kStageBytes;
+                    mbar_expect_tx(&full_bar[stage], kStageBytes);
+                    if constexpr (!QRES) tma_load_2d(sa, &map_q, kb * BK, qt * BM, &full_bar[stage]);
+                    tma_load_2d(sa + (QRES ? 0 : A_BYTES), &map_x, kb * BK, row0, &full_bar[stage]);
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -281,6 +295,7 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            if constexpr (QRES) mbar_wait(q_full, 0);
             for (int t = 0; t < my_tiles; t++) {
                 const int acc = t & 1;
                 const uint32_t acc_phase = (t >> 1) & 1;
@@ -290,9 +305,9 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 for (int kb = 0; kb < kblocks; kb++) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
-                    const uint64_t adesc = make_smem_desc(sa);
-                    const uint64_t bdesc = make_smem_desc(sa + A_BYTES);
+                    const uint32_t sa = smem_u32(smem + L::stages_off + (size_t)stage * kStageBytes);
+                    const uint64_t adesc = make_smem_desc(QRES ? smem_u32(smem + L::q_off + (size_t)kb * A_BYTES) : sa);
+                    const uint64_t bdesc = make_smem_desc(sa + (QRES ? 0 : A_BYTES));
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; k++) {
                         // advance both descriptors by 32 bytes (16 bf16) inside the 128-byte swizzle atom
@@ -357,7 +372,7 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             for (int i = 0; i < JSLOTS; i++) best[i] = (i < JSLOTS - la.j) ? -kInf : kInf;
             float thr = 3.0e38f, pub = kInf;  // refreshed before the first compare; never +inf (padding rows have key +inf)
             int cnt = 0;
-            uint2* mylist = la.cand + ((int64_t)(active ? qrow : 0) * nsplits + split) * LIST_CAP;
+            uint2* mylist = la.cand + ((int64_t)(active ? qrow : 0) * nsplits + split) * la.cap;
             // shared thresholds are laid out [split][query] so that a warp's loads for one split coalesce
             float* gq = la.shared_thr + (active ? qrow : 0);
             const int64_t gstride = (int64_t)nq_tiles * BM;
@@ -408,7 +423,7 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                     if (mask & (1u << j)) {
                         const float sdot = __uint_as_float(v);
                         const float key = L2 ? fmaf(-2.f, sdot, tbc[j]) : tbc[j] - sdot;
-                        if (cnt < LIST_CAP) mylist[cnt] = make_uint2(__float_as_uint(key), (uint32_t)(rowc + j));
+                        if (cnt < la.cap) mylist[cnt] = make_uint2(__float_as_uint(key), (uint32_t)(rowc + j));
                         cnt++;
                         if (key < best[JSLOTS - 1]) {
                             best[JSLOTS - 1] = key;
@@ -446,7 +461,24 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tmem_empty[acc]);
             }
-            if (active) la.counts[(int64_t)qrow * nsplits + split] = cnt;
+            if (active) {
+                // End-of-stream pruning: the final shared threshold is far tighter than the ones most
+                // entries were admitted under (the first chunk is admitted blindly), so re-filter the
+                // thread's own list in place.  Shrinks the merge input ~10x (C2: 1460 -> ~100 per query).
+                refresh();
+                const int have = cnt < la.cap ? cnt : la.cap;
+                int w = 0;
+#pragma unroll 1
+                for (int i0 = 0; i0 < have; i0 += 8) {
+                    uint2 e[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) e[u] = (i0 + u < have) ? mylist[i0 + u] : make_uint2(0x7f800000u, 0u);
+#pragma unroll
+                    for (int u = 0; u < 8; u++)
+                        if (i0 + u < have && __uint_as_float(e[u].x) <= thr) mylist[w++] = e[u];
+                }
+                la.counts[(int64_t)qrow * nsplits + split] = cnt > la.cap ? cnt : w;  // > cap marks an overflow
+            }
         } else {
             // ---- HEAP mode: thread-private max-heap of k' in shared memory ------------------------------
             for (int j = 0; j < KP; j++) {
@@ -535,8 +567,9 @@ __device__ __forceinline__ int block_count_le(const unsigned long long* comp, in
 }
 
 __global__ void __launch_bounds__(MERGE_THREADS)
-merge_lists_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ counts, int nsplits, int kp, int cap_entries,
-                   float* __restrict__ ck, int32_t* __restrict__ ci, int32_t* __restrict__ ovf) {
+merge_lists_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ counts, int nsplits, int kp, int list_cap,
+                   int cap_entries, float* __restrict__ ck, int32_t* __restrict__ ci, int32_t* __restrict__ ovf,
+                   unsigned long long* __restrict__ total_entries) {
     extern __shared__ __align__(16) unsigned long long comp[];  // [cap_entries] + survivors [kp]
     __shared__ int s_off[kNumSMs + 2];
     __shared__ int s_cnt[3];
@@ -550,8 +583,8 @@ merge_lists_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ c
         for (int s0 = 0; s0 < nsplits; s0 += 32) {
             const int s = s0 + lane;
             int c = s < nsplits ? counts[(int64_t)q * nsplits + s] : 0;
-            if (c > LIST_CAP) {
-                c = LIST_CAP;
+            if (c > list_cap) {
+                c = list_cap;
                 o = 1;
             }
             int incl = c;
@@ -566,6 +599,7 @@ merge_lists_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ c
         o = __reduce_or_sync(kFull, o);
         if (lane == 0) {
             s_off[nsplits] = run;
+            if (total_entries) atomicAdd(total_entries, (unsigned long long)run);
             s_ovf = (o || run > cap_entries) ? 1 : 0;
             s_nsurv = 0;
             s_cnt[0] = 0;
@@ -573,14 +607,28 @@ merge_lists_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ c
     }
     __syncthreads();
     const int M = s_off[nsplits] < cap_entries ? s_off[nsplits] : cap_entries;
-    for (int s = warp; s < nsplits; s += MERGE_THREADS / 32) {
-        const int o = s_off[s];
-        int c = s_off[s + 1] - o;
-        if (o + c > M) c = M - o > 0 ? M - o : 0;
-        const uint2* src = cand + ((int64_t)q * nsplits + s) * LIST_CAP;
-        for (int i = lane; i < c; i += 32) {
-            const uint2 e = src[i];
-            comp[o + i] = ((unsigned long long)enc_key(__uint_as_float(e.x)) << 32) | (unsigned long long)e.y;
+    // gather: flattened over all candidates so every thread has independent loads in flight; the owning
+    // list of element i is found by binary search in the prefix array (<= 8 steps in shared memory)
+    for (int i0 = tid; i0 < M; i0 += 4 * MERGE_THREADS) {
+        uint2 e[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int i = i0 + u * MERGE_THREADS;
+            e[u] = make_uint2(0u, 0u);
+            if (i < M) {
+                int lo = 0, hi = nsplits - 1;
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (s_off[mid] <= i) lo = mid;
+                    else hi = mid - 1;
+                }
+                e[u] = cand[((int64_t)q * nsplits + lo) * list_cap + (i - s_off[lo])];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int i = i0 + u * MERGE_THREADS;
+            if (i < M) comp[i] = ((unsigned long long)enc_key(__uint_as_float(e[u].x)) << 32) | (unsigned long long)e[u].y;
         }
     }
     __syncthreads();
@@ -670,11 +718,12 @@ static int make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t
     return B2F_OK;
 }
 
-template <int KP, bool L2, bool LIST>
+template <int KP, bool L2, bool LIST, bool QRES>
 static int launch_k2(const CUtensorMap& mq, const CUtensorMap& mx, const float* norms, int64_t n, int nq, int kblocks,
                      const TensorScanPlan& plan, float* pk, int32_t* pi, const ListArgs& la, cudaStream_t st) {
-    auto kern = tensor_scan_kernel<KP, L2, LIST>;
-    constexpr size_t smem = Smem<LIST ? 0 : KP, LIST ? STAGES_LIST : STAGES_HEAP>::alloc;
+    auto kern = tensor_scan_kernel<KP, L2, LIST, QRES>;
+    constexpr size_t smem = Smem<LIST ? 0 : KP, QRES ? STAGES_QRES : (LIST ? STAGES_LIST : STAGES_HEAP), QRES ? QRES_MAX_KB : 0>::alloc;
+    static_assert(smem <= 232448, "shared memory budget exceeded");
     static bool configured = false;
     if (!configured) {
         B2F_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -714,7 +763,8 @@ int plan_tensor_scan(int nq, int64_t n, int d, int kp, TensorScanPlan* plan) {
     }
     plan->list_j = j;
     plan->list_g = (kp + j - 1) / j;
-    plan->list_cap = k2::LIST_CAP;
+    // expected list length ~ 32 + (j + spread) * ln(rows per split / 32): longer streams and larger j need room
+    plan->list_cap = plan->nsplits >= 16 ? k2::LIST_CAP_MIN : (plan->nsplits >= 8 ? 2 * k2::LIST_CAP_MIN : 4 * k2::LIST_CAP_MIN);
     return B2F_OK;
 }
 
@@ -733,25 +783,29 @@ int launch_tensor_scan(const __nv_bfloat16* scan, int64_t dpad, const float* nor
         la.counts = lists.counts;
         la.j = plan.list_j;
         la.g = plan.list_g;
+        la.cap = plan.list_cap;
         // "no information yet": 0x7f7f7f7f = 3.39e38, above every admissible key
         B2F_CUDA(cudaMemsetAsync(lists.shared_thr, 0x7f, (size_t)nq_pad * plan.nsplits * sizeof(float), st));  // [split][query]
-        return l2 ? k2::launch_k2<0, true, true>(mq, mx, norms, n, nq, kblocks, plan, pk, pi, la, st)
-                  : k2::launch_k2<0, false, true>(mq, mx, norms, n, nq, kblocks, plan, pk, pi, la, st);
+        if (kblocks <= k2::QRES_MAX_KB)
+            return l2 ? k2::launch_k2<0, true, true, true>(mq, mx, norms, n, nq, kblocks, plan, pk, pi, la, st)
+                      : k2::launch_k2<0, false, true, true>(mq, mx, norms, n, nq, kblocks, plan, pk, pi, la, st);
+        return l2 ? k2::launch_k2<0, true, true, false>(mq, mx, norms, n, nq, kblocks, plan, pk, pi, la, st)
+                  : k2::launch_k2<0, false, true, false>(mq, mx, norms, n, nq, kblocks, plan, pk, pi, la, st);
     }
     if (plan.kp == 32)
-        return l2 ? k2::launch_k2<32, true, false>(mq, mx, norms, n, nq, kblocks, plan, pk, pi, la, st)
-                  : k2::launch_k2<32, false, false>(mq, mx, norms, n, nq, kblocks, plan, pk, pi, la, st);
+        return l2 ? k2::launch_k2<32, true, false, false>(mq, mx, norms, n, nq, kblocks, plan, pk, pi, la, st)
+                  : k2::launch_k2<32, false, false, false>(mq, mx, norms, n, nq, kblocks, plan, pk, pi, la, st);
     if (plan.kp == 64)
-        return l2 ? k2::launch_k2<64, true, false>(mq, mx, norms, n, nq, kblocks, plan, pk, pi, la, st)
-                  : k2::launch_k2<64, false, false>(mq, mx, norms, n, nq, kblocks, plan, pk, pi, la, st);
+        return l2 ? k2::launch_k2<64, true, false, false>(mq, mx, norms, n, nq, kblocks, plan, pk, pi, la, st)
+                  : k2::launch_k2<64, false, false, false>(mq, mx, norms, n, nq, kblocks, plan, pk, pi, la, st);
     set_error("tensor scan: k' = %d not supported", plan.kp);
     return B2F_EINVAL;
 }
 
 int launch_merge_lists(const TensorScanLists& lists, int nq, const TensorScanPlan& plan, float* ck, int32_t* ci,
-                       int32_t* ovf, cudaStream_t st) {
+                       int32_t* ovf, unsigned long long* total_entries, cudaStream_t st) {
     if (nq <= 0) return B2F_OK;
-    int cap_entries = plan.nsplits * k2::LIST_CAP;
+    int cap_entries = plan.nsplits * plan.list_cap;
     if (cap_entries > k2::MERGE_MAX) cap_entries = k2::MERGE_MAX;
     const size_t smem = (size_t)(cap_entries + plan.kp) * 8;
     static size_t configured = 0;
@@ -761,7 +815,7 @@ int launch_merge_lists(const TensorScanLists& lists, int nq, const TensorScanPla
         configured = (size_t)(k2::MERGE_MAX + 64) * 8;
     }
     k2::merge_lists_kernel<<<nq, k2::MERGE_THREADS, smem, st>>>(reinterpret_cast<const uint2*>(lists.cand), lists.counts,
-                                                               plan.nsplits, plan.kp, cap_entries, ck, ci, ovf);
+                                                               plan.nsplits, plan.kp, plan.list_cap, cap_entries, ck, ci, ovf, total_entries);
     B2F_CUDA(cudaGetLastError());
     return B2F_OK;
 }

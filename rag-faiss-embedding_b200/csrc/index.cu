@@ -640,16 +640,16 @@ int b2f_index_search(b2f_index* ix, int64_t nq64, const float* q, int64_t k64, f
         float* xk = bump.take<float>((size_t)nq * k);
         int32_t* xi = bump.take<int32_t>((size_t)nq * k);
         int32_t* fail_list = bump.take<int32_t>(nq);
-        int32_t* fail_count = bump.take<int32_t>(2);
+        int32_t* fail_count = bump.take<int32_t>(4);  // [0] uncertified, [1] overflowed, [2..3] u64 list entries
         B2F_TRY(refresh_host_stats(ix, st));
-        B2F_CUDA(cudaMemsetAsync(fail_count, 0, 8, st));
+        B2F_CUDA(cudaMemsetAsync(fail_count, 0, 16, st));
         B2F_TRY(launch_prep_queries(qd, nq, nq_pad, ix->d, qb, ix->dpad, qnorm, qerr, st));
         if (profile) B2F_CUDA(cudaEventRecord(get_event(ix, ev_main), st));
         B2F_TRY(launch_tensor_scan(ix->scan, ix->dpad, ix->norms, ix->ntotal, ix->metric, qb, nq, nq_pad, plan, pk, pi, lists, st));
         if (profile) B2F_CUDA(cudaEventRecord(get_event(ix, ev_main + 1), st));
         n_main = 1;
         if (plan.list_mode)
-            B2F_TRY(launch_merge_lists(lists, nq, plan, ck, ci, ovf, st));
+            B2F_TRY(launch_merge_lists(lists, nq, plan, ck, ci, ovf, reinterpret_cast<unsigned long long*>(fail_count + 2), st));
         else
             B2F_TRY(launch_merge_parts(pk, pi, nq, plan.nsplits, kp, kp, ck, ci, st));
         RerankArgs ra{};
@@ -682,10 +682,11 @@ int b2f_index_search(b2f_index* ix, int64_t nq64, const float* q, int64_t k64, f
         if (certify || plan.list_mode) {
             B2F_TRY(ensure_pinned(ix, 4096));
             int32_t* hcount = reinterpret_cast<int32_t*>(ix->pinned);
-            B2F_CUDA(cudaMemcpyAsync(hcount, fail_count, 8, cudaMemcpyDeviceToHost, st));
+            B2F_CUDA(cudaMemcpyAsync(hcount, fail_count, 16, cudaMemcpyDeviceToHost, st));
             B2F_CUDA(cudaStreamSynchronize(st));
             const int nfail = hcount[0];
             ix->st.overflow_queries += hcount[1];
+            ix->st.last_list_entries = *reinterpret_cast<int64_t*>(hcount + 2);
             if (nfail > 0) {
                 ix->st.fallback_queries += nfail;
                 int dummy = 0;

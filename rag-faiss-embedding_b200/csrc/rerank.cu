@@ -35,24 +35,49 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankArgs a) {
         s_nvalid = 0;
     }
     __syncthreads();
-    for (int c = warp; c < a.kp; c += kRerankThreads / 32) {
-        const int32_t id = a.cand_id[(int64_t)q * a.kp + c];
+    // 8 lanes per candidate, 4 candidates per warp, 16 per pass: every lane has independent 16-byte
+    // loads in flight, so a pass costs about one DRAM round trip instead of eight.
+    const int sub = lane >> 3, sl = lane & 7;
+    const bool vec_f32 = a.rows_f32 && (a.d & 3) == 0;
+    const bool vec_b16 = !a.rows_f32 && (a.d & 7) == 0;
+    for (int c0 = warp * 4; c0 < a.kp; c0 += (kRerankThreads / 32) * 4) {
+        const int c = c0 + sub;
+        const int32_t id = c < a.kp ? a.cand_id[(int64_t)q * a.kp + c] : -1;
         float acc = 0.f;
         if (id >= 0) {
-            if (a.rows_f32) {
+            if (vec_f32) {
                 const float* x = a.rows_f32 + (int64_t)id * a.d;
-                for (int j = lane; j < a.d; j += 32) {
+                for (int j = sl * 4; j < a.d; j += 32) {
+                    const float4 xv = *reinterpret_cast<const float4*>(x + j);
+                    const float4 qq = *reinterpret_cast<const float4*>(qv + j);
                     if (l2) {
-                        const float t = x[j] - qv[j];
-                        acc = fmaf(t, t, acc);
+                        const float t0 = xv.x - qq.x, t1 = xv.y - qq.y, t2 = xv.z - qq.z, t3 = xv.w - qq.w;
+                        acc = fmaf(t0, t0, acc); acc = fmaf(t1, t1, acc); acc = fmaf(t2, t2, acc); acc = fmaf(t3, t3, acc);
                     } else {
-                        acc = fmaf(x[j], qv[j], acc);
+                        acc = fmaf(xv.x, qq.x, acc); acc = fmaf(xv.y, qq.y, acc); acc = fmaf(xv.z, qq.z, acc); acc = fmaf(xv.w, qq.w, acc);
+                    }
+                }
+            } else if (vec_b16) {
+                const __nv_bfloat16* x = a.rows_bf16 + (int64_t)id * a.pitch_bf16;
+                for (int j = sl * 8; j < a.d; j += 64) {
+                    const uint4 w = *reinterpret_cast<const uint4*>(x + j);
+                    const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                    for (int h = 0; h < 4; h++) {
+                        const float x0 = __uint_as_float(ww[h] << 16), x1 = __uint_as_float(ww[h] & 0xffff0000u);
+                        const float q0 = qv[j + 2 * h], q1 = qv[j + 2 * h + 1];
+                        if (l2) {
+                            const float t0 = x0 - q0, t1 = x1 - q1;
+                            acc = fmaf(t0, t0, acc); acc = fmaf(t1, t1, acc);
+                        } else {
+                            acc = fmaf(x0, q0, acc); acc = fmaf(x1, q1, acc);
+                        }
                     }
                 }
             } else {
-                const __nv_bfloat16* x = a.rows_bf16 + (int64_t)id * a.pitch_bf16;
-                for (int j = lane; j < a.d; j += 32) {
-                    const float xv = __bfloat162float(x[j]);
+                for (int j = sl; j < a.d; j += 8) {
+                    const float xv = a.rows_f32 ? a.rows_f32[(int64_t)id * a.d + j]
+                                                : __bfloat162float(a.rows_bf16[(int64_t)id * a.pitch_bf16 + j]);
                     if (l2) {
                         const float t = xv - qv[j];
                         acc = fmaf(t, t, acc);
@@ -61,10 +86,11 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankArgs a) {
                     }
                 }
             }
-#pragma unroll
-            for (int s = 16; s >= 1; s >>= 1) acc += __shfl_xor_sync(kFull, acc, s);
         }
-        if (lane == 0) {
+        acc += __shfl_xor_sync(kFull, acc, 4);
+        acc += __shfl_xor_sync(kFull, acc, 2);
+        acc += __shfl_xor_sync(kFull, acc, 1);
+        if (sl == 0 && c < a.kp) {
             const bool ok = id >= 0 && !(acc != acc);  // NaN never enters (faiss heap semantics)
             ek[c] = ok ? (l2 ? acc : -acc) : FLT_MAX;
             ei[c] = ok ? id : -1;

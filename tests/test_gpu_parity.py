@@ -157,7 +157,7 @@ def test_incremental_add_and_growth(m):
 @pytest.mark.parametrize("n,d,nq,k", [
     (300, 384, 1, 10), (5000, 384, 33, 10), (20000, 384, 128, 10), (100000, 384, 200, 10),
     (7000, 768, 64, 10), (9000, 100, 130, 5), (70000, 64, 1024, 10), (4000, 384, 16, 20),
-    (256, 384, 9, 1), (257, 128, 300, 10),
+    (256, 384, 9, 1), (257, 128, 300, 10), (100000, 64, 2400, 10),
 ])
 def test_tensor_vs_oracle(m, metric, n, d, nq, k):
     xb = orc.c_synth_rows(1234, 0, n, d)
@@ -168,6 +168,8 @@ def test_tensor_vs_oracle(m, metric, n, d, nq, k):
     _check(D, I, D_ref, I_ref, metric)
     st = ix.stats()
     assert st["last_algo"] == m.ALGO_TENSOR and st["last_kprime"] in (32, 64)
+    if n >= 5000:   # random data: the fused filter must not overflow its candidate lists
+        assert st["overflow_queries"] == 0, st
 
 
 def test_tensor_hard_inputs(m):
