@@ -344,6 +344,14 @@ def main():
             ach = bytes_ / (kernel_ms * 1e-3) / 1e9
             roof = {"bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm"], "unit": "GB/s",
                     "frac": round(ach / peaks["hbm"], 4), "traffic": None, "launches_per_step": nlaunch}
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            key = f"{args.workload}|{'tensor' if used_algo == b2f.ALGO_TENSOR else 'scan'}"
+            if key in tr and world == 1:
+                roof["traffic"] = tr[key]["bytes"]
+                roof["traffic_source"] = tr[key]["capture"]
+        except Exception:
+            pass
         roof["kernel"] = "tensor_scan_kernel (K2 tcgen05)" if used_algo == b2f.ALGO_TENSOR else "scan_kernel (K1)"
         roof["kernel_ms"] = round(kernel_ms, 4)
         roof["peak_source"] = peaks["src"] + (" burst" if roof["bound"] == "tensor" else "")

@@ -560,7 +560,7 @@ int b2f_index_search(b2f_index* ix, int64_t nq64, const float* q, int64_t k64, f
     const bool profile = P.profile != 0;
 
     int algo = P.algo;
-    const int scan_max = P.scan_max_nq > 0 ? P.scan_max_nq : 8;
+    const int scan_max = P.scan_max_nq > 0 ? P.scan_max_nq : 1;
     int kp = tensor_kprime(k, P.slack);
     TensorScanPlan plan{};
     bool tensor_ok = kp <= 128 && ix->ntotal > 0 && plan_tensor_scan(nq, ix->ntotal, ix->d, kp, &plan) == B2F_OK;
