@@ -287,12 +287,12 @@ def main():
         return ms
 
     # ---- warm-up, then the device-resident timed region -------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()   # samples through warm-up, the timed region and the e2e region (GPU busy throughout)
     for _ in range(args.warmup):
         step_device()
     launches0 = ix.stats()["launches"]
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     main_ms, total_ms = [], []
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

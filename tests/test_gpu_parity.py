@@ -211,8 +211,12 @@ def test_tensor_list_overflow_falls_back(m):
 def test_auto_dispatch(m):
     xb = orc.c_synth_rows(1, 0, 4000, 128)
     ix = _make(m, xb, 1)
-    ix.search(orc.c_synth_rows(2, 0, 4, 128), 10)
+    ix.search(orc.c_synth_rows(2, 0, 1, 128), 10)     # the reference's batch size -> exact fp32 scan
     assert ix.stats()["last_algo"] == m.ALGO_SCAN
+    ix.set_search_params(scan_max_nq=8)
+    ix.search(orc.c_synth_rows(2, 0, 8, 128), 10)
+    assert ix.stats()["last_algo"] == m.ALGO_SCAN
+    ix.set_search_params(scan_max_nq=1)
     ix.search(orc.c_synth_rows(2, 0, 64, 128), 10)
     assert ix.stats()["last_algo"] == m.ALGO_TENSOR
     D, I = ix.search(orc.c_synth_rows(2, 0, 64, 128), 200)   # k' > 64: falls back to the exact scan

@@ -1,0 +1,70 @@
+"""GPU tier, N > 1: the row-sharded index over NCCL (one process per GPU) against a single-GPU index and
+the oracle.  Skipped unless at least 2 GPUs are visible (run under `gpurun --gpus 2`)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out_dir):
+    import torch
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import rag_faiss_embedding_b200 as b2f
+
+        d, n, nq, k = 128, 60001, 150, 10
+        xq = torch.from_numpy(orc.c_synth_rows(5678, 0, nq, d)).cuda()
+        for metric in (1, 0):
+            ix = b2f.ShardedIndexFlat(d, metric, device=rank)
+            ix.add_synthetic(1234, n)            # every rank generates its own slice on its own GPU
+            assert ix.ntotal == n
+            D, I = ix.search(xq, k)               # replicated queries -> identical merged result on all ranks
+            D1, I1 = ix.search(xq[:1], k)         # nq = 1 goes through the streaming scan on every shard
+            torch.cuda.synchronize()
+            np.savez(os.path.join(out_dir, f"r{rank}_m{metric}.npz"), D=D.cpu().numpy(), I=I.cpu().numpy(),
+                     D1=D1.cpu().numpy(), I1=I1.cpu().numpy(), nlocal=ix.local.ntotal)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_nccl_matches_oracle(tmp_path):
+    import torch
+    import torch.multiprocessing as mp
+
+    world = torch.cuda.device_count()
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = min(world, 8)
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    d, n, nq, k = 128, 60001, 150, 10
+    xb = orc.c_synth_rows(1234, 0, n, d)
+    xq = orc.c_synth_rows(5678, 0, nq, d)
+    for metric in (1, 0):
+        D_ref, I_ref = orc.np_search_f64(xb, xq, k, metric)
+        total = 0
+        for r in range(world):
+            z = np.load(os.path.join(tmp_path, f"r{r}_m{metric}.npz"))
+            res = orc.recall_and_errors(z["D"], z["I"], D_ref, I_ref, metric)
+            assert res["recall"] == 1.0 and res["id_mismatch"] == 0 and res["max_rel_err"] <= 1e-5, (r, metric, res)
+            res1 = orc.recall_and_errors(z["D1"], z["I1"], D_ref[:1], I_ref[:1], metric)
+            assert res1["recall"] == 1.0 and res1["id_mismatch"] == 0, (r, metric, res1)
+            total += int(z["nlocal"])
+        assert total == n
