@@ -31,6 +31,7 @@
 // Roofline: nq <= 128 -> HBM-bound, algorithmic bytes n * dpad * 2; large nq -> tensor-bound,
 // 2 * nq * n * d flop.
 #include <cuda.h>
+#include <math.h>
 
 #include "common.cuh"
 
@@ -466,7 +467,7 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 // entries were admitted under (the first chunk is admitted blindly), so re-filter the
                 // thread's own list in place.  Shrinks the merge input ~10x (C2: 1460 -> ~100 per query).
                 refresh();
-                const int have = cnt < la.cap ? cnt : la.cap;
+                const int have = cnt <= la.cap ? cnt : 0;  // an overflowed list is left as is (the query falls back)
                 int w = 0;
 #pragma unroll 1
                 for (int i0 = 0; i0 < have; i0 += 8) {
@@ -669,8 +670,8 @@ merge_lists_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ c
     for (int t = tid; t < kp; t += MERGE_THREADS) {
         if (t < ns) {
             const unsigned long long mine = surv[t];
-            int rank = 0;
-            for (int j = 0; j < ns; j++) rank += surv[j] < mine ? 1 : 0;
+            int rank = 0;  // ties broken by slot, so ranks are a permutation even if composites repeat
+            for (int j = 0; j < ns; j++) rank += (surv[j] < mine || (surv[j] == mine && j < t)) ? 1 : 0;
             ck[(int64_t)q * kp + rank] = dec_key((uint32_t)(mine >> 32));
             ci[(int64_t)q * kp + rank] = (int32_t)(uint32_t)(mine & 0xffffffffu);
         } else {
@@ -763,8 +764,16 @@ int plan_tensor_scan(int nq, int64_t n, int d, int kp, TensorScanPlan* plan) {
     }
     plan->list_j = j;
     plan->list_g = (kp + j - 1) / j;
-    // expected list length ~ 32 + (j + spread) * ln(rows per split / 32): longer streams and larger j need room
-    plan->list_cap = plan->nsplits >= 16 ? k2::LIST_CAP_MIN : (plan->nsplits >= 8 ? 2 * k2::LIST_CAP_MIN : 4 * k2::LIST_CAP_MIN);
+    // expected list length ~ 32 (blind first chunk) + (j + spread) * ln(rows per split / 32); 2.5x headroom
+    {
+        const double rows_per_split = (double)n / plan->nsplits;
+        const double expected = 32.0 + (j + 2.5) * log(rows_per_split > 64.0 ? rows_per_split / 32.0 : 2.0);
+        int cap = (int)(2.5 * expected);
+        cap = (cap + 63) / 64 * 64;
+        if (cap < k2::LIST_CAP_MIN) cap = k2::LIST_CAP_MIN;
+        if (cap > 1024) cap = 1024;
+        plan->list_cap = cap;
+    }
     return B2F_OK;
 }
 

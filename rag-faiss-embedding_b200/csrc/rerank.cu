@@ -42,7 +42,8 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankArgs a) {
     const bool vec_b16 = !a.rows_f32 && (a.d & 7) == 0;
     for (int c0 = warp * 4; c0 < a.kp; c0 += (kRerankThreads / 32) * 4) {
         const int c = c0 + sub;
-        const int32_t id = c < a.kp ? a.cand_id[(int64_t)q * a.kp + c] : -1;
+        int32_t id = c < a.kp ? a.cand_id[(int64_t)q * a.kp + c] : -1;
+        if ((int64_t)id >= a.ntotal) id = -1;  // never dereference a label outside the index
         float acc = 0.f;
         if (id >= 0) {
             if (vec_f32) {

@@ -344,3 +344,24 @@ def test_full_size_properties(m):
     # idempotence and batch-independence: a query's answer does not depend on its batch
     D1, I1 = ix.set_search_params(algo=m.ALGO_TENSOR).search(xq[100:101], k)
     assert np.array_equal(I1[0], It[100]) and np.allclose(D1[0], Dt[100], rtol=1e-6)
+
+
+def test_large_bf16_index_properties(m):
+    """> 4 GiB of bf16 rows (6M x 384) and long per-split streams: exercises 64-bit addressing, the adaptive
+    candidate-list capacity and the overflow path.  Checked through size-independent properties: self
+    queries return themselves at distance 0, and the tensor path agrees with the exact scan."""
+    import torch
+
+    n, d, k = 6_000_000, 384, 10
+    ix = m.IndexFlat(d, 1, storage=m.STORE_BF16)
+    ix.reserve(n)
+    ix.add_synthetic(1234, 0, n)
+    rows = [0, 1, n // 2, n - 1]
+    q_self = np.stack([orc.c_synth_rows(1234, r, 1, d)[0] for r in rows])
+    q_self = torch.from_numpy(q_self).to(torch.bfloat16).to(torch.float32).numpy()   # the stored (rounded) rows
+    xq = np.concatenate([q_self, orc.c_synth_rows(5678, 0, 1020, d)])
+    Dt, It = ix.set_search_params(algo=m.ALGO_TENSOR).search(xq, k)
+    assert It[:4, 0].tolist() == rows and (Dt[:4, 0] == 0).all()
+    assert (np.diff(Dt, axis=1) >= 0).all() and (It >= 0).all() and (It < n).all()
+    Ds, Is = ix.set_search_params(algo=m.ALGO_SCAN).search(xq[:16], k)
+    _check(Dt[:16], It[:16], Ds, Is, 1)
