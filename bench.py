@@ -11,9 +11,10 @@ A "step" is one index.search() over the whole query batch.
              per launch with CUDA events on its own stream inside the library
   cpu_baseline  the CPU restatement of IndexFlat (oracle/) on the box's host cores, bounded sample
 
-N > 1 (torchrun): the 1M rows are row-sharded over the ranks (strong scaling of the same database),
-queries replicated, per-rank top-k exchanged with one NCCL all-gather and merged by the CUDA merge
-kernel.  --impl reference times the CPU restatement instead (faiss-cpu itself cannot be installed
+N > 1 (torchrun): the 1M rows are row-sharded over the ranks (contiguous ranges) and the query batch
+grows with N (1024 x N queries, replicated on every rank), so per-GPU work is constant ("weak"): every
+rank searches its shard for the whole batch, per-rank top-k lists are exchanged with one NCCL all-gather
+and merged by the CUDA merge kernel.  value = all queries answered / max-over-ranks time.  --impl reference times the CPU restatement instead (faiss-cpu itself cannot be installed
 here: no wheel, no network -- see DESIGN.md).
 """
 from __future__ import annotations
@@ -180,7 +181,7 @@ def run_reference(args, wl, rank, world):
     line = {
         "impl": "reference", "metric": "queries/sec @k=10 (flat L2, 384-d)", "value": round(qps, 2), "unit": "queries/sec",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 3),
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl["label"], "rows": wl["n"], "d": wl["d"], "nq": wl["nq"], "k": wl["k"]},
         "cpu_baseline": {"value": round(qps, 2), "unit": "queries/sec", "cores": int(cores), "kind": "port",
                          "sample": f"{nq_s} of {wl['nq']} queries x {n_cpu} rows per step; CPU restatement of IndexFlat "
@@ -230,13 +231,14 @@ def main():
     storage = b2f.STORE_BF16 if wl["storage"] == "bf16" else b2f.STORE_F32
 
     n, d, nq, k = wl["n"], wl["d"], wl["nq"], wl["k"]
-    weak = args.workload == "c4shard"
-    if weak:   # per-GPU shard of config 4: every rank holds n rows
+    shard_per_gpu = args.workload == "c4shard"
+    if shard_per_gpu:   # per-GPU shard of config 4: every rank holds n rows, batch fixed
         lo, hi = rank * n, (rank + 1) * n
         n_global = n * world
-    else:      # strong scaling of the same database
+    else:               # the same database row-sharded; the batch grows with N so per-GPU work is constant
         lo, hi = partition_rows(n, world)[rank]
         n_global = n
+        nq = nq * world
     ix = b2f.IndexFlat(d, wl["metric"], storage=storage, device=local_rank)
     ix.reserve(hi - lo)
     ix.add_synthetic(SEED_DB, lo, hi - lo, wl["normalize"])   # generated on the device, bit-identical to the oracle
@@ -359,14 +361,15 @@ def main():
         line = {
             "metric": "queries/sec @k=10 (flat L2, 384-d)", "value": round(nq / (ms_step * 1e-3), 1), "unit": "queries/sec",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4),
-            "higher_is_better": True, "scaling": "weak" if weak else "strong", "vs_baseline": None,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16 tensor-core candidates + f32 exact re-rank" if used_algo == b2f.ALGO_TENSOR else "f32",
             "data": "synthetic",
             "config": {"workload": wl["label"], "rows_total": n_global, "rows_per_gpu": rows_local, "d": d, "nq": nq, "k": k,
                        "storage": wl["storage"], "algo": {1: "scan", 2: "tensor"}.get(used_algo, "?"),
                        "kprime": st["last_kprime"], "fallback_queries": st["fallback_queries"], "overflow_queries": st["overflow_queries"], "filter_survivors_per_query": round(st["last_list_entries"] / max(nq, 1), 1),
                        "l2_policy": "inputs larger than L2 (bf16 scan copy %.0f MB per GPU, L2 126 MB)" % (rows_local * dpad * 2 / 1e6),
-                       "sharding": "rows, contiguous ranges; one all-gather + CUDA merge per step" if world > 1 else "single GPU"},
+                       "sharding": ("rows in contiguous ranges over %d GPUs, batch %d = %d x N replicated; one NCCL all-gather + CUDA merge per step"
+                                    % (world, nq, wl["nq"])) if world > 1 else "single GPU"},
             "roofline": roof,
             "e2e": {"value": round(nq / (e2e_ms * 1e-3), 1), "unit": "queries/sec", "ms_per_step": round(e2e_ms, 4),
                     "h2d_bytes_per_step": nq * d * 4, "d2h_bytes_per_step": nq * k * 12},

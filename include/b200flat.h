@@ -11,7 +11,8 @@
  *     thread-local message of the last failure.  Nothing throws or aborts across the ABI.
  *   - `mem` says where the caller's buffers live: B2F_MEM_HOST (numpy) or B2F_MEM_DEVICE (a CUDA
  *     pointer on the index's device, e.g. torch.Tensor.data_ptr()).
- *   - `stream` is a cudaStream_t passed as void*; NULL = the index's own stream.  With host buffers
+ *   - `stream` is a cudaStream_t passed as void*; NULL = the index's own (non-blocking) stream; pass
+ *     cudaStreamLegacy (0x1) to mean the legacy default stream.  With host buffers
  *     every call is synchronous on return (faiss semantics).  With device buffers the work is
  *     enqueued on `stream` and the call returns without synchronising.
  *   - the caller allocates D / I (as faiss's search_c does); the library owns all device storage

@@ -48,7 +48,7 @@ constexpr int STAGES_LIST = 4;
 constexpr int STAGES_QRES = 4;    // Q-resident variant: stages hold database blocks only (32 KB each)
 constexpr int QRES_MAX_KB = 6;    // query tile kept resident in smem when dpad <= 384 (6 x 16 KB)
 constexpr int LIST_CAP_MIN = 128;  // entries per (query, split) candidate list: 128 / 256 / 512 by stream length
-constexpr int JSLOTS = 8;         // register slots for the split-local j-th best (j <= 8)
+constexpr int JSLOTS = 16;        // register slots for the split-local j-th best (j <= 16: LIST mode from 2 splits up)
 constexpr int A_BYTES = BM * BK * 2;  // 16 KB
 constexpr int B_BYTES = BN * BK * 2;  // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -368,7 +368,7 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         if constexpr (LIST) {
             // ---- LIST mode: shared cross-split threshold + append-only candidate lists -----------------
             const float kInf = __int_as_float(0x7f800000);
-            float best[JSLOTS];  // ascending; the first JSLOTS - j slots are pinned at -inf, so best[7] = j-th best
+            float best[JSLOTS];  // ascending; the first JSLOTS - j slots are pinned at -inf, so best[JSLOTS-1] = j-th best
 #pragma unroll
             for (int i = 0; i < JSLOTS; i++) best[i] = (i < JSLOTS - la.j) ? -kInf : kInf;
             float thr = 3.0e38f, pub = kInf;  // refreshed before the first compare; never +inf (padding rows have key +inf)

@@ -63,20 +63,33 @@ struct DeviceGuard {
 };
 
 int check_device(int device) {
-    int n = 0;
-    cudaError_t e = cudaGetDeviceCount(&n);
-    if (e != cudaSuccess || n <= 0) {
-        cudaGetLastError();
-        set_error("no CUDA device available (%s); this engine has no CPU path", e == cudaSuccess ? "count=0" : cudaGetErrorString(e));
-        return B2F_ENOGPU;
+    // cached: cudaGetDeviceProperties costs milliseconds and this runs on per-search entry points
+    static int cached_count = -1;
+    static int cached_major[64];
+    if (cached_count < 0) {
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess || n <= 0) {
+            cudaGetLastError();
+            set_error("no CUDA device available (%s); this engine has no CPU path", e == cudaSuccess ? "count=0" : cudaGetErrorString(e));
+            return B2F_ENOGPU;
+        }
+        if (n > 64) n = 64;
+        for (int i = 0; i < n; i++) {
+            int major = 0;
+            if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, i) != cudaSuccess) {
+                cudaGetLastError();
+                major = 0;
+            }
+            cached_major[i] = major;
+        }
+        cached_count = n;
     }
-    if (device < 0 || device >= n) {
-        set_error("device %d out of range [0,%d)", device, n);
+    if (device < 0 || device >= cached_count) {
+        set_error("device %d out of range [0,%d)", device, cached_count);
         return B2F_EINVAL;
     }
-    cudaDeviceProp p;
-    if (cudaGetDeviceProperties(&p, device) != cudaSuccess || p.major != 10) {
-        cudaGetLastError();
+    if (cached_major[device] != 10) {
         set_error("device %d is not sm_100 (Blackwell B200); kernels are built for sm_100a only", device);
         return B2F_ENOGPU;
     }

@@ -26,7 +26,7 @@ def pool_normalize(hidden, attention_mask=None, pool: str = "cls", normalize: bo
     if attention_mask is not None:
         attention_mask = attention_mask.to(device=hidden.device, dtype=torch.int64).contiguous()
         mptr = attention_mask.data_ptr()
-    stream = int(torch.cuda.current_stream(hidden.device).cuda_stream)
+    stream = int(torch.cuda.current_stream(hidden.device).cuda_stream) or 1  # 0x1 = cudaStreamLegacy
     C.check(C.load().b2f_pool_normalize(hidden.data_ptr(), mptr, B, T, d,
                                         C.POOL_MEAN if pool == "mean" else C.POOL_CLS, int(bool(normalize)),
                                         out.data_ptr(), hidden.device.index or 0, ctypes.c_void_p(stream)))
@@ -38,7 +38,7 @@ def synth_rows(seed: int, row0: int, nrows: int, d: int, normalize: bool = False
     import torch
 
     out = torch.empty((nrows, d), dtype=torch.float32, device=f"cuda:{device}")
-    stream = int(torch.cuda.current_stream(out.device).cuda_stream)
+    stream = int(torch.cuda.current_stream(out.device).cuda_stream) or 1  # 0x1 = cudaStreamLegacy
     C.check(C.load().b2f_synth_rows(int(seed), int(row0), int(nrows), int(d), int(bool(normalize)), out.data_ptr(),
                                     device, ctypes.c_void_p(stream)))
     return out

@@ -44,9 +44,13 @@ def _default_storage() -> int:
 
 
 def _torch_stream(t) -> int:
+    """cudaStream_t of torch's current stream.  torch's default stream is the legacy default stream, whose
+    handle is 0 -- which the C-ABI reads as "use the index's own stream" -- so it is passed as
+    cudaStreamLegacy (0x1) to keep the work ordered with the caller's other torch ops."""
     import torch
 
-    return int(torch.cuda.current_stream(t.device).cuda_stream)
+    h = int(torch.cuda.current_stream(t.device).cuda_stream)
+    return h if h != 0 else 1
 
 
 class IndexFlat:

@@ -80,7 +80,7 @@ def merge_topk(metric: int, D_parts, I_parts):
     I_parts = I_parts.contiguous()
     D = torch.empty((nq, k), dtype=torch.float32, device=D_parts.device)
     I = torch.empty((nq, k), dtype=torch.int64, device=D_parts.device)
-    stream = int(torch.cuda.current_stream(D_parts.device).cuda_stream)
+    stream = int(torch.cuda.current_stream(D_parts.device).cuda_stream) or 1  # 0x1 = cudaStreamLegacy
     C.check(C.load().b2f_merge_topk(int(metric), nq, k, G, D_parts.data_ptr(), I_parts.data_ptr(), D.data_ptr(),
                                     I.data_ptr(), D_parts.device.index or 0, ctypes.c_void_p(stream)))
     return D, I
