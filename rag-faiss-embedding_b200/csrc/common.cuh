@@ -219,6 +219,7 @@ struct TensorScanPlan {
     int nsplits;       // database streams per query tile
     int kp;            // candidates kept per query
     int list_mode;     // 1: shared-threshold candidate lists (K3b merge), 0: per-thread heaps (K3 merge)
+    int pair_mode;     // 1: CTA pairs (tcgen05 cta_group::2, M = 256 queries per pair); nq_tiles is then even
     int list_j;        // rows each split vouches for
     int list_g;        // splits consulted for the shared threshold (g * j >= kp)
     int list_cap;      // entries per (query, split) list

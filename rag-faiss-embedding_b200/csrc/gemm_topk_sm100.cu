@@ -32,6 +32,7 @@
 // 2 * nq * n * d flop.
 #include <cuda.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -113,6 +114,58 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
         "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate)
         : "memory");
 }
+// ---- cta_group::2 (CTA pair) primitives --------------------------------------------------------------
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address -> the even CTA
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load issued by either CTA of the pair; the bytes are credited to the LEADER CTA's mbarrier
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerBitMask), "r"(x), "r"(y)
+        : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// commit of the pair's MMAs: arrives on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+// arrive on the barrier at the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(rank)
+        : "memory");
+}
+// kind::f16 instruction descriptor for the pair: M = 256 (128 per CTA), N = 256
+constexpr uint32_t kIdescPair = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+constexpr int STAGES_PAIR = 8;        // pair variant: each CTA stages its 128-row half of the database block (16 KB)
+constexpr int BH_BYTES = B_BYTES / 2;
+
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -137,16 +190,16 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-template <int KP, int NST, int QKB = 0>
+template <int KP, int NST, int QKB = 0, bool PAIRED = false>
 struct Smem {
     static constexpr size_t q_off = 0;                                   // resident query tile: QKB x 16 KB
-    static constexpr size_t stage_bytes = QKB ? (size_t)B_BYTES : (size_t)STAGE_BYTES;
+    static constexpr size_t stage_bytes = PAIRED ? (size_t)B_BYTES / 2 : (QKB ? (size_t)B_BYTES : (size_t)STAGE_BYTES);
     static constexpr size_t stages_off = (size_t)QKB * A_BYTES;
     static constexpr size_t heapk_off = stages_off + (size_t)NST * stage_bytes;
     static constexpr size_t heapi_off = heapk_off + (size_t)EPI_THREADS * KP * 4;
     static constexpr size_t bias_off = heapi_off + (size_t)EPI_THREADS * KP * 4;
     static constexpr size_t bar_off = bias_off + 2 * BN * 4;
-    static constexpr int nbars = 2 * NST + 7;
+    static constexpr int nbars = 2 * NST + 9;
     static constexpr size_t tmem_off = bar_off + nbars * 8;
     static constexpr size_t total = tmem_off + 16;
     static constexpr size_t alloc = total;  // the dynamic smem base is declared __align__(1024)
@@ -208,14 +261,15 @@ __device__ __forceinline__ float dec_key(uint32_t e) {
     return __uint_as_float((e & 0x80000000u) ? (e & 0x7fffffffu) : ~e);
 }
 
-template <int KP, bool L2, bool LIST, bool QRES>
+template <int KP, bool L2, bool LIST, bool QRES, bool PAIR>
 __global__ void __launch_bounds__(THREADS, 1)
 tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
                    const float* __restrict__ norms, int64_t n, int nq, int kblocks, int nq_tiles, int nsplits,
                    float* __restrict__ pk, int32_t* __restrict__ pi, ListArgs la) {
     static_assert(!QRES || LIST, "the Q-resident variant exists for LIST mode only");
-    constexpr int STAGES = QRES ? STAGES_QRES : (LIST ? STAGES_LIST : STAGES_HEAP);
-    using L = Smem<LIST ? 0 : KP, STAGES, QRES ? QRES_MAX_KB : 0>;
+    static_assert(!PAIR || QRES, "the CTA-pair variant builds on the Q-resident one");
+    constexpr int STAGES = PAIR ? STAGES_PAIR : (QRES ? STAGES_QRES : (LIST ? STAGES_LIST : STAGES_HEAP));
+    using L = Smem<LIST ? 0 : KP, STAGES, QRES ? QRES_MAX_KB : 0, PAIR>;
     constexpr uint32_t kStageBytes = (uint32_t)L::stage_bytes;
     extern __shared__ __align__(1024) uint8_t smem[];  // SWIZZLE_128B tiles need 1024-byte alignment
     if ((smem_u32(smem) & 1023u) != 0) __trap();
@@ -229,10 +283,18 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // [2]       epilogue -> MMA, bias loader
     uint64_t* bias_full = bars + 2 * STAGES + 4;   // [2]       bias loader -> epilogue
     uint64_t* q_full = bars + 2 * STAGES + 6;      // [1]       resident query tile landed (QRES)
+    uint64_t* bias_empty = bars + 2 * STAGES + 7;  // [2]       epilogue -> bias loader (PAIR: local to each CTA)
     uint32_t* tmem_base_holder = reinterpret_cast<uint32_t*>(smem + L::tmem_off);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int qt = blockIdx.x % nq_tiles, split = blockIdx.x / nq_tiles;
+    // PAIR: a cluster of two CTAs (one TPC) works on 256 queries x one database split; CTA rank r owns
+    // queries [128 r, 128 r + 128) of the pair tile and stages rows [128 r, 128 r + 128) of every
+    // 256-row database block; the leader (rank 0) issues tcgen05.mma.cta_group::2 for both.
+    const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+    const int unit = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;       // cluster (PAIR) or CTA index
+    const int units_per_split = PAIR ? (nq_tiles >> 1) : nq_tiles;
+    const int qt = PAIR ? (unit % units_per_split) * 2 + (int)cta_rank : unit % units_per_split;
+    const int split = unit / units_per_split;
     const int64_t ntiles = (n + BN - 1) / BN;
     const int64_t t_begin = ntiles * split / nsplits, t_end = ntiles * (split + 1) / nsplits;
     const int my_tiles = (int)(t_end - t_begin);
@@ -248,20 +310,29 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         }
         for (int a = 0; a < 2; a++) {
             mbar_init(&tmem_full[a], 1);
-            mbar_init(&tmem_empty[a], 4);  // one arrive per epilogue warp
+            mbar_init(&tmem_empty[a], PAIR ? 8 : 4);  // one arrive per epilogue warp (of both CTAs for a pair)
             mbar_init(&bias_full[a], 1);
+            mbar_init(&bias_empty[a], 4);
         }
         mbar_init(q_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_holder)),
-                     "r"((uint32_t)TMEM_COLS)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_holder)),
+                         "r"((uint32_t)TMEM_COLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_holder)),
+                         "r"((uint32_t)TMEM_COLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();  // the peer's barriers must be initialised before any remote arrive / TMA credit
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_holder;
 
@@ -270,7 +341,12 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            if constexpr (QRES) {
+            if constexpr (PAIR) {
+                // both CTAs load their own 128-query tile; the bytes of both are credited to the leader's barrier
+                if (cta_rank == 0) mbar_expect_tx(q_full, (uint32_t)(2 * kblocks * A_BYTES));
+                for (int kb = 0; kb < kblocks; kb++)
+                    tma_load_2d_pair(smem + L::q_off + (size_t)kb * A_BYTES, &map_q, kb * BK, qt * BM, q_full);
+            } else if constexpr (QRES) {
                 // the whole query tile (all k-blocks) is loaded once and stays in shared memory
                 mbar_expect_tx(q_full, (uint32_t)(kblocks * A_BYTES));
                 for (int kb = 0; kb < kblocks; kb++) tma_load_2d(smem + L::q_off + (size_t)kb * A_BYTES, &map_q, kb * BK, qt * BM, q_full);
@@ -280,6 +356,16 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 for (int kb = 0; kb < kblocks; kb++) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + L::stages_off + (size_t)stage * kStageBytes;
+                    if constexpr (PAIR) {
+                        // this CTA's half of the 256-row block; the leader's full barrier collects both halves
+                        if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * kStageBytes);
+                        tma_load_2d_pair(sa, &map_x, kb * BK, row0 + (int)cta_rank * (BN / 2), &full_bar[stage]);
+                        if (++stage == STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                        continue;
+                    }
                     mbar_expect_tx(&full_bar[stage], kStageBytes);
                     if constexpr (!QRES) tma_load_2d(sa, &map_q, kb * BK, qt * BM, &full_bar[stage]);
                     tma_load_2d(sa + (QRES ? 0 : A_BYTES), &map_x, kb * BK, row0, &full_bar[stage]);
@@ -293,7 +379,7 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         __syncwarp();
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        if (lane == 0 && cta_rank == 0) {  // PAIR: only the leader CTA issues MMAs
             int stage = 0;
             uint32_t phase = 0;
             if constexpr (QRES) mbar_wait(q_full, 0);
@@ -312,15 +398,20 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; k++) {
                         // advance both descriptors by 32 bytes (16 bf16) inside the 128-byte swizzle atom
-                        umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), (kb | k) != 0 ? 1u : 0u);
+                        if constexpr (PAIR)
+                            umma_bf16_pair(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), kIdescPair, (kb | k) != 0 ? 1u : 0u);
+                        else
+                            umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), (kb | k) != 0 ? 1u : 0u);
                     }
-                    umma_commit(&empty_bar[stage]);
+                    if constexpr (PAIR) umma_commit_pair(&empty_bar[stage]);
+                    else umma_commit(&empty_bar[stage]);
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-                umma_commit(&tmem_full[acc]);
+                if constexpr (PAIR) umma_commit_pair(&tmem_full[acc]);
+                else umma_commit(&tmem_full[acc]);
             }
         }
         __syncwarp();
@@ -329,7 +420,7 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         for (int t = 0; t < my_tiles; t++) {
             const int acc = t & 1;
             const uint32_t acc_phase = (t >> 1) & 1;
-            mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+            mbar_wait(PAIR ? &bias_empty[acc] : &tmem_empty[acc], acc_phase ^ 1);
             const int64_t row0 = (t_begin + t) * BN;
 #pragma unroll
             for (int j = 0; j < BN / 32; j++) {
@@ -460,7 +551,14 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                if (lane == 0) {
+                    if constexpr (PAIR) {
+                        mbar_arrive(&bias_empty[acc]);             // this CTA's bias buffer is free again
+                        mbar_arrive_cluster(&tmem_empty[acc], 0);  // the leader may overwrite both CTAs' accumulators
+                    } else {
+                        mbar_arrive(&tmem_empty[acc]);
+                    }
+                }
             }
             if (active) {
                 // End-of-stream pruning: the final shared threshold is far tighter than the ones most
@@ -541,9 +639,13 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();  // neither CTA may free TMEM / exit while the other still uses the pair
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+        if constexpr (PAIR)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
     }
 }
 
@@ -719,19 +821,36 @@ static int make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t
     return B2F_OK;
 }
 
-template <int KP, bool L2, bool LIST, bool QRES>
+template <int KP, bool L2, bool LIST, bool QRES, bool PAIR = false>
 static int launch_k2(const CUtensorMap& mq, const CUtensorMap& mx, const float* norms, int64_t n, int nq, int kblocks,
                      const TensorScanPlan& plan, float* pk, int32_t* pi, const ListArgs& la, cudaStream_t st) {
-    auto kern = tensor_scan_kernel<KP, L2, LIST, QRES>;
-    constexpr size_t smem = Smem<LIST ? 0 : KP, QRES ? STAGES_QRES : (LIST ? STAGES_LIST : STAGES_HEAP), QRES ? QRES_MAX_KB : 0>::alloc;
+    auto kern = tensor_scan_kernel<KP, L2, LIST, QRES, PAIR>;
+    constexpr size_t smem = Smem < LIST ? 0 : KP, PAIR ? STAGES_PAIR : (QRES ? STAGES_QRES : (LIST ? STAGES_LIST : STAGES_HEAP)),
+                     QRES ? QRES_MAX_KB : 0, PAIR > ::alloc;
     static_assert(smem <= 232448, "shared memory budget exceeded");
     static bool configured = false;
     if (!configured) {
         B2F_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    kern<<<plan.nq_tiles * plan.nsplits, THREADS, smem, st>>>(mq, mx, norms, n, nq, kblocks, plan.nq_tiles, plan.nsplits, pk,
-                                                              pi, la);
+    if constexpr (PAIR) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)(plan.nq_tiles * plan.nsplits));  // nq_tiles is even: 2 CTAs per cluster
+        cfg.blockDim = dim3(THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        B2F_CUDA(cudaLaunchKernelEx(&cfg, kern, mq, mx, norms, n, nq, kblocks, plan.nq_tiles, plan.nsplits, pk, pi, la));
+    } else {
+        kern<<<plan.nq_tiles * plan.nsplits, THREADS, smem, st>>>(mq, mx, norms, n, nq, kblocks, plan.nq_tiles, plan.nsplits,
+                                                                  pk, pi, la);
+    }
     B2F_CUDA(cudaGetLastError());
     return B2F_OK;
 }
@@ -741,27 +860,45 @@ static int launch_k2(const CUtensorMap& mq, const CUtensorMap& mx, const float* 
 int plan_tensor_scan(int nq, int64_t n, int d, int kp, TensorScanPlan* plan) {
     if (kp != 32 && kp != 64) return B2F_EINVAL;
     if (n <= 0 || nq <= 0) return B2F_EINVAL;
-    (void)d;
     plan->kp = kp;
     plan->nq_tiles = (nq + k2::BM - 1) / k2::BM;
-    const int64_t ntiles = (n + k2::BN - 1) / k2::BN;
-    int ns = kNumSMs / plan->nq_tiles;
-    if (ns < 1) ns = 1;
-    if (ns > ntiles) ns = (int)ntiles;
-    plan->nsplits = ns;
-    // LIST mode needs every split resident at once (one wave), j = ceil(kp / nsplits) <= 8 rows vouched
-    // per split, and at least two tiles per split so that every split can vouch for its j rows early.
-    int j = (kp + ns - 1) / ns;
+    plan->pair_mode = 0;
     plan->list_mode = 0;
-    if (plan->nq_tiles * ns <= kNumSMs) {
-        int ns_list = ns;
-        if (ntiles < 2 * (int64_t)ns_list) ns_list = (int)(ntiles / 2);
-        if (ns_list >= 2 && (kp + ns_list - 1) / ns_list <= k2::JSLOTS) {
+    const int64_t ntiles = (n + k2::BN - 1) / k2::BN;
+    const int kblocks = (d + k2::BK - 1) / k2::BK;
+    int ns = 0, j = 0;
+    // (1) CTA pairs (cta_group::2) halve the L2->SM traffic of the database blocks; worth it once the
+    //     batch spans several 128-query tiles (an odd tile count wastes half a pair on padding).
+    const char* no_pair = getenv("B200FLAT_NO_PAIR");
+    if (!(no_pair && no_pair[0] == '1') && kblocks <= k2::QRES_MAX_KB && plan->nq_tiles >= 2 &&
+        (plan->nq_tiles % 2 == 0 || plan->nq_tiles >= 7)) {
+        const int npt = (plan->nq_tiles + 1) / 2;
+        int nsp = (kNumSMs / 2) / npt;
+        if (nsp > ntiles / 2) nsp = (int)(ntiles / 2);
+        if (nsp >= 2 && (kp + nsp - 1) / nsp <= k2::JSLOTS) {
+            plan->pair_mode = 1;
             plan->list_mode = 1;
-            plan->nsplits = ns = ns_list;
-            j = (kp + ns - 1) / ns;
+            plan->nq_tiles = 2 * npt;
+            ns = nsp;
         }
     }
+    if (!plan->pair_mode) {
+        ns = kNumSMs / plan->nq_tiles;
+        if (ns < 1) ns = 1;
+        if (ns > ntiles) ns = (int)ntiles;
+        // (2) LIST mode needs every split resident at once (one wave), j = ceil(kp / nsplits) <= JSLOTS rows
+        //     vouched per split, and at least two tiles per split so every split can vouch for its rows early.
+        if (plan->nq_tiles * ns <= kNumSMs) {
+            int ns_list = ns;
+            if (ntiles < 2 * (int64_t)ns_list) ns_list = (int)(ntiles / 2);
+            if (ns_list >= 2 && (kp + ns_list - 1) / ns_list <= k2::JSLOTS) {
+                plan->list_mode = 1;
+                ns = ns_list;
+            }
+        }
+    }
+    plan->nsplits = ns;
+    j = (kp + ns - 1) / ns;
     plan->list_j = j;
     plan->list_g = (kp + j - 1) / j;
     // expected list length ~ 32 (blind first chunk) + (j + spread) * ln(rows per split / 32); 2.5x headroom
@@ -782,7 +919,7 @@ int launch_tensor_scan(const __nv_bfloat16* scan, int64_t dpad, const float* nor
                        const TensorScanLists& lists, cudaStream_t st) {
     CUtensorMap mq, mx;
     B2F_TRY(k2::make_map(&mq, qb, (uint64_t)dpad, (uint64_t)nq_pad, (uint64_t)dpad, k2::BM));
-    B2F_TRY(k2::make_map(&mx, scan, (uint64_t)dpad, (uint64_t)n, (uint64_t)dpad, k2::BN));
+    B2F_TRY(k2::make_map(&mx, scan, (uint64_t)dpad, (uint64_t)n, (uint64_t)dpad, plan.pair_mode ? k2::BN / 2 : k2::BN));
     const int kblocks = (int)(dpad / k2::BK);
     const bool l2 = metric == B2F_METRIC_L2;
     k2::ListArgs la{};
@@ -795,6 +932,9 @@ int launch_tensor_scan(const __nv_bfloat16* scan, int64_t dpad, const float* nor
         la.cap = plan.list_cap;
         // "no information yet": 0x7f7f7f7f = 3.39e38, above every admissible key
         B2F_CUDA(cudaMemsetAsync(lists.shared_thr, 0x7f, (size_t)nq_pad * plan.nsplits * sizeof(float), st));  // [split][query]
+        if (plan.pair_mode)
+            return l2 ? k2::launch_k2<0, true, true, true, true>(mq, mx, norms, n, nq, kblocks, plan, pk, pi, la, st)
+                      : k2::launch_k2<0, false, true, true, true>(mq, mx, norms, n, nq, kblocks, plan, pk, pi, la, st);
         if (kblocks <= k2::QRES_MAX_KB)
             return l2 ? k2::launch_k2<0, true, true, true>(mq, mx, norms, n, nq, kblocks, plan, pk, pi, la, st)
                       : k2::launch_k2<0, false, true, true>(mq, mx, norms, n, nq, kblocks, plan, pk, pi, la, st);
