@@ -217,6 +217,7 @@ int launch_rerank(const RerankArgs& a, cudaStream_t st);
 struct TensorScanPlan {
     int nq_tiles;      // ceil(nq / 128)
     int nsplits;       // database streams per query tile
+    int nlists;        // LIST mode: candidate lists per query = nsplits x column halves (virtual splits)
     int kp;            // candidates kept per query
     int list_mode;     // 1: shared-threshold candidate lists (K3b merge), 0: per-thread heaps (K3 merge)
     int pair_mode;     // 1: CTA pairs (tcgen05 cta_group::2, M = 256 queries per pair); nq_tiles is then even
@@ -225,9 +226,9 @@ struct TensorScanPlan {
     int list_cap;      // entries per (query, split) list
 };
 struct TensorScanLists {  // LIST-mode scratch (device)
-    float* shared_thr;    // [nq_pad][nsplits]
-    void* cand;           // [nq_pad * nsplits][list_cap] x 8 bytes
-    int32_t* counts;      // [nq_pad * nsplits]
+    float* shared_thr;    // [nlists][nq_pad]
+    void* cand;           // [nq_pad * nlists][list_cap] x 8 bytes
+    int32_t* counts;      // [nq_pad * nlists]
 };
 int plan_tensor_scan(int nq, int64_t n, int d, int kp, TensorScanPlan* plan);
 int launch_tensor_scan(const __nv_bfloat16* scan, int64_t dpad, const float* norms, int64_t n, int metric,

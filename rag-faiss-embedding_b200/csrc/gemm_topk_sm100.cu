@@ -53,8 +53,10 @@ constexpr int JSLOTS = 16;        // register slots for the split-local j-th bes
 constexpr int A_BYTES = BM * BK * 2;  // 16 KB
 constexpr int B_BYTES = BN * BK * 2;  // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int THREADS = 256;
-constexpr int EPI_THREADS = 128;
+constexpr int EPI_THREADS = 128;          // TMEM lanes = queries per CTA tile
+constexpr int EPI_WARPS_HEAP = 4;
+constexpr int EPI_WARPS_LIST = 8;         // two warps per TMEM lane quarter, each owning half of the tile's columns
+__host__ __device__ constexpr int k2_threads(bool list) { return 128 + 32 * (list ? EPI_WARPS_LIST : EPI_WARPS_HEAP); }
 constexpr int TMEM_COLS = 512;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -164,7 +166,6 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank
 // kind::f16 instruction descriptor for the pair: M = 256 (128 per CTA), N = 256
 constexpr uint32_t kIdescPair = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 constexpr int STAGES_PAIR = 8;        // pair variant: each CTA stages its 128-row half of the database block (16 KB)
-constexpr int BH_BYTES = B_BYTES / 2;
 
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -262,7 +263,7 @@ __device__ __forceinline__ float dec_key(uint32_t e) {
 }
 
 template <int KP, bool L2, bool LIST, bool QRES, bool PAIR>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(k2_threads(LIST), 1)
 tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
                    const float* __restrict__ norms, int64_t n, int nq, int kblocks, int nq_tiles, int nsplits,
                    float* __restrict__ pk, int32_t* __restrict__ pi, ListArgs la) {
@@ -271,6 +272,9 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     constexpr int STAGES = PAIR ? STAGES_PAIR : (QRES ? STAGES_QRES : (LIST ? STAGES_LIST : STAGES_HEAP));
     using L = Smem<LIST ? 0 : KP, STAGES, QRES ? QRES_MAX_KB : 0, PAIR>;
     constexpr uint32_t kStageBytes = (uint32_t)L::stage_bytes;
+    constexpr int EPI_WARPS = LIST ? EPI_WARPS_LIST : EPI_WARPS_HEAP;
+    constexpr int HALVES = EPI_WARPS / 4;        // column halves of a tile, one per epilogue warp of a lane quarter
+    constexpr int COLS = BN / HALVES;            // columns of each tile that one thread examines
     extern __shared__ __align__(1024) uint8_t smem[];  // SWIZZLE_128B tiles need 1024-byte alignment
     if ((smem_u32(smem) & 1023u) != 0) __trap();
     float* heap_k = reinterpret_cast<float*>(smem + L::heapk_off);
@@ -310,9 +314,9 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         }
         for (int a = 0; a < 2; a++) {
             mbar_init(&tmem_full[a], 1);
-            mbar_init(&tmem_empty[a], PAIR ? 8 : 4);  // one arrive per epilogue warp (of both CTAs for a pair)
+            mbar_init(&tmem_empty[a], (PAIR ? 2 : 1) * EPI_WARPS);  // one arrive per epilogue warp (of both CTAs for a pair)
             mbar_init(&bias_full[a], 1);
-            mbar_init(&bias_empty[a], 4);
+            mbar_init(&bias_empty[a], EPI_WARPS);
         }
         mbar_init(q_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -434,44 +438,69 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         }
     } else if (warp >= 4) {
         // ===================== epilogue: fused distance + top-k' =====================
-        const int tid = threadIdx.x - 128;            // 0..127 == TMEM lane == query row in the tile
-        const int wq = warp & 3;                      // TMEM lane quarter this warp may access
+        const int ew = warp - 4;                      // epilogue warp index
+        const int wq = ew & 3;                        // TMEM lane quarter this warp may access (= warp % 4)
+        const int half = ew >> 2;                     // which COLS-wide slice of every tile this warp examines
+        const int tid = wq * 32 + lane;               // 0..127 == TMEM lane == query row in the tile
         const int qrow = qt * BM + tid;
         const bool active = qrow < nq;
         const uint32_t lane_taddr = tmem_base + ((uint32_t)(wq * 32) << 16);
 
-        // Hot loop (both modes): 32 accumulator columns per tcgen05.ld, double buffered; per value one
-        // FFMA + one compare + one predicated OR into a bit mask.  Survivors are rare, so the cold path
-        // is a warp-uniform loop over the union of the lanes' masks that re-reads the one column with
-        // tcgen05.ld.x1 -- nothing is unrolled 32x, which keeps the whole epilogue inside the
-        // instruction cache (ncu: the unrolled version stalled 46% of issue slots on no_instruction).
+        // Hot loop (both modes): 32 accumulator columns per tcgen05.ld; per value one FFMA + one compare +
+        // one predicated OR into one of four partial bit masks (four short dependency chains instead of
+        // one 32-long one).  Survivors are rare, so the cold path is a warp-uniform loop over the union of
+        // the lanes' masks; the needed accumulator is picked out of the registers by a 32-way switch --
+        // nothing is unrolled 32x, which keeps the epilogue inside the instruction cache (ncu: the unrolled
+        // version stalled 46% of issue slots on no_instruction).
         auto chunk_mask = [&](const uint32_t (&r)[32], const float* tbc, float thr) -> uint32_t {
-            uint32_t mask = 0;
+            uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
 #pragma unroll
-            for (int j = 0; j < 32; j++) {
-                const float sdot = __uint_as_float(r[j]);
-                const float key = L2 ? fmaf(-2.f, sdot, tbc[j]) : tbc[j] - sdot;
-                if (LIST ? (key <= thr) : (key < thr)) mask |= 1u << j;
+            for (int j = 0; j < 32; j += 4) {
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const float sdot = __uint_as_float(r[j + u]);
+                    const float key = L2 ? fmaf(-2.f, sdot, tbc[j + u]) : tbc[j + u] - sdot;
+                    const bool pass = LIST ? (key <= thr) : (key < thr);
+                    if (u == 0) { if (pass) m0 |= 1u << (j + u); }
+                    else if (u == 1) { if (pass) m1 |= 1u << (j + u); }
+                    else if (u == 2) { if (pass) m2 |= 1u << (j + u); }
+                    else { if (pass) m3 |= 1u << (j + u); }
+                }
             }
-            return mask;
+            return (m0 | m1) | (m2 | m3);
+        };
+        auto pick = [](const uint32_t (&r)[32], int j) -> uint32_t {  // j is warp-uniform: a branch table, no memory
+            uint32_t v = 0;
+            switch (j) {
+#define B2F_PICK(i) case i: v = r[i]; break;
+                B2F_PICK(0) B2F_PICK(1) B2F_PICK(2) B2F_PICK(3) B2F_PICK(4) B2F_PICK(5) B2F_PICK(6) B2F_PICK(7)
+                B2F_PICK(8) B2F_PICK(9) B2F_PICK(10) B2F_PICK(11) B2F_PICK(12) B2F_PICK(13) B2F_PICK(14) B2F_PICK(15)
+                B2F_PICK(16) B2F_PICK(17) B2F_PICK(18) B2F_PICK(19) B2F_PICK(20) B2F_PICK(21) B2F_PICK(22) B2F_PICK(23)
+                B2F_PICK(24) B2F_PICK(25) B2F_PICK(26) B2F_PICK(27) B2F_PICK(28) B2F_PICK(29) B2F_PICK(30) B2F_PICK(31)
+#undef B2F_PICK
+            }
+            return v;
         };
 
         if constexpr (LIST) {
             // ---- LIST mode: shared cross-split threshold + append-only candidate lists -----------------
+            // Every (database split, column half) pair is a "virtual split" with its own list and its own
+            // published j-th best; nvs = nsplits * HALVES of them cooperate on each query.
             const float kInf = __int_as_float(0x7f800000);
+            const int vsplit = split * HALVES + half, nvs = nsplits * HALVES;
             float best[JSLOTS];  // ascending; the first JSLOTS - j slots are pinned at -inf, so best[JSLOTS-1] = j-th best
 #pragma unroll
             for (int i = 0; i < JSLOTS; i++) best[i] = (i < JSLOTS - la.j) ? -kInf : kInf;
             float thr = 3.0e38f, pub = kInf;  // refreshed before the first compare; never +inf (padding rows have key +inf)
             int cnt = 0;
-            uint2* mylist = la.cand + ((int64_t)(active ? qrow : 0) * nsplits + split) * la.cap;
-            // shared thresholds are laid out [split][query] so that a warp's loads for one split coalesce
+            uint2* mylist = la.cand + ((int64_t)(active ? qrow : 0) * nvs + vsplit) * la.cap;
+            // shared thresholds are laid out [virtual split][query] so that a warp's loads for one split coalesce
             float* gq = la.shared_thr + (active ? qrow : 0);
             const int64_t gstride = (int64_t)nq_tiles * BM;
             auto refresh = [&]() {
                 if (best[JSLOTS - 1] < pub) {
                     pub = best[JSLOTS - 1];
-                    __stcg(gq + (int64_t)split * gstride, pub);
+                    __stcg(gq + (int64_t)vsplit * gstride, pub);
                 }
                 float t = -kInf;
 #pragma unroll 1
@@ -479,8 +508,8 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                     float v[16];
 #pragma unroll
                     for (int u = 0; u < 16; u++) {
-                        int s2 = split + i0 + u;
-                        if (s2 >= nsplits) s2 -= nsplits;
+                        int s2 = vsplit + i0 + u;
+                        if (s2 >= nvs) s2 -= nvs;
                         v[u] = (i0 + u < la.g) ? __ldcg(gq + (int64_t)s2 * gstride) : -kInf;
                     }
 #pragma unroll
@@ -488,7 +517,7 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 }
                 thr = t;
             };
-            auto process = [&](const uint32_t (&r)[32], int t, int c, uint32_t chunk_taddr, const float* tbc, int32_t rowc) {
+            auto process = [&](const uint32_t (&r)[32], int t, int c, const float* tbc, int32_t rowc) {
                 // refresh schedule: thresholds move like 1/rows_seen, so consult the other splits often
                 // at the start and rarely later
                 const bool do_refresh = t == 0 || (t == 1 && (c & 1) == 0) ||
@@ -496,9 +525,9 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 if (active && do_refresh) {
                     refresh();
                     if (t == 0 && c == 1) {
-                        // Every split has now seen 32 rows and published.  CTAs start a few microseconds
-                        // apart; wait (bounded -- never a hard dependency) for the slowest of the g splits
-                        // we consult instead of appending blindly into the list meanwhile.
+                        // Every virtual split has now seen 32 rows and published.  CTAs start a few
+                        // microseconds apart; wait (bounded -- never a hard dependency) for the slowest of
+                        // the g splits we consult instead of appending blindly into the list meanwhile.
                         for (int spin = 0; spin < 64 && thr > 1.0e38f; spin++) {
                             __nanosleep(256);
                             refresh();
@@ -510,8 +539,7 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 while (um) {
                     const int j = __ffs(um) - 1;
                     um &= um - 1;
-                    const uint32_t v = tmem_ld1(chunk_taddr + (uint32_t)j);
-                    tmem_ld_wait();
+                    const uint32_t v = pick(r, j);
                     if (mask & (1u << j)) {
                         const float sdot = __uint_as_float(v);
                         const float key = L2 ? fmaf(-2.f, sdot, tbc[j]) : tbc[j] - sdot;
@@ -535,19 +563,19 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 mbar_wait(&bias_full[acc], acc_phase);
                 mbar_wait(&tmem_full[acc], acc_phase);
                 tc_fence_after();
-                const int32_t row0 = (int32_t)((t_begin + t) * BN);
-                const float* tb = bias + acc * BN;
-                const uint32_t tile_taddr = lane_taddr + (uint32_t)(acc * BN);
+                const int32_t row0 = (int32_t)((t_begin + t) * BN) + half * COLS;
+                const float* tb = bias + acc * BN + half * COLS;
+                const uint32_t tile_taddr = lane_taddr + (uint32_t)(acc * BN + half * COLS);
                 uint32_t ra[32], rb[32];
                 tmem_ld32(tile_taddr, ra);
 #pragma unroll 1
-                for (int c = 0; c < BN / 32; c += 2) {
+                for (int c = 0; c < COLS / 32; c += 2) {
                     tmem_ld_wait();
                     tmem_ld32(tile_taddr + (uint32_t)((c + 1) * 32), rb);
-                    process(ra, t, c, tile_taddr + (uint32_t)(c * 32), tb + c * 32, row0 + c * 32);
+                    process(ra, t, c, tb + c * 32, row0 + c * 32);
                     tmem_ld_wait();
-                    if (c + 2 < BN / 32) tmem_ld32(tile_taddr + (uint32_t)((c + 2) * 32), ra);
-                    process(rb, t, c + 1, tile_taddr + (uint32_t)((c + 1) * 32), tb + (c + 1) * 32, row0 + (c + 1) * 32);
+                    if (c + 2 < COLS / 32) tmem_ld32(tile_taddr + (uint32_t)((c + 2) * 32), ra);
+                    process(rb, t, c + 1, tb + (c + 1) * 32, row0 + (c + 1) * 32);
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -576,7 +604,7 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                     for (int u = 0; u < 8; u++)
                         if (i0 + u < have && __uint_as_float(e[u].x) <= thr) mylist[w++] = e[u];
                 }
-                la.counts[(int64_t)qrow * nsplits + split] = cnt > la.cap ? cnt : w;  // > cap marks an overflow
+                la.counts[(int64_t)qrow * nvs + vsplit] = cnt > la.cap ? cnt : w;  // > cap marks an overflow
             }
         } else {
             // ---- HEAP mode: thread-private max-heap of k' in shared memory ------------------------------
@@ -605,8 +633,7 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                     while (um) {
                         const int j = __ffs(um) - 1;
                         um &= um - 1;
-                        const uint32_t v = tmem_ld1(tile_taddr + (uint32_t)(c * 32 + j));
-                        tmem_ld_wait();
+                        const uint32_t v = pick(r, j);
                         if (mask & (1u << j)) {
                             const float sdot = __uint_as_float(v);
                             const float key = L2 ? fmaf(-2.f, sdot, tbc[j]) : tbc[j] - sdot;
@@ -674,7 +701,7 @@ merge_lists_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ c
                    int cap_entries, float* __restrict__ ck, int32_t* __restrict__ ci, int32_t* __restrict__ ovf,
                    unsigned long long* __restrict__ total_entries) {
     extern __shared__ __align__(16) unsigned long long comp[];  // [cap_entries] + survivors [kp]
-    __shared__ int s_off[kNumSMs + 2];
+    __shared__ int s_off[2 * kNumSMs + 2];
     __shared__ int s_cnt[3];
     __shared__ int s_nsurv;
     __shared__ int s_ovf;
@@ -836,7 +863,7 @@ static int launch_k2(const CUtensorMap& mq, const CUtensorMap& mx, const float* 
     if constexpr (PAIR) {
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3((unsigned)(plan.nq_tiles * plan.nsplits));  // nq_tiles is even: 2 CTAs per cluster
-        cfg.blockDim = dim3(THREADS);
+        cfg.blockDim = dim3(k2_threads(LIST));
         cfg.dynamicSmemBytes = smem;
         cfg.stream = st;
         cudaLaunchAttribute attr[1];
@@ -848,7 +875,7 @@ static int launch_k2(const CUtensorMap& mq, const CUtensorMap& mx, const float* 
         cfg.numAttrs = 1;
         B2F_CUDA(cudaLaunchKernelEx(&cfg, kern, mq, mx, norms, n, nq, kblocks, plan.nq_tiles, plan.nsplits, pk, pi, la));
     } else {
-        kern<<<plan.nq_tiles * plan.nsplits, THREADS, smem, st>>>(mq, mx, norms, n, nq, kblocks, plan.nq_tiles, plan.nsplits,
+        kern<<<plan.nq_tiles * plan.nsplits, k2_threads(LIST), smem, st>>>(mq, mx, norms, n, nq, kblocks, plan.nq_tiles, plan.nsplits,
                                                                   pk, pi, la);
     }
     B2F_CUDA(cudaGetLastError());
@@ -875,7 +902,7 @@ int plan_tensor_scan(int nq, int64_t n, int d, int kp, TensorScanPlan* plan) {
         const int npt = (plan->nq_tiles + 1) / 2;
         int nsp = (kNumSMs / 2) / npt;
         if (nsp > ntiles / 2) nsp = (int)(ntiles / 2);
-        if (nsp >= 2 && (kp + nsp - 1) / nsp <= k2::JSLOTS) {
+        if (nsp >= 1 && (kp + 2 * nsp - 1) / (2 * nsp) <= k2::JSLOTS) {
             plan->pair_mode = 1;
             plan->list_mode = 1;
             plan->nq_tiles = 2 * npt;
@@ -891,19 +918,21 @@ int plan_tensor_scan(int nq, int64_t n, int d, int kp, TensorScanPlan* plan) {
         if (plan->nq_tiles * ns <= kNumSMs) {
             int ns_list = ns;
             if (ntiles < 2 * (int64_t)ns_list) ns_list = (int)(ntiles / 2);
-            if (ns_list >= 2 && (kp + ns_list - 1) / ns_list <= k2::JSLOTS) {
+            if (ns_list >= 1 && (kp + 2 * ns_list - 1) / (2 * ns_list) <= k2::JSLOTS) {
                 plan->list_mode = 1;
                 ns = ns_list;
             }
         }
     }
     plan->nsplits = ns;
-    j = (kp + ns - 1) / ns;
+    // LIST mode: every (split, column half) is a virtual split with its own list and published value
+    plan->nlists = plan->list_mode ? ns * (k2::EPI_WARPS_LIST / 4) : ns;
+    j = (kp + plan->nlists - 1) / plan->nlists;
     plan->list_j = j;
     plan->list_g = (kp + j - 1) / j;
     // expected list length ~ 32 (blind first chunk) + (j + spread) * ln(rows per split / 32); 2.5x headroom
     {
-        const double rows_per_split = (double)n / plan->nsplits;
+        const double rows_per_split = (double)n / plan->nlists;
         const double expected = 32.0 + (j + 2.5) * log(rows_per_split > 64.0 ? rows_per_split / 32.0 : 2.0);
         int cap = (int)(2.5 * expected);
         cap = (cap + 63) / 64 * 64;
@@ -931,7 +960,7 @@ int launch_tensor_scan(const __nv_bfloat16* scan, int64_t dpad, const float* nor
         la.g = plan.list_g;
         la.cap = plan.list_cap;
         // "no information yet": 0x7f7f7f7f = 3.39e38, above every admissible key
-        B2F_CUDA(cudaMemsetAsync(lists.shared_thr, 0x7f, (size_t)nq_pad * plan.nsplits * sizeof(float), st));  // [split][query]
+        B2F_CUDA(cudaMemsetAsync(lists.shared_thr, 0x7f, (size_t)nq_pad * plan.nlists * sizeof(float), st));  // [split][query]
         if (plan.pair_mode)
             return l2 ? k2::launch_k2<0, true, true, true, true>(mq, mx, norms, n, nq, kblocks, plan, pk, pi, la, st)
                       : k2::launch_k2<0, false, true, true, true>(mq, mx, norms, n, nq, kblocks, plan, pk, pi, la, st);
@@ -954,7 +983,7 @@ int launch_tensor_scan(const __nv_bfloat16* scan, int64_t dpad, const float* nor
 int launch_merge_lists(const TensorScanLists& lists, int nq, const TensorScanPlan& plan, float* ck, int32_t* ci,
                        int32_t* ovf, unsigned long long* total_entries, cudaStream_t st) {
     if (nq <= 0) return B2F_OK;
-    int cap_entries = plan.nsplits * plan.list_cap;
+    int cap_entries = plan.nlists * plan.list_cap;
     if (cap_entries > k2::MERGE_MAX) cap_entries = k2::MERGE_MAX;
     const size_t smem = (size_t)(cap_entries + plan.kp) * 8;
     static size_t configured = 0;
@@ -964,7 +993,7 @@ int launch_merge_lists(const TensorScanLists& lists, int nq, const TensorScanPla
         configured = (size_t)(k2::MERGE_MAX + 64) * 8;
     }
     k2::merge_lists_kernel<<<nq, k2::MERGE_THREADS, smem, st>>>(reinterpret_cast<const uint2*>(lists.cand), lists.counts,
-                                                               plan.nsplits, plan.kp, plan.list_cap, cap_entries, ck, ci, ovf, total_entries);
+                                                               plan.nlists, plan.kp, plan.list_cap, cap_entries, ck, ci, ovf, total_entries);
     B2F_CUDA(cudaGetLastError());
     return B2F_OK;
 }

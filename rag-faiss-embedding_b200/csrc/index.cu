@@ -592,8 +592,8 @@ int b2f_index_search(b2f_index* ix, int64_t nq64, const float* q, int64_t k64, f
         const size_t nq_pad = (size_t)plan.nq_tiles * 128;
         need += align_up(nq_pad * ix->dpad * 2, 256) + 2 * align_up(nq_pad * 4, 256);
         if (plan.list_mode) {
-            need += align_up(nq_pad * plan.nsplits * 4, 256) * 2;                       // shared thresholds + counts
-            need += align_up(nq_pad * plan.nsplits * (size_t)plan.list_cap * 8, 256);   // candidate lists
+            need += align_up(nq_pad * plan.nlists * 4, 256) * 2;                       // shared thresholds + counts
+            need += align_up(nq_pad * plan.nlists * (size_t)plan.list_cap * 8, 256);   // candidate lists
             need += align_up((size_t)nq * 4, 256);                                      // overflow flags
         } else {
             need += 2 * align_up(nq_pad * plan.nsplits * kp * 4, 256);  // partial lists
@@ -640,9 +640,9 @@ int b2f_index_search(b2f_index* ix, int64_t nq64, const float* q, int64_t k64, f
         TensorScanLists lists{};
         int32_t* ovf = nullptr;
         if (plan.list_mode) {
-            lists.shared_thr = bump.take<float>((size_t)nq_pad * plan.nsplits);
-            lists.counts = bump.take<int32_t>((size_t)nq_pad * plan.nsplits);
-            lists.cand = bump.take<uint2>((size_t)nq_pad * plan.nsplits * plan.list_cap);
+            lists.shared_thr = bump.take<float>((size_t)nq_pad * plan.nlists);
+            lists.counts = bump.take<int32_t>((size_t)nq_pad * plan.nlists);
+            lists.cand = bump.take<uint2>((size_t)nq_pad * plan.nlists * plan.list_cap);
             ovf = bump.take<int32_t>(nq);
         } else {
             pk = bump.take<float>((size_t)nq_pad * plan.nsplits * kp);
