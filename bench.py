@@ -295,15 +295,12 @@ def main():
     for _ in range(args.warmup):
         step_device()
     launches0 = ix.stats()["launches"]
-    main_ms, total_ms = [], []
+    prof0 = ix.stats()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         step_device()
-        st = ix.stats()
-        main_ms.append(st["last_main_ms"] / max(st["last_main_launches"], 1))
-        total_ms.append(st["last_total_ms"])
     e1.record()
     barrier()
     ms_step = e0.elapsed_time(e1) / args.steps
@@ -311,6 +308,11 @@ def main():
         t = torch.tensor([ms_step], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_step = float(t.item())
+    prof1 = ix.stats()
+    # per-launch time of the dominant kernel: CUDA events recorded by the library around every launch in
+    # the timed region (running sums, read once so that the host loop stays tight)
+    main_ms = [(prof1["prof_main_ms_sum"] - prof0["prof_main_ms_sum"]) / max(prof1["prof_main_launches"] - prof0["prof_main_launches"], 1)]
+    total_ms = [(prof1["prof_total_ms_sum"] - prof0["prof_total_ms_sum"]) / max(prof1["prof_searches"] - prof0["prof_searches"], 1)]
     st = ix.stats()
     launches = st["launches"] - launches0 + (args.steps if world > 1 else 0)  # + the merge kernel per step
     # ---- end-to-end through host buffers ----------------------------------------------------------------

@@ -96,6 +96,10 @@ typedef struct b2f_stats {
     int64_t bytes_scan;        /* device bytes held: bf16 scan copy + norms */
     int64_t overflow_queries;  /* subset of fallback_queries caused by a candidate-list overflow */
     int64_t last_list_entries; /* rows that survived the fused threshold filter in the last tensor-path search */
+    double prof_main_ms_sum;   /* profile=1: running sums over searches, so a benchmark reads them once */
+    double prof_total_ms_sum;
+    int64_t prof_main_launches;
+    int64_t prof_searches;
 } b2f_stats;
 
 /* ---- lifecycle -------------------------------------------------------------------------------

@@ -50,6 +50,10 @@ class Stats(ctypes.Structure):
         ("bytes_scan", ctypes.c_int64),
         ("overflow_queries", ctypes.c_int64),
         ("last_list_entries", ctypes.c_int64),
+        ("prof_main_ms_sum", ctypes.c_double),
+        ("prof_total_ms_sum", ctypes.c_double),
+        ("prof_main_launches", ctypes.c_int64),
+        ("prof_searches", ctypes.c_int64),
     ]
 
     def as_dict(self):

@@ -186,8 +186,10 @@ int launch_pool(const float* hidden, const int64_t* mask, int64_t B, int64_t T, 
 int launch_synth(uint64_t seed, int64_t row0, int64_t nrows, int d, int normalize, float* out, cudaStream_t st);
 // query preparation for the tensor path: bf16 copy (pitch dpad, rows padded to nq_pad with zeros),
 // |q|^2 in fp32 and the norm of the bf16 rounding error of each query.
+// also clears `zero_words` 32-bit words at `zero` and fills `fill_words` words at `fill` with 0x7f7f7f7f
+// (the "no information yet" value of the shared thresholds), saving two memset launches per search
 int launch_prep_queries(const float* q, int nq, int nq_pad, int d, __nv_bfloat16* qb, int64_t dpad, float* qnorm,
-                        float* qerr, cudaStream_t st);
+                        float* qerr, uint32_t* zero, int zero_words, uint32_t* fill, int64_t fill_words, cudaStream_t st);
 int launch_bf16_to_f32(const __nv_bfloat16* src, int64_t pitch, int64_t n, int d, float* dst, cudaStream_t st);
 
 // K4: exact fp32 re-rank of coarse candidates + certification.
@@ -205,8 +207,11 @@ struct RerankArgs {
     float max_row_norm;             // max |x~| over the index (bf16 copy)
     float max_row_err;              // max |x - bf16(x)| over the index (0 for bf16 storage)
     int certify;
-    float* out_key;                 // [nq, k] exact keys
+    float* out_key;                 // [nq, k] exact keys   (used when D == nullptr)
     int32_t* out_id;                // [nq, k]
+    float* D;                       // optional fused finalize: faiss-formatted distances [nq, k]
+    int64_t* I;                     //                          labels [nq, k] (+ id_offset)
+    int64_t id_offset;
     const int32_t* overflow;        // optional [nq]: 1 = candidate list overflowed (treated as uncertified)
     int32_t* fail_list;             // queries that could not be certified
     int32_t* fail_count;            // [2]: uncertified queries, of which list overflows
@@ -235,7 +240,8 @@ int launch_tensor_scan(const __nv_bfloat16* scan, int64_t dpad, const float* nor
                        const __nv_bfloat16* qb, int nq, int nq_pad, const TensorScanPlan& plan, float* pk,
                        int32_t* pi, const TensorScanLists& lists, cudaStream_t st);
 // K3b: per query, the kp best of the variable-length lists -> ck/ci [nq][kp]; ovf[q]=1 on list overflow
+// ra (optional): when given, the kernel continues with the exact re-rank (K4) + finalize of each query
 int launch_merge_lists(const TensorScanLists& lists, int nq, const TensorScanPlan& plan, float* ck, int32_t* ci,
-                       int32_t* ovf, unsigned long long* total_entries, cudaStream_t st);
+                       int32_t* ovf, unsigned long long* total_entries, const RerankArgs* ra, cudaStream_t st);
 
 }  // namespace b2f

@@ -35,6 +35,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "rerank.cuh"
 
 namespace b2f {
 
@@ -682,7 +683,7 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 // key bits, then -- only when equal keys straddle the cut -- over the 32 id bits), the k' survivors are
 // rank-sorted.  Output: ck/ci [nq][kp] ascending, padded with (FLT_MAX,-1).  ovf[q] = 1 when a list
 // overflowed (the query is then re-run by the exact scan).
-constexpr int MERGE_THREADS = 128;
+constexpr int MERGE_THREADS = kRerankThreads;  // 128: the fused kernel continues with the block-level re-rank
 constexpr int MERGE_MAX = 12288;  // composites held in shared memory (96 KB) at most
 
 __device__ __forceinline__ int block_count_le(const unsigned long long* comp, int M, unsigned long long bound, int* s_cnt,
@@ -699,13 +700,17 @@ __device__ __forceinline__ int block_count_le(const unsigned long long* comp, in
 __global__ void __launch_bounds__(MERGE_THREADS)
 merge_lists_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ counts, int nsplits, int kp, int list_cap,
                    int cap_entries, float* __restrict__ ck, int32_t* __restrict__ ci, int32_t* __restrict__ ovf,
-                   unsigned long long* __restrict__ total_entries) {
-    extern __shared__ __align__(16) unsigned long long comp[];  // [cap_entries] + survivors [kp]
+                   unsigned long long* __restrict__ total_entries, RerankArgs ra, int fused) {
+    extern __shared__ __align__(16) unsigned long long comp[];  // [cap_entries] + survivors [kp] + sorted (key,id) [kp] + re-rank scratch [kp]
     __shared__ int s_off[2 * kNumSMs + 2];
     __shared__ int s_cnt[3];
     __shared__ int s_nsurv;
     __shared__ int s_ovf;
     unsigned long long* surv = comp + cap_entries;
+    float* sk = reinterpret_cast<float*>(surv + kp);  // [kp] sorted coarse keys
+    int32_t* si = reinterpret_cast<int32_t*>(sk + kp);  // [kp]
+    float* ek = reinterpret_cast<float*>(si + kp);      // [kp] re-rank scratch
+    int32_t* ei = reinterpret_cast<int32_t*>(ek + kp);  // [kp]
     const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (warp == 0) {
         // exclusive prefix sum of the (clamped) list lengths, 32 splits at a time
@@ -801,14 +806,24 @@ merge_lists_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ c
             const unsigned long long mine = surv[t];
             int rank = 0;  // ties broken by slot, so ranks are a permutation even if composites repeat
             for (int j = 0; j < ns; j++) rank += (surv[j] < mine || (surv[j] == mine && j < t)) ? 1 : 0;
-            ck[(int64_t)q * kp + rank] = dec_key((uint32_t)(mine >> 32));
-            ci[(int64_t)q * kp + rank] = (int32_t)(uint32_t)(mine & 0xffffffffu);
+            sk[rank] = dec_key((uint32_t)(mine >> 32));
+            si[rank] = (int32_t)(uint32_t)(mine & 0xffffffffu);
         } else {
-            ck[(int64_t)q * kp + t] = FLT_MAX;
-            ci[(int64_t)q * kp + t] = -1;
+            sk[t] = FLT_MAX;
+            si[t] = -1;
         }
     }
     if (tid == 0) ovf[q] = s_ovf;
+    __syncthreads();
+    if (!fused) {
+        for (int t = tid; t < kp; t += MERGE_THREADS) {
+            ck[(int64_t)q * kp + t] = sk[t];
+            ci[(int64_t)q * kp + t] = si[t];
+        }
+        return;
+    }
+    // fused K4: exact fp32 re-rank of the kp candidates + certification + faiss-formatted output
+    rerank_block(ra, q, sk, si, ek, ei);
 }
 
 // ---- host side --------------------------------------------------------------------------------------
@@ -959,8 +974,7 @@ int launch_tensor_scan(const __nv_bfloat16* scan, int64_t dpad, const float* nor
         la.j = plan.list_j;
         la.g = plan.list_g;
         la.cap = plan.list_cap;
-        // "no information yet": 0x7f7f7f7f = 3.39e38, above every admissible key
-        B2F_CUDA(cudaMemsetAsync(lists.shared_thr, 0x7f, (size_t)nq_pad * plan.nlists * sizeof(float), st));  // [split][query]
+        // lists.shared_thr was filled with 0x7f7f7f7f (3.39e38, "no information yet") by the query-prep kernel
         if (plan.pair_mode)
             return l2 ? k2::launch_k2<0, true, true, true, true>(mq, mx, norms, n, nq, kblocks, plan, pk, pi, la, st)
                       : k2::launch_k2<0, false, true, true, true>(mq, mx, norms, n, nq, kblocks, plan, pk, pi, la, st);
@@ -981,19 +995,20 @@ int launch_tensor_scan(const __nv_bfloat16* scan, int64_t dpad, const float* nor
 }
 
 int launch_merge_lists(const TensorScanLists& lists, int nq, const TensorScanPlan& plan, float* ck, int32_t* ci,
-                       int32_t* ovf, unsigned long long* total_entries, cudaStream_t st) {
+                       int32_t* ovf, unsigned long long* total_entries, const RerankArgs* ra, cudaStream_t st) {
     if (nq <= 0) return B2F_OK;
     int cap_entries = plan.nlists * plan.list_cap;
     if (cap_entries > k2::MERGE_MAX) cap_entries = k2::MERGE_MAX;
-    const size_t smem = (size_t)(cap_entries + plan.kp) * 8;
+    const size_t smem = (size_t)(cap_entries + plan.kp) * 8 + (size_t)plan.kp * 16;
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
         B2F_CUDA(cudaFuncSetAttribute(k2::merge_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)((k2::MERGE_MAX + 64) * 8)));
-        configured = (size_t)(k2::MERGE_MAX + 64) * 8;
+                                      (int)((k2::MERGE_MAX + 64) * 8 + 64 * 16)));
+        configured = (size_t)(k2::MERGE_MAX + 64) * 8 + 64 * 16;
     }
     k2::merge_lists_kernel<<<nq, k2::MERGE_THREADS, smem, st>>>(reinterpret_cast<const uint2*>(lists.cand), lists.counts,
-                                                               plan.nlists, plan.kp, plan.list_cap, cap_entries, ck, ci, ovf, total_entries);
+                                                               plan.nlists, plan.kp, plan.list_cap, cap_entries, ck, ci, ovf, total_entries,
+                                                               ra ? *ra : RerankArgs{}, ra ? 1 : 0);
     B2F_CUDA(cudaGetLastError());
     return B2F_OK;
 }

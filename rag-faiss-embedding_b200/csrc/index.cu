@@ -655,16 +655,14 @@ int b2f_index_search(b2f_index* ix, int64_t nq64, const float* q, int64_t k64, f
         int32_t* fail_list = bump.take<int32_t>(nq);
         int32_t* fail_count = bump.take<int32_t>(4);  // [0] uncertified, [1] overflowed, [2..3] u64 list entries
         B2F_TRY(refresh_host_stats(ix, st));
-        B2F_CUDA(cudaMemsetAsync(fail_count, 0, 16, st));
-        B2F_TRY(launch_prep_queries(qd, nq, nq_pad, ix->d, qb, ix->dpad, qnorm, qerr, st));
+        // one launch: bf16 copy / norms of the queries, clear the 4 counters, reset the shared thresholds
+        B2F_TRY(launch_prep_queries(qd, nq, nq_pad, ix->d, qb, ix->dpad, qnorm, qerr, reinterpret_cast<uint32_t*>(fail_count), 4,
+                                    reinterpret_cast<uint32_t*>(lists.shared_thr),
+                                    plan.list_mode ? (int64_t)nq_pad * plan.nlists : 0, st));
         if (profile) B2F_CUDA(cudaEventRecord(get_event(ix, ev_main), st));
         B2F_TRY(launch_tensor_scan(ix->scan, ix->dpad, ix->norms, ix->ntotal, ix->metric, qb, nq, nq_pad, plan, pk, pi, lists, st));
         if (profile) B2F_CUDA(cudaEventRecord(get_event(ix, ev_main + 1), st));
         n_main = 1;
-        if (plan.list_mode)
-            B2F_TRY(launch_merge_lists(lists, nq, plan, ck, ci, ovf, reinterpret_cast<unsigned long long*>(fail_count + 2), st));
-        else
-            B2F_TRY(launch_merge_parts(pk, pi, nq, plan.nsplits, kp, kp, ck, ci, st));
         RerankArgs ra{};
         ra.rows_f32 = ix->storage == B2F_STORE_F32 ? ix->rows_f32 : nullptr;
         ra.rows_bf16 = ix->scan;
@@ -686,12 +684,22 @@ int b2f_index_search(b2f_index* ix, int64_t nq64, const float* q, int64_t k64, f
         ra.overflow = ovf;
         ra.out_key = xk;
         ra.out_id = xi;
+        ra.D = Dd;   // the re-rank writes faiss-formatted results directly (no separate finalize launch)
+        ra.I = Id;
+        ra.id_offset = P.id_offset;
         ra.fail_list = fail_list;
         ra.fail_count = fail_count;
-        B2F_TRY(launch_rerank(ra, st));
-        B2F_TRY(launch_finalize(xk, xi, nq, k, k, ix->metric, P.id_offset, nullptr, Dd, Id, st));
-        ix->st.launches += 5;
-        ix->st.last_launches += 5;
+        if (plan.list_mode) {
+            // K3b + K4 + finalize fused: per query, merge the lists, re-rank exactly, certify, write (D, I)
+            B2F_TRY(launch_merge_lists(lists, nq, plan, ck, ci, ovf, reinterpret_cast<unsigned long long*>(fail_count + 2), &ra, st));
+            ix->st.launches += 3;
+            ix->st.last_launches += 3;
+        } else {
+            B2F_TRY(launch_merge_parts(pk, pi, nq, plan.nsplits, kp, kp, ck, ci, st));
+            B2F_TRY(launch_rerank(ra, st));
+            ix->st.launches += 4;
+            ix->st.last_launches += 4;
+        }
         if (certify || plan.list_mode) {
             B2F_TRY(ensure_pinned(ix, 4096));
             int32_t* hcount = reinterpret_cast<int32_t*>(ix->pinned);
@@ -725,6 +733,10 @@ int b2f_index_search(b2f_index* ix, int64_t nq64, const float* q, int64_t k64, f
         ix->st.last_main_ms = ms;
         ix->st.last_total_ms = tot;
         ix->st.last_main_launches = n_main;
+        ix->st.prof_main_ms_sum += ms;
+        ix->st.prof_total_ms_sum += tot;
+        ix->st.prof_main_launches += n_main;
+        ix->st.prof_searches += 1;
     }
     return B2F_OK;
 }

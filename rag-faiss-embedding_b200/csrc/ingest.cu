@@ -217,7 +217,13 @@ int launch_synth(uint64_t seed, int64_t row0, int64_t nrows, int d, int normaliz
 // qb: [nq_pad, dpad] bf16 (zero padded), qnorm[r] = |bf16(q_r)|^2, qerr[r] = |q_r - bf16(q_r)|
 __global__ void __launch_bounds__(256)
 prep_queries_kernel(const float* __restrict__ q, int nq, int nq_pad, int d, __nv_bfloat16* __restrict__ qb, int64_t dpad,
-                    float* __restrict__ qnorm, float* __restrict__ qerr) {
+                    float* __restrict__ qnorm, float* __restrict__ qerr, uint32_t* __restrict__ zero, int zero_words,
+                    uint32_t* __restrict__ fill, int64_t fill_words) {
+    {
+        const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gn = (int64_t)gridDim.x * blockDim.x;
+        for (int64_t i = gt; i < zero_words; i += gn) zero[i] = 0u;
+        for (int64_t i = gt; i < fill_words; i += gn) fill[i] = 0x7f7f7f7fu;
+    }
     const int lane = threadIdx.x & 31;
     const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (r >= nq_pad) return;
@@ -239,9 +245,10 @@ prep_queries_kernel(const float* __restrict__ q, int nq, int nq_pad, int d, __nv
 }
 
 int launch_prep_queries(const float* q, int nq, int nq_pad, int d, __nv_bfloat16* qb, int64_t dpad, float* qnorm,
-                        float* qerr, cudaStream_t st) {
+                        float* qerr, uint32_t* zero, int zero_words, uint32_t* fill, int64_t fill_words, cudaStream_t st) {
     if (nq_pad <= 0) return B2F_OK;
-    prep_queries_kernel<<<(nq_pad + 7) / 8, 256, 0, st>>>(q, nq, nq_pad, d, qb, dpad, qnorm, qerr);
+    prep_queries_kernel<<<(nq_pad + 7) / 8, 256, 0, st>>>(q, nq, nq_pad, d, qb, dpad, qnorm, qerr, zero, zero_words, fill,
+                                                          fill_words);
     B2F_CUDA(cudaGetLastError());
     return B2F_OK;
 }
