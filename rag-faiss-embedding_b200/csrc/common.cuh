@@ -221,7 +221,9 @@ int launch_rerank(const RerankArgs& a, cudaStream_t st);
 // K2: tcgen05 / TMEM / TMA contraction with fused top-k (gemm_topk_sm100.cu)
 struct TensorScanPlan {
     int nq_tiles;      // ceil(nq / 128)
-    int nsplits;       // database streams per query tile
+    int nsplits;       // database streams per query tile (LIST mode: the smaller of the two per-tile counts)
+    int units;         // CTAs (or CTA pairs) launched
+    int tile_units;    // query tiles (pair tiles) the units are dealt over
     int nlists;        // LIST mode: candidate lists per query = nsplits x column halves (virtual splits)
     int kp;            // candidates kept per query
     int list_mode;     // 1: shared-threshold candidate lists (K3b merge), 0: per-thread heaps (K3 merge)

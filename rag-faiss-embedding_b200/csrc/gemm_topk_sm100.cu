@@ -212,8 +212,8 @@ struct ListArgs {
     float* shared_thr;   // [nq_pad][nsplits]  each split's published j-th best key (init: huge)
     uint2* cand;         // [nq_pad * nsplits][cap]  (key bits, row id)
     int32_t* counts;     // [nq_pad * nsplits]  entries appended (may exceed cap => overflow)
-    int j;               // rows each split vouches for
-    int g;               // splits consulted: g * j >= k'
+    int kp;              // k': every query's lists together must cover the k' best
+    int nl_stride;       // lists per query allocated (the largest per-tile list count)
     int cap;             // entries per list
 };
 
@@ -300,8 +300,14 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     const int units_per_split = PAIR ? (nq_tiles >> 1) : nq_tiles;
     const int qt = PAIR ? (unit % units_per_split) * 2 + (int)cta_rank : unit % units_per_split;
     const int split = unit / units_per_split;
+    // Units (CTAs / CTA pairs) are dealt round-robin over the query tiles, so when the unit count is not a
+    // multiple of the tile count the first `extra` tiles get one more database split than the others:
+    // every SM stays busy (nq = 4096: 74 pairs over 16 pair tiles = 5,5,...,4 splits instead of 4 x 16).
+    const int total_units = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int my_nsplits = LIST ? total_units / units_per_split + ((unit % units_per_split) < (total_units % units_per_split) ? 1 : 0)
+                                : nsplits;
     const int64_t ntiles = (n + BN - 1) / BN;
-    const int64_t t_begin = ntiles * split / nsplits, t_end = ntiles * (split + 1) / nsplits;
+    const int64_t t_begin = ntiles * split / my_nsplits, t_end = ntiles * (split + 1) / my_nsplits;
     const int my_tiles = (int)(t_end - t_begin);
 
     if (warp == 0 && lane == 0) {
@@ -488,13 +494,15 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             // Every (database split, column half) pair is a "virtual split" with its own list and its own
             // published j-th best; nvs = nsplits * HALVES of them cooperate on each query.
             const float kInf = __int_as_float(0x7f800000);
-            const int vsplit = split * HALVES + half, nvs = nsplits * HALVES;
+            const int vsplit = split * HALVES + half, nvs = my_nsplits * HALVES;
+            const int jv = (la.kp + nvs - 1) / nvs;      // rows each virtual split vouches for
+            const int gv = (la.kp + jv - 1) / jv;        // virtual splits consulted: gv * jv >= k'
             float best[JSLOTS];  // ascending; the first JSLOTS - j slots are pinned at -inf, so best[JSLOTS-1] = j-th best
 #pragma unroll
-            for (int i = 0; i < JSLOTS; i++) best[i] = (i < JSLOTS - la.j) ? -kInf : kInf;
+            for (int i = 0; i < JSLOTS; i++) best[i] = (i < JSLOTS - jv) ? -kInf : kInf;
             float thr = 3.0e38f, pub = kInf;  // refreshed before the first compare; never +inf (padding rows have key +inf)
             int cnt = 0;
-            uint2* mylist = la.cand + ((int64_t)(active ? qrow : 0) * nvs + vsplit) * la.cap;
+            uint2* mylist = la.cand + ((int64_t)(active ? qrow : 0) * la.nl_stride + vsplit) * la.cap;
             // shared thresholds are laid out [virtual split][query] so that a warp's loads for one split coalesce
             float* gq = la.shared_thr + (active ? qrow : 0);
             const int64_t gstride = (int64_t)nq_tiles * BM;
@@ -505,13 +513,13 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 }
                 float t = -kInf;
 #pragma unroll 1
-                for (int i0 = 0; i0 < la.g; i0 += 16) {  // 16 independent L2 loads in flight
+                for (int i0 = 0; i0 < gv; i0 += 16) {  // 16 independent L2 loads in flight
                     float v[16];
 #pragma unroll
                     for (int u = 0; u < 16; u++) {
                         int s2 = vsplit + i0 + u;
                         if (s2 >= nvs) s2 -= nvs;
-                        v[u] = (i0 + u < la.g) ? __ldcg(gq + (int64_t)s2 * gstride) : -kInf;
+                        v[u] = (i0 + u < gv) ? __ldcg(gq + (int64_t)s2 * gstride) : -kInf;
                     }
 #pragma unroll
                     for (int u = 0; u < 16; u++) t = fmaxf(t, v[u]);
@@ -605,7 +613,7 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                     for (int u = 0; u < 8; u++)
                         if (i0 + u < have && __uint_as_float(e[u].x) <= thr) mylist[w++] = e[u];
                 }
-                la.counts[(int64_t)qrow * nvs + vsplit] = cnt > la.cap ? cnt : w;  // > cap marks an overflow
+                la.counts[(int64_t)qrow * la.nl_stride + vsplit] = cnt > la.cap ? cnt : w;  // > cap marks an overflow
             }
         } else {
             // ---- HEAP mode: thread-private max-heap of k' in shared memory ------------------------------
@@ -698,8 +706,8 @@ __device__ __forceinline__ int block_count_le(const unsigned long long* comp, in
 }
 
 __global__ void __launch_bounds__(MERGE_THREADS)
-merge_lists_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ counts, int nsplits, int kp, int list_cap,
-                   int cap_entries, float* __restrict__ ck, int32_t* __restrict__ ci, int32_t* __restrict__ ovf,
+merge_lists_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ counts, int nl_stride, int tile_queries,
+                   int ntile_units, int total_units, int halves, int kp, int list_cap, int cap_entries, float* __restrict__ ck, int32_t* __restrict__ ci, int32_t* __restrict__ ovf,
                    unsigned long long* __restrict__ total_entries, RerankArgs ra, int fused) {
     extern __shared__ __align__(16) unsigned long long comp[];  // [cap_entries] + survivors [kp] + sorted (key,id) [kp] + re-rank scratch [kp]
     __shared__ int s_off[2 * kNumSMs + 2];
@@ -712,12 +720,15 @@ merge_lists_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ c
     float* ek = reinterpret_cast<float*>(si + kp);      // [kp] re-rank scratch
     int32_t* ei = reinterpret_cast<int32_t*>(ek + kp);  // [kp]
     const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // lists of this query: (database splits of its tile) x (column halves); see the kernel's my_nsplits
+    const int tile = q / tile_queries;
+    const int nsplits = (total_units / ntile_units + (tile < total_units % ntile_units ? 1 : 0)) * halves;
     if (warp == 0) {
         // exclusive prefix sum of the (clamped) list lengths, 32 splits at a time
         int run = 0, o = 0;
         for (int s0 = 0; s0 < nsplits; s0 += 32) {
             const int s = s0 + lane;
-            int c = s < nsplits ? counts[(int64_t)q * nsplits + s] : 0;
+            int c = s < nsplits ? counts[(int64_t)q * nl_stride + s] : 0;
             if (c > list_cap) {
                 c = list_cap;
                 o = 1;
@@ -757,7 +768,7 @@ merge_lists_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ c
                     if (s_off[mid] <= i) lo = mid;
                     else hi = mid - 1;
                 }
-                e[u] = cand[((int64_t)q * nsplits + lo) * list_cap + (i - s_off[lo])];
+                e[u] = cand[((int64_t)q * nl_stride + lo) * list_cap + (i - s_off[lo])];
             }
         }
 #pragma unroll
@@ -877,7 +888,7 @@ static int launch_k2(const CUtensorMap& mq, const CUtensorMap& mx, const float* 
     }
     if constexpr (PAIR) {
         cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3((unsigned)(plan.nq_tiles * plan.nsplits));  // nq_tiles is even: 2 CTAs per cluster
+        cfg.gridDim = dim3((unsigned)(2 * plan.units));  // one cluster of 2 CTAs per unit
         cfg.blockDim = dim3(k2_threads(LIST));
         cfg.dynamicSmemBytes = smem;
         cfg.stream = st;
@@ -890,7 +901,7 @@ static int launch_k2(const CUtensorMap& mq, const CUtensorMap& mx, const float* 
         cfg.numAttrs = 1;
         B2F_CUDA(cudaLaunchKernelEx(&cfg, kern, mq, mx, norms, n, nq, kblocks, plan.nq_tiles, plan.nsplits, pk, pi, la));
     } else {
-        kern<<<plan.nq_tiles * plan.nsplits, k2_threads(LIST), smem, st>>>(mq, mx, norms, n, nq, kblocks, plan.nq_tiles, plan.nsplits,
+        kern<<<plan.units, k2_threads(LIST), smem, st>>>(mq, mx, norms, n, nq, kblocks, plan.nq_tiles, plan.nsplits,
                                                                   pk, pi, la);
     }
     B2F_CUDA(cudaGetLastError());
@@ -906,49 +917,60 @@ int plan_tensor_scan(int nq, int64_t n, int d, int kp, TensorScanPlan* plan) {
     plan->nq_tiles = (nq + k2::BM - 1) / k2::BM;
     plan->pair_mode = 0;
     plan->list_mode = 0;
+    const int halves = k2::EPI_WARPS_LIST / 4;
     const int64_t ntiles = (n + k2::BN - 1) / k2::BN;
     const int kblocks = (d + k2::BK - 1) / k2::BK;
-    int ns = 0, j = 0;
-    // (1) CTA pairs (cta_group::2) halve the L2->SM traffic of the database blocks; worth it once the
-    //     batch spans several 128-query tiles (an odd tile count wastes half a pair on padding).
-    const char* no_pair = getenv("B200FLAT_NO_PAIR");
-    if (!(no_pair && no_pair[0] == '1') && kblocks <= k2::QRES_MAX_KB && plan->nq_tiles >= 2 &&
-        (plan->nq_tiles % 2 == 0 || plan->nq_tiles >= 7)) {
-        const int npt = (plan->nq_tiles + 1) / 2;
-        int nsp = (kNumSMs / 2) / npt;
-        if (nsp > ntiles / 2) nsp = (int)(ntiles / 2);
-        if (nsp >= 1 && (kp + 2 * nsp - 1) / (2 * nsp) <= k2::JSLOTS) {
-            plan->pair_mode = 1;
-            plan->list_mode = 1;
-            plan->nq_tiles = 2 * npt;
-            ns = nsp;
+    // A "unit" is one CTA, or one CTA pair (cta_group::2).  Units are dealt round-robin over the query
+    // tiles; a tile with s units splits the database s ways.  LIST mode lets s differ by one between tiles
+    // (all SMs busy); it needs every unit resident at once (one wave), at least two database tiles per
+    // split, and j = ceil(k' / lists per query) <= JSLOTS.
+    auto try_list = [&](int tiles, int max_units, int* units_out) -> bool {
+        int units = max_units;
+        if (tiles > units) return false;                      // more than one wave
+        int ns_max = (units + tiles - 1) / tiles;
+        if ((int64_t)ns_max * 2 > ntiles) {                    // short database: uniform, fewer splits
+            const int ns = (int)(ntiles / 2);
+            if (ns < 1) return false;
+            units = tiles * ns;
         }
-    }
-    if (!plan->pair_mode) {
-        ns = kNumSMs / plan->nq_tiles;
+        const int ns_min = units / tiles;
+        if ((kp + halves * ns_min - 1) / (halves * ns_min) > k2::JSLOTS) return false;
+        *units_out = units;
+        return true;
+    };
+    // (1) CTA pairs halve the L2->SM traffic of the database blocks; worth it once the batch spans several
+    //     128-query tiles (an odd tile count wastes half a pair on padding).
+    const char* no_pair = getenv("B200FLAT_NO_PAIR");
+    int units = 0;
+    if (!(no_pair && no_pair[0] == '1') && kblocks <= k2::QRES_MAX_KB && plan->nq_tiles >= 2 &&
+        (plan->nq_tiles % 2 == 0 || plan->nq_tiles >= 7) && try_list((plan->nq_tiles + 1) / 2, kNumSMs / 2, &units)) {
+        plan->pair_mode = 1;
+        plan->list_mode = 1;
+        plan->nq_tiles = 2 * ((plan->nq_tiles + 1) / 2);
+        plan->tile_units = plan->nq_tiles / 2;
+    } else if (try_list(plan->nq_tiles, kNumSMs, &units)) {
+        plan->list_mode = 1;
+        plan->tile_units = plan->nq_tiles;
+    } else {
+        // (2) HEAP mode: uniform splits, any number of waves
+        int ns = kNumSMs / plan->nq_tiles;
         if (ns < 1) ns = 1;
         if (ns > ntiles) ns = (int)ntiles;
-        // (2) LIST mode needs every split resident at once (one wave), j = ceil(kp / nsplits) <= JSLOTS rows
-        //     vouched per split, and at least two tiles per split so every split can vouch for its rows early.
-        if (plan->nq_tiles * ns <= kNumSMs) {
-            int ns_list = ns;
-            if (ntiles < 2 * (int64_t)ns_list) ns_list = (int)(ntiles / 2);
-            if (ns_list >= 1 && (kp + 2 * ns_list - 1) / (2 * ns_list) <= k2::JSLOTS) {
-                plan->list_mode = 1;
-                ns = ns_list;
-            }
-        }
+        plan->tile_units = plan->nq_tiles;
+        units = plan->nq_tiles * ns;
     }
-    plan->nsplits = ns;
-    // LIST mode: every (split, column half) is a virtual split with its own list and published value
-    plan->nlists = plan->list_mode ? ns * (k2::EPI_WARPS_LIST / 4) : ns;
-    j = (kp + plan->nlists - 1) / plan->nlists;
+    plan->units = units;
+    const int ns_min = units / plan->tile_units, ns_max = (units + plan->tile_units - 1) / plan->tile_units;
+    plan->nsplits = ns_min;  // HEAP mode: exact; LIST mode: the smaller of the two per-tile split counts
+    plan->nlists = plan->list_mode ? ns_max * halves : ns_min;  // lists allocated per query (stride)
+    const int nl_min = plan->list_mode ? ns_min * halves : ns_min;
+    const int j = (kp + nl_min - 1) / nl_min;
     plan->list_j = j;
     plan->list_g = (kp + j - 1) / j;
-    // expected list length ~ 32 (blind first chunk) + (j + spread) * ln(rows per split / 32); 2.5x headroom
+    // expected list length ~ 32 (blind first chunk) + (j + spread) * ln(rows per list / 32); 2.5x headroom
     {
-        const double rows_per_split = (double)n / plan->nlists;
-        const double expected = 32.0 + (j + 2.5) * log(rows_per_split > 64.0 ? rows_per_split / 32.0 : 2.0);
+        const double rows_per_list = (double)n / nl_min;
+        const double expected = 32.0 + (j + 2.5) * log(rows_per_list > 64.0 ? rows_per_list / 32.0 : 2.0);
         int cap = (int)(2.5 * expected);
         cap = (cap + 63) / 64 * 64;
         if (cap < k2::LIST_CAP_MIN) cap = k2::LIST_CAP_MIN;
@@ -971,8 +993,8 @@ int launch_tensor_scan(const __nv_bfloat16* scan, int64_t dpad, const float* nor
         la.shared_thr = lists.shared_thr;
         la.cand = reinterpret_cast<uint2*>(lists.cand);
         la.counts = lists.counts;
-        la.j = plan.list_j;
-        la.g = plan.list_g;
+        la.kp = plan.kp;
+        la.nl_stride = plan.nlists;
         la.cap = plan.list_cap;
         // lists.shared_thr was filled with 0x7f7f7f7f (3.39e38, "no information yet") by the query-prep kernel
         if (plan.pair_mode)
@@ -1007,7 +1029,8 @@ int launch_merge_lists(const TensorScanLists& lists, int nq, const TensorScanPla
         configured = (size_t)(k2::MERGE_MAX + 64) * 8 + 64 * 16;
     }
     k2::merge_lists_kernel<<<nq, k2::MERGE_THREADS, smem, st>>>(reinterpret_cast<const uint2*>(lists.cand), lists.counts,
-                                                               plan.nlists, plan.kp, plan.list_cap, cap_entries, ck, ci, ovf, total_entries,
+                                                               plan.nlists, plan.pair_mode ? 2 * k2::BM : k2::BM, plan.tile_units, plan.units,
+                                                               k2::EPI_WARPS_LIST / 4, plan.kp, plan.list_cap, cap_entries, ck, ci, ovf, total_entries,
                                                                ra ? *ra : RerankArgs{}, ra ? 1 : 0);
     B2F_CUDA(cudaGetLastError());
     return B2F_OK;
