@@ -911,8 +911,7 @@ static int launch_k2(const CUtensorMap& mq, const CUtensorMap& mx, const float* 
 }  // namespace k2
 
 int plan_tensor_scan(int nq, int64_t n, int d, int kp, TensorScanPlan* plan) {
-    if (kp != 32 && kp != 64) return B2F_EINVAL;
-    if (n <= 0 || nq <= 0) return B2F_EINVAL;
+    if (kp < 8 || kp > 256 || n <= 0 || nq <= 0) return B2F_EINVAL;
     plan->kp = kp;
     plan->nq_tiles = (nq + k2::BM - 1) / k2::BM;
     plan->pair_mode = 0;
@@ -952,7 +951,8 @@ int plan_tensor_scan(int nq, int64_t n, int d, int kp, TensorScanPlan* plan) {
         plan->list_mode = 1;
         plan->tile_units = plan->nq_tiles;
     } else {
-        // (2) HEAP mode: uniform splits, any number of waves
+        // (2) HEAP mode: uniform splits, any number of waves; the heaps exist for k' = 32 and 64 only
+        if (kp != 32 && kp != 64) return B2F_EINVAL;
         int ns = kNumSMs / plan->nq_tiles;
         if (ns < 1) ns = 1;
         if (ns > ntiles) ns = (int)ntiles;
@@ -1025,8 +1025,8 @@ int launch_merge_lists(const TensorScanLists& lists, int nq, const TensorScanPla
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
         B2F_CUDA(cudaFuncSetAttribute(k2::merge_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)((k2::MERGE_MAX + 64) * 8 + 64 * 16)));
-        configured = (size_t)(k2::MERGE_MAX + 64) * 8 + 64 * 16;
+                                      (int)((k2::MERGE_MAX + 256) * 8 + 256 * 16)));
+        configured = (size_t)(k2::MERGE_MAX + 256) * 8 + 256 * 16;
     }
     k2::merge_lists_kernel<<<nq, k2::MERGE_THREADS, smem, st>>>(reinterpret_cast<const uint2*>(lists.cand), lists.counts,
                                                                plan.nlists, plan.pair_mode ? 2 * k2::BM : k2::BM, plan.tile_units, plan.units,

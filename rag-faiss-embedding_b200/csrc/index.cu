@@ -274,13 +274,28 @@ size_t scan_ws_bytes(int k) {
     return 2 * (g * mp * k * 4 + 256) + 2 * (g * k * 4 + 256) + 4096;
 }
 
+// Candidates kept per query by the tensor pass.  The slack above k must cover the rows whose coarse
+// (bf16) key can fall inside the rounding band around the k-th result; that count grows with k (the
+// neighbour density at rank k), hence ~0.9 k with a floor of 22.  32 / 64 are also the heap sizes of HEAP
+// mode; larger values (multiples of 8, up to 256) exist in LIST mode only.  0 = k too large for K2.
 int tensor_kprime(int k, int slack) {
-    int kp = slack > 0 ? k + slack : (k + 22 > 2 * k ? k + 22 : 2 * k);
-    // the fused epilogue keeps per-thread candidate buffers of a few fixed sizes
+    int extra = slack > 0 ? slack : ((9 * k + 9) / 10 > 22 ? (9 * k + 9) / 10 : 22);
+    int kp = k + extra;
     if (kp <= 32) return 32;
     if (kp <= 64) return 64;
-    if (kp <= 128) return 128;
-    return kp;  // unsupported by K2; caller falls back to the scan
+    kp = (kp + 7) / 8 * 8;
+    return kp <= 256 ? kp : 0;
+}
+
+// Largest query chunk (<= nq) the tensor path can take in one pass: big k' with a big batch leaves too few
+// database splits per query tile for the shared-threshold lists, so the batch is processed in chunks.
+int plan_tensor_chunked(int nq, int64_t n, int d, int kp, TensorScanPlan* plan) {
+    int chunk = nq;
+    while (true) {
+        if (plan_tensor_scan(chunk, n, d, kp, plan) == B2F_OK) return chunk;
+        if (chunk <= 128) return 0;
+        chunk = ((chunk / 2 + 127) / 128) * 128;
+    }
 }
 
 }  // namespace
@@ -574,12 +589,13 @@ int b2f_index_search(b2f_index* ix, int64_t nq64, const float* q, int64_t k64, f
 
     int algo = P.algo;
     const int scan_max = P.scan_max_nq > 0 ? P.scan_max_nq : 1;
-    int kp = tensor_kprime(k, P.slack);
+    const int kp = tensor_kprime(k, P.slack);
     TensorScanPlan plan{};
-    bool tensor_ok = kp <= 128 && ix->ntotal > 0 && plan_tensor_scan(nq, ix->ntotal, ix->d, kp, &plan) == B2F_OK;
+    const int chunk_nq = (kp > 0 && ix->ntotal > 0) ? plan_tensor_chunked(nq, ix->ntotal, ix->d, kp, &plan) : 0;
+    const bool tensor_ok = chunk_nq > 0;
     if (algo == B2F_ALGO_AUTO) algo = (nq <= scan_max || !tensor_ok) ? B2F_ALGO_SCAN : B2F_ALGO_TENSOR;
     if (algo == B2F_ALGO_TENSOR && !tensor_ok && ix->ntotal > 0) {
-        set_error("tensor path unavailable for k=%d (k' = %d > 128) or this shape", k, kp);
+        set_error("tensor path unavailable for k=%d (k' = %d) on this shape", k, kp);
         return B2F_EINVAL;
     }
     const int certify = P.certify >= 0 ? 1 : 0;
@@ -594,13 +610,13 @@ int b2f_index_search(b2f_index* ix, int64_t nq64, const float* q, int64_t k64, f
         if (plan.list_mode) {
             need += align_up(nq_pad * plan.nlists * 4, 256) * 2;                       // shared thresholds + counts
             need += align_up(nq_pad * plan.nlists * (size_t)plan.list_cap * 8, 256);   // candidate lists
-            need += align_up((size_t)nq * 4, 256);                                      // overflow flags
+            need += align_up((size_t)chunk_nq * 4, 256);                                // overflow flags
         } else {
             need += 2 * align_up(nq_pad * plan.nsplits * kp * 4, 256);  // partial lists
         }
-        need += 2 * align_up((size_t)nq * kp * 4, 256);             // merged coarse
-        need += 2 * align_up((size_t)nq * k * 4, 256);              // exact
-        need += align_up((size_t)nq * 4, 256) + 256;                // fail list + count
+        need += 2 * align_up((size_t)chunk_nq * kp * 4, 256);       // merged coarse
+        need += 2 * align_up((size_t)chunk_nq * k * 4, 256);        // exact
+        need += align_up((size_t)chunk_nq * 4, 256) + 256;          // fail list + count
     }
     B2F_TRY(ensure_ws(ix, need));
     Bump bump(ix->ws);
@@ -632,6 +648,7 @@ int b2f_index_search(b2f_index* ix, int64_t nq64, const float* q, int64_t k64, f
     } else {
         const int nq_pad = plan.nq_tiles * 128;
         ix->st.last_kprime = kp;
+        ix->st.last_list_entries = 0;
         __nv_bfloat16* qb = bump.take<__nv_bfloat16>((size_t)nq_pad * ix->dpad);
         float* qnorm = bump.take<float>(nq_pad);
         float* qerr = bump.take<float>(nq_pad);
@@ -643,36 +660,41 @@ int b2f_index_search(b2f_index* ix, int64_t nq64, const float* q, int64_t k64, f
             lists.shared_thr = bump.take<float>((size_t)nq_pad * plan.nlists);
             lists.counts = bump.take<int32_t>((size_t)nq_pad * plan.nlists);
             lists.cand = bump.take<uint2>((size_t)nq_pad * plan.nlists * plan.list_cap);
-            ovf = bump.take<int32_t>(nq);
+            ovf = bump.take<int32_t>(chunk_nq);
         } else {
             pk = bump.take<float>((size_t)nq_pad * plan.nsplits * kp);
             pi = bump.take<int32_t>((size_t)nq_pad * plan.nsplits * kp);
         }
-        float* ck = bump.take<float>((size_t)nq * kp);
-        int32_t* ci = bump.take<int32_t>((size_t)nq * kp);
-        float* xk = bump.take<float>((size_t)nq * k);
-        int32_t* xi = bump.take<int32_t>((size_t)nq * k);
-        int32_t* fail_list = bump.take<int32_t>(nq);
+        float* ck = bump.take<float>((size_t)chunk_nq * kp);
+        int32_t* ci = bump.take<int32_t>((size_t)chunk_nq * kp);
+        float* xk = bump.take<float>((size_t)chunk_nq * k);
+        int32_t* xi = bump.take<int32_t>((size_t)chunk_nq * k);
+        int32_t* fail_list = bump.take<int32_t>(chunk_nq);
         int32_t* fail_count = bump.take<int32_t>(4);  // [0] uncertified, [1] overflowed, [2..3] u64 list entries
         B2F_TRY(refresh_host_stats(ix, st));
+        for (int c0 = 0; c0 < nq; c0 += chunk_nq) {
+        const int cn = nq - c0 < chunk_nq ? nq - c0 : chunk_nq;  // queries in this pass (the plan covers chunk_nq)
+        const float* qc = qd + (int64_t)c0 * ix->d;
+        float* Dc = Dd + (int64_t)c0 * k;
+        int64_t* Ic = Id + (int64_t)c0 * k;
         // one launch: bf16 copy / norms of the queries, clear the 4 counters, reset the shared thresholds
-        B2F_TRY(launch_prep_queries(qd, nq, nq_pad, ix->d, qb, ix->dpad, qnorm, qerr, reinterpret_cast<uint32_t*>(fail_count), 4,
+        B2F_TRY(launch_prep_queries(qc, cn, nq_pad, ix->d, qb, ix->dpad, qnorm, qerr, reinterpret_cast<uint32_t*>(fail_count), 4,
                                     reinterpret_cast<uint32_t*>(lists.shared_thr),
                                     plan.list_mode ? (int64_t)nq_pad * plan.nlists : 0, st));
-        if (profile) B2F_CUDA(cudaEventRecord(get_event(ix, ev_main), st));
-        B2F_TRY(launch_tensor_scan(ix->scan, ix->dpad, ix->norms, ix->ntotal, ix->metric, qb, nq, nq_pad, plan, pk, pi, lists, st));
-        if (profile) B2F_CUDA(cudaEventRecord(get_event(ix, ev_main + 1), st));
-        n_main = 1;
+        if (profile) B2F_CUDA(cudaEventRecord(get_event(ix, ev_main + 2 * (size_t)n_main), st));
+        B2F_TRY(launch_tensor_scan(ix->scan, ix->dpad, ix->norms, ix->ntotal, ix->metric, qb, cn, nq_pad, plan, pk, pi, lists, st));
+        if (profile) B2F_CUDA(cudaEventRecord(get_event(ix, ev_main + 2 * (size_t)n_main + 1), st));
+        n_main++;
         RerankArgs ra{};
         ra.rows_f32 = ix->storage == B2F_STORE_F32 ? ix->rows_f32 : nullptr;
         ra.rows_bf16 = ix->scan;
         ra.pitch_bf16 = ix->dpad;
-        ra.q = qd;
+        ra.q = qc;
         ra.qnorm = qnorm;
         ra.qerr = qerr;
         ra.cand_key = ck;
         ra.cand_id = ci;
-        ra.nq = nq;
+        ra.nq = cn;
         ra.kp = kp;
         ra.k = k;
         ra.d = ix->d;
@@ -684,18 +706,18 @@ int b2f_index_search(b2f_index* ix, int64_t nq64, const float* q, int64_t k64, f
         ra.overflow = ovf;
         ra.out_key = xk;
         ra.out_id = xi;
-        ra.D = Dd;   // the re-rank writes faiss-formatted results directly (no separate finalize launch)
-        ra.I = Id;
+        ra.D = Dc;   // the re-rank writes faiss-formatted results directly (no separate finalize launch)
+        ra.I = Ic;
         ra.id_offset = P.id_offset;
         ra.fail_list = fail_list;
         ra.fail_count = fail_count;
         if (plan.list_mode) {
             // K3b + K4 + finalize fused: per query, merge the lists, re-rank exactly, certify, write (D, I)
-            B2F_TRY(launch_merge_lists(lists, nq, plan, ck, ci, ovf, reinterpret_cast<unsigned long long*>(fail_count + 2), &ra, st));
+            B2F_TRY(launch_merge_lists(lists, cn, plan, ck, ci, ovf, reinterpret_cast<unsigned long long*>(fail_count + 2), &ra, st));
             ix->st.launches += 3;
             ix->st.last_launches += 3;
         } else {
-            B2F_TRY(launch_merge_parts(pk, pi, nq, plan.nsplits, kp, kp, ck, ci, st));
+            B2F_TRY(launch_merge_parts(pk, pi, cn, plan.nsplits, kp, kp, ck, ci, st));
             B2F_TRY(launch_rerank(ra, st));
             ix->st.launches += 4;
             ix->st.last_launches += 4;
@@ -707,13 +729,15 @@ int b2f_index_search(b2f_index* ix, int64_t nq64, const float* q, int64_t k64, f
             B2F_CUDA(cudaStreamSynchronize(st));
             const int nfail = hcount[0];
             ix->st.overflow_queries += hcount[1];
-            ix->st.last_list_entries = *reinterpret_cast<int64_t*>(hcount + 2);
+            ix->st.last_list_entries += *reinterpret_cast<int64_t*>(hcount + 2);
             if (nfail > 0) {
                 ix->st.fallback_queries += nfail;
                 int dummy = 0;
-                B2F_TRY(run_scan(ix, qd, fail_list, nfail, k, Dd, Id, P.id_offset, bump, st, false, 0, &dummy));
+                Bump fb = bump;  // the fallback's scratch is carved after the tensor buffers, per chunk
+                B2F_TRY(run_scan(ix, qc, fail_list, nfail, k, Dc, Ic, P.id_offset, fb, st, false, 0, &dummy));
             }
         }
+        }  // chunk loop
     }
     if (profile) B2F_CUDA(cudaEventRecord(get_event(ix, ev_tot + 1), st));
     if (host) {

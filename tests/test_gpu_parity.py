@@ -172,6 +172,22 @@ def test_tensor_vs_oracle(m, metric, n, d, nq, k):
         assert st["overflow_queries"] == 0, st
 
 
+@pytest.mark.parametrize("metric,normalize,n,d,nq,k", [
+    (0, True, 60000, 768, 70, 100),     # config 3's shape in small: normalised inner product, k = 100 (k' = 192)
+    (1, False, 40000, 384, 300, 100),
+    (1, False, 30000, 64, 4096, 100),   # big batch x big k': processed in query chunks
+    (0, False, 20000, 128, 33, 128),    # largest k served by the tensor path (k' = 256)
+])
+def test_tensor_large_k(m, metric, normalize, n, d, nq, k):
+    xb = orc.c_synth_rows(1234, 0, n, d, normalize)
+    xq = orc.c_synth_rows(5678, 0, nq, d, normalize)
+    ix = _make(m, xb, metric).set_search_params(algo=m.ALGO_TENSOR)
+    D, I = ix.search(xq, k)
+    _check(D, I, *orc.np_search_f64(xb, xq, k, metric), metric)
+    st = ix.stats()
+    assert st["last_algo"] == m.ALGO_TENSOR and st["last_kprime"] >= k + 22 and st["overflow_queries"] == 0, st
+
+
 def test_tensor_hard_inputs(m):
     """Near-duplicates and mean-shifted rows (the fixture's distribution: norm ~7.7, tiny relative gaps)
     stress the bf16 coarse pass; certification + exact fallback must keep results exact."""
