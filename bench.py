@@ -49,6 +49,12 @@ WORKLOADS = {
                       label="synthetic 1Mx384 fp32 flat L2, 4096 queries, k=10 (large-batch series)"),
     "c2_nq32": dict(n=1_000_000, d=384, nq=32, k=10, metric=1, normalize=False, storage="fp32",
                     label="synthetic 1Mx384 fp32 flat L2, 32 queries, k=10 (small-batch series)"),
+    "c3_nq1": dict(n=10_000_000, d=768, nq=1, k=100, metric=0, normalize=True, storage="fp32",
+                   label="synthetic 10Mx768 flat inner-product (normalized), batch 1, k=100 (BASELINE configs[2])"),
+    "c3_nq32": dict(n=10_000_000, d=768, nq=32, k=100, metric=0, normalize=True, storage="fp32",
+                    label="synthetic 10Mx768 flat inner-product (normalized), batch 32, k=100 (BASELINE configs[2])"),
+    "c3_nq4096": dict(n=10_000_000, d=768, nq=4096, k=100, metric=0, normalize=True, storage="fp32",
+                      label="synthetic 10Mx768 flat inner-product (normalized), batch 4096, k=100 (BASELINE configs[2])"),
     "c4shard": dict(n=12_500_000, d=384, nq=4096, k=10, metric=1, normalize=False, storage="bf16",
                     label="synthetic 12.5Mx384 bf16 flat L2 per GPU (config 4 shard), 4096 queries, k=10"),
 }
@@ -311,7 +317,10 @@ def main():
     prof1 = ix.stats()
     # per-launch time of the dominant kernel: CUDA events recorded by the library around every launch in
     # the timed region (running sums, read once so that the host loop stays tight)
-    main_ms = [(prof1["prof_main_ms_sum"] - prof0["prof_main_ms_sum"]) / max(prof1["prof_main_launches"] - prof0["prof_main_launches"], 1)]
+    n_launch = max(prof1["prof_main_launches"] - prof0["prof_main_launches"], 1)
+    n_search = max(prof1["prof_searches"] - prof0["prof_searches"], 1)
+    launches_per_search = n_launch / n_search   # > 1 when a big batch x big k' is processed in query chunks
+    main_ms = [(prof1["prof_main_ms_sum"] - prof0["prof_main_ms_sum"]) / n_launch]
     total_ms = [(prof1["prof_total_ms_sum"] - prof0["prof_total_ms_sum"]) / max(prof1["prof_searches"] - prof0["prof_searches"], 1)]
     st = ix.stats()
     launches = st["launches"] - launches0 + (args.steps if world > 1 else 0)  # + the merge kernel per step
@@ -338,7 +347,7 @@ def main():
         elem = 2 if (used_algo == b2f.ALGO_TENSOR or storage == b2f.STORE_BF16) else 4
         dpad = (d + 63) // 64 * 64 if elem == 2 else d
         if used_algo == b2f.ALGO_TENSOR and nq > 128:
-            flops = 2.0 * nq * rows_local * d
+            flops = 2.0 * nq * rows_local * d / launches_per_search   # per launch
             ach = flops / (kernel_ms * 1e-3) / 1e12
             roof = {"bound": "tensor", "achieved": round(ach, 2), "peak": peaks["tf"], "unit": "TFLOP/s",
                     "frac": round(ach / peaks["tf"], 4), "traffic": None}
@@ -358,10 +367,12 @@ def main():
             pass
         roof["kernel"] = "tensor_scan_kernel (K2 tcgen05)" if used_algo == b2f.ALGO_TENSOR else "scan_kernel (K1)"
         roof["kernel_ms"] = round(kernel_ms, 4)
+        roof["launches_per_search"] = round(launches_per_search, 2)
         roof["peak_source"] = peaks["src"] + (" burst" if roof["bound"] == "tensor" else "")
         roof["pipeline_ms"] = round(statistics.mean(total_ms), 4)
         line = {
-            "metric": "queries/sec @k=10 (flat L2, 384-d)", "value": round(nq / (ms_step * 1e-3), 1), "unit": "queries/sec",
+            "metric": "queries/sec @k=%d (flat %s, %d-d)" % (k, "L2" if wl["metric"] == 1 else "IP", d),
+            "value": round(nq / (ms_step * 1e-3), 1), "unit": "queries/sec",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16 tensor-core candidates + f32 exact re-rank" if used_algo == b2f.ALGO_TENSOR else "f32",

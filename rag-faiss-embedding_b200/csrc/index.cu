@@ -46,6 +46,7 @@ struct b2f_index {
     b2f_stats st{};
     float host_stats[2] = {0.f, 0.f};
     bool stats_dirty = true;
+    int slack_boost = 0;              // extra candidates per query, raised when too many queries fail certification
 };
 
 namespace {
@@ -589,7 +590,11 @@ int b2f_index_search(b2f_index* ix, int64_t nq64, const float* q, int64_t k64, f
 
     int algo = P.algo;
     const int scan_max = P.scan_max_nq > 0 ? P.scan_max_nq : 1;
-    const int kp = tensor_kprime(k, P.slack);
+    int kp = tensor_kprime(k, P.slack);
+    if (kp > 0 && P.slack <= 0 && ix->slack_boost > 0) {  // adaptive slack learned from earlier searches on this index
+        int boosted = ((kp + ix->slack_boost + 7) / 8) * 8;
+        if (boosted > 64) kp = boosted <= 256 ? boosted : 256;
+    }
     TensorScanPlan plan{};
     const int chunk_nq = (kp > 0 && ix->ntotal > 0) ? plan_tensor_chunked(nq, ix->ntotal, ix->d, kp, &plan) : 0;
     const bool tensor_ok = chunk_nq > 0;
@@ -730,6 +735,11 @@ int b2f_index_search(b2f_index* ix, int64_t nq64, const float* q, int64_t k64, f
             const int nfail = hcount[0];
             ix->st.overflow_queries += hcount[1];
             ix->st.last_list_entries += *reinterpret_cast<int64_t*>(hcount + 2);
+            // The slack that certification needs grows with the neighbour density at rank k (i.e. with the
+            // database size and the data distribution): when more than ~2% of a batch had to fall back,
+            // keep more candidates per query from now on.
+            if (certify && P.slack <= 0 && nfail - hcount[1] > (cn / 50 > 2 ? cn / 50 : 2) && kp + ix->slack_boost < 256)
+                ix->slack_boost += 32;
             if (nfail > 0) {
                 ix->st.fallback_queries += nfail;
                 int dummy = 0;

@@ -8,7 +8,7 @@
 // streaming scan (K1), so the final answer never depends on bf16.
 //
 // Bound (L2).  x~, q~ = bf16-rounded row / query, e_x = |x - x~| <= E, e_q = |q - q~|.
-//   coarse c(x) = |q~|^2 + |x~|^2 - 2 <q~,x~> + nu,  |nu| <= NU (fp32 accumulation noise)
+//   coarse c(x) = |q~|^2 + |x~|^2 - 2 <q~,x~> + nu,  |nu| <= NU = 4 (d+16) 2^-24 (2|q~||x~| + |q~|^2 + |x~|^2)
 //   every non-candidate has c(x) >= c_k'  (the k'-th smallest coarse value)
 //   sqrt(dist(q,x)) = |q - x| >= |q~ - x~| - e_q - e_x >= sqrt(max(c_k' - NU, 0)) - e_q - E =: L
 //   certified  <=>  L > 0 and L^2 > tau_k  (tau_k = exact k-th best distance among the candidates)

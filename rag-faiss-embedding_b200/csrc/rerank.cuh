@@ -122,13 +122,18 @@ __device__ __forceinline__ void rerank_block(const RerankArgs& a, int q, const f
             const float qn2 = a.qnorm[q];
             const float qn = sqrtf(qn2);
             const float eq = a.qerr[q];
-            const float nu = 4.f * (float)(a.d + 16) * 1.1920929e-7f * (qn * a.max_row_norm + qn2 + a.max_row_norm * a.max_row_norm);
+            // fp32 accumulation slack: gamma_n * sum|q_i x_i| <= n u |q||x| per inner product (n = d + 16 guards
+            // the tensor core's chunked accumulation order, u = 2^-24), doubled for non-IEEE accumulator rounding
+            const float gam = 4.f * (float)(a.d + 16) * 5.9604645e-8f;
             if (l2) {
+                // c = |q~|^2 + |x~|^2 - 2<q~,x~>: the two norms are fp32 sums as well
+                const float nu = gam * (2.f * qn * a.max_row_norm + qn2 + a.max_row_norm * a.max_row_norm);
                 const float c = ckp + qn2 - nu;
                 const float L = sqrtf(fmaxf(c, 0.f)) - eq - a.max_row_err;
                 certified = L > 0.f && L * L * (1.f - 4e-7f) > tau;
             } else {
                 // keys are negated inner products: non-candidates have <q,x> <= -ckp + slack
+                const float nu = gam * qn * a.max_row_norm;
                 const float U = -ckp + nu + (qn + eq) * a.max_row_err + a.max_row_norm * eq;
                 certified = U < -tau;
             }
