@@ -214,7 +214,10 @@ struct RerankArgs {
     int64_t id_offset;
     const int32_t* overflow;        // optional [nq]: 1 = candidate list overflowed (treated as uncertified)
     int32_t* fail_list;             // queries that could not be certified
-    int32_t* fail_count;            // [2]: uncertified queries, of which list overflows
+    int32_t* fail_count;            // [0] uncertified queries, [1] of which list overflows, [2..3] u64 list entries, [4] blocks done
+    int32_t* host_flag;             // optional mapped host memory [8]: the last block copies the counters here, then seq
+    int32_t seq;                    // value written to host_flag[4] when every query of this launch is done
+    int32_t nblocks;                // blocks of this launch (= queries)
 };
 int launch_rerank(const RerankArgs& a, cudaStream_t st);
 

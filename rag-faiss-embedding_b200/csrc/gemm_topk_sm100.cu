@@ -778,6 +778,27 @@ merge_lists_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ c
         }
     }
     __syncthreads();
+    if (M <= 768) {
+        // small merge input (the usual case after end-of-stream pruning): one pass of direct ranking, each
+        // element counts the composites below it and lands on its sorted slot -- no bisection, one barrier
+        for (int t = tid; t < kp; t += MERGE_THREADS) {
+            sk[t] = FLT_MAX;
+            si[t] = -1;
+        }
+        __syncthreads();
+        for (int i = tid; i < M; i += MERGE_THREADS) {
+            const unsigned long long mine = comp[i];
+            int rank = 0;
+            for (int j = 0; j < M; j++) {
+                const unsigned long long o = comp[j];
+                rank += (o < mine || (o == mine && j < i)) ? 1 : 0;
+            }
+            if (rank < kp) {
+                sk[rank] = dec_key((uint32_t)(mine >> 32));
+                si[rank] = (int32_t)(uint32_t)(mine & 0xffffffffu);
+            }
+        }
+    } else {
     unsigned long long T = ~0ull;
     if (M > kp) {
         int it = 0;
@@ -823,6 +844,7 @@ merge_lists_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ c
             sk[t] = FLT_MAX;
             si[t] = -1;
         }
+    }
     }
     if (tid == 0) ovf[q] = s_ovf;
     __syncthreads();
@@ -983,9 +1005,26 @@ int plan_tensor_scan(int nq, int64_t n, int d, int kp, TensorScanPlan* plan) {
 int launch_tensor_scan(const __nv_bfloat16* scan, int64_t dpad, const float* norms, int64_t n, int metric,
                        const __nv_bfloat16* qb, int nq, int nq_pad, const TensorScanPlan& plan, float* pk, int32_t* pi,
                        const TensorScanLists& lists, cudaStream_t st) {
-    CUtensorMap mq, mx;
-    B2F_TRY(k2::make_map(&mq, qb, (uint64_t)dpad, (uint64_t)nq_pad, (uint64_t)dpad, k2::BM));
-    B2F_TRY(k2::make_map(&mx, scan, (uint64_t)dpad, (uint64_t)n, (uint64_t)dpad, plan.pair_mode ? k2::BN / 2 : k2::BN));
+    // cuTensorMapEncodeTiled costs microseconds of host time per call and sits between two launches, so the
+    // two descriptors are cached per thread and re-encoded only when a pointer or shape changes
+    struct MapKey {
+        const void* base;
+        uint64_t inner, rows;
+        uint32_t box;
+        bool operator==(const MapKey& o) const { return base == o.base && inner == o.inner && rows == o.rows && box == o.box; }
+    };
+    static thread_local MapKey kq{}, kx{};
+    static thread_local CUtensorMap mq, mx;
+    const MapKey nkq{qb, (uint64_t)dpad, (uint64_t)nq_pad, (uint32_t)k2::BM};
+    const MapKey nkx{scan, (uint64_t)dpad, (uint64_t)n, (uint32_t)(plan.pair_mode ? k2::BN / 2 : k2::BN)};
+    if (!(nkq == kq)) {
+        B2F_TRY(k2::make_map(&mq, qb, (uint64_t)dpad, (uint64_t)nq_pad, (uint64_t)dpad, k2::BM));
+        kq = nkq;
+    }
+    if (!(nkx == kx)) {
+        B2F_TRY(k2::make_map(&mx, scan, (uint64_t)dpad, (uint64_t)n, (uint64_t)dpad, nkx.box));
+        kx = nkx;
+    }
     const int kblocks = (int)(dpad / k2::BK);
     const bool l2 = metric == B2F_METRIC_L2;
     k2::ListArgs la{};

@@ -6,6 +6,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <mutex>
 #include <new>
 #include <vector>
@@ -46,6 +47,8 @@ struct b2f_index {
     b2f_stats st{};
     float host_stats[2] = {0.f, 0.f};
     bool stats_dirty = true;
+    int32_t* host_flag = nullptr;     // mapped pinned memory: completion flag + counters written by the last block
+    int32_t seq = 0;
     int slack_boost = 0;              // extra candidates per query, raised when too many queries fail certification
 };
 
@@ -352,6 +355,8 @@ int b2f_index_create(int32_t d, int32_t metric, int32_t storage, int32_t device,
     cudaError_t e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc(&ix->stats, 2 * sizeof(float));
     if (e == cudaSuccess) e = cudaMemset(ix->stats, 0, 2 * sizeof(float));
+    if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&ix->host_flag), 64, cudaHostAllocMapped | cudaHostAllocPortable);
+    if (e == cudaSuccess) memset(ix->host_flag, 0, 64);
     if (e != cudaSuccess) {
         set_error("index init failed: %s", cudaGetErrorString(e));
         delete ix;
@@ -371,6 +376,7 @@ int b2f_index_destroy(b2f_index* ix) {
     cudaFree(ix->stats);
     cudaFree(ix->ws);
     if (ix->pinned) cudaFreeHost(ix->pinned);
+    if (ix->host_flag) cudaFreeHost(ix->host_flag);
     for (cudaEvent_t e : ix->ev) cudaEventDestroy(e);
     if (ix->stream) cudaStreamDestroy(ix->stream);
     delete ix;
@@ -675,7 +681,7 @@ int b2f_index_search(b2f_index* ix, int64_t nq64, const float* q, int64_t k64, f
         float* xk = bump.take<float>((size_t)chunk_nq * k);
         int32_t* xi = bump.take<int32_t>((size_t)chunk_nq * k);
         int32_t* fail_list = bump.take<int32_t>(chunk_nq);
-        int32_t* fail_count = bump.take<int32_t>(4);  // [0] uncertified, [1] overflowed, [2..3] u64 list entries
+        int32_t* fail_count = bump.take<int32_t>(8);  // [0] uncertified, [1] overflowed, [2..3] u64 list entries, [4] blocks done
         B2F_TRY(refresh_host_stats(ix, st));
         for (int c0 = 0; c0 < nq; c0 += chunk_nq) {
         const int cn = nq - c0 < chunk_nq ? nq - c0 : chunk_nq;  // queries in this pass (the plan covers chunk_nq)
@@ -683,7 +689,7 @@ int b2f_index_search(b2f_index* ix, int64_t nq64, const float* q, int64_t k64, f
         float* Dc = Dd + (int64_t)c0 * k;
         int64_t* Ic = Id + (int64_t)c0 * k;
         // one launch: bf16 copy / norms of the queries, clear the 4 counters, reset the shared thresholds
-        B2F_TRY(launch_prep_queries(qc, cn, nq_pad, ix->d, qb, ix->dpad, qnorm, qerr, reinterpret_cast<uint32_t*>(fail_count), 4,
+        B2F_TRY(launch_prep_queries(qc, cn, nq_pad, ix->d, qb, ix->dpad, qnorm, qerr, reinterpret_cast<uint32_t*>(fail_count), 8,
                                     reinterpret_cast<uint32_t*>(lists.shared_thr),
                                     plan.list_mode ? (int64_t)nq_pad * plan.nlists : 0, st));
         if (profile) B2F_CUDA(cudaEventRecord(get_event(ix, ev_main + 2 * (size_t)n_main), st));
@@ -716,6 +722,9 @@ int b2f_index_search(b2f_index* ix, int64_t nq64, const float* q, int64_t k64, f
         ra.id_offset = P.id_offset;
         ra.fail_list = fail_list;
         ra.fail_count = fail_count;
+        ra.host_flag = ix->host_flag;
+        ra.seq = ++ix->seq;
+        ra.nblocks = cn;
         if (plan.list_mode) {
             // K3b + K4 + finalize fused: per query, merge the lists, re-rank exactly, certify, write (D, I)
             B2F_TRY(launch_merge_lists(lists, cn, plan, ck, ci, ovf, reinterpret_cast<unsigned long long*>(fail_count + 2), &ra, st));
@@ -727,14 +736,45 @@ int b2f_index_search(b2f_index* ix, int64_t nq64, const float* q, int64_t k64, f
             ix->st.launches += 4;
             ix->st.last_launches += 4;
         }
+        if (host) {  // overlaps the flag wait; redone below in the rare fallback case
+            B2F_CUDA(cudaMemcpyAsync(D + (int64_t)c0 * k, Dc, (size_t)cn * k * 4, cudaMemcpyDeviceToHost, st));
+            B2F_CUDA(cudaMemcpyAsync(I + (int64_t)c0 * k, Ic, (size_t)cn * k * 8, cudaMemcpyDeviceToHost, st));
+        }
         if (certify || plan.list_mode) {
-            B2F_TRY(ensure_pinned(ix, 4096));
-            int32_t* hcount = reinterpret_cast<int32_t*>(ix->pinned);
-            B2F_CUDA(cudaMemcpyAsync(hcount, fail_count, 16, cudaMemcpyDeviceToHost, st));
-            B2F_CUDA(cudaStreamSynchronize(st));
+            // Wait for the completion flag the last block writes into mapped host memory (a few microseconds
+            // after the kernel ends); fall back to a stream synchronize if the stream ends without it (fault).
+            volatile int32_t* hf = ix->host_flag;
+            int32_t hcount[4];
+            bool got = false;
+            for (long spin = 0;; spin++) {
+                if (hf[4] == ra.seq) {
+                    got = true;
+                    break;
+                }
+                if ((spin & 1023) == 1023) {
+                    const cudaError_t qe = cudaStreamQuery(st);
+                    if (qe != cudaErrorNotReady) {
+                        if (qe != cudaSuccess) B2F_CUDA(qe);
+                        if (hf[4] == ra.seq) got = true;
+                        break;
+                    }
+                }
+#if defined(__x86_64__)
+                __builtin_ia32_pause();
+#endif
+            }
+            if (!got) {
+                set_error("search: completion flag missing after the stream finished");
+                return B2F_ECUDA;
+            }
+            std::atomic_thread_fence(std::memory_order_acquire);
+            hcount[0] = hf[0];
+            hcount[1] = hf[1];
+            hcount[2] = hf[2];
+            hcount[3] = hf[3];
             const int nfail = hcount[0];
             ix->st.overflow_queries += hcount[1];
-            ix->st.last_list_entries += *reinterpret_cast<int64_t*>(hcount + 2);
+            ix->st.last_list_entries += (int64_t)(((uint64_t)(uint32_t)hcount[3] << 32) | (uint32_t)hcount[2]);
             // The slack that certification needs grows with the neighbour density at rank k (i.e. with the
             // database size and the data distribution): when more than ~2% of a batch had to fall back,
             // keep more candidates per query from now on.
@@ -745,14 +785,20 @@ int b2f_index_search(b2f_index* ix, int64_t nq64, const float* q, int64_t k64, f
                 int dummy = 0;
                 Bump fb = bump;  // the fallback's scratch is carved after the tensor buffers, per chunk
                 B2F_TRY(run_scan(ix, qc, fail_list, nfail, k, Dc, Ic, P.id_offset, fb, st, false, 0, &dummy));
+                if (host) {
+                    B2F_CUDA(cudaMemcpyAsync(D + (int64_t)c0 * k, Dc, (size_t)cn * k * 4, cudaMemcpyDeviceToHost, st));
+                    B2F_CUDA(cudaMemcpyAsync(I + (int64_t)c0 * k, Ic, (size_t)cn * k * 8, cudaMemcpyDeviceToHost, st));
+                }
             }
         }
         }  // chunk loop
     }
     if (profile) B2F_CUDA(cudaEventRecord(get_event(ix, ev_tot + 1), st));
     if (host) {
-        B2F_CUDA(cudaMemcpyAsync(D, Dd, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, st));
-        B2F_CUDA(cudaMemcpyAsync(I, Id, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, st));
+        if (!(algo == B2F_ALGO_TENSOR && ix->ntotal > 0)) {  // the tensor path already queued its copies per chunk
+            B2F_CUDA(cudaMemcpyAsync(D, Dd, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, st));
+            B2F_CUDA(cudaMemcpyAsync(I, Id, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, st));
+        }
         B2F_CUDA(cudaStreamSynchronize(st));
     }
     if (profile) {

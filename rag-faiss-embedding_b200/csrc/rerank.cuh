@@ -144,6 +144,23 @@ __device__ __forceinline__ void rerank_block(const RerankArgs& a, int q, const f
             if (overflowed) atomicAdd(a.fail_count + 1, 1);
         }
     }
+    // Completion flag: the last block to finish publishes the counters to mapped host memory, so the host
+    // learns "done, n failures" by polling one cache line instead of a D2H copy + stream synchronize.
+    if (threadIdx.x == 0 && a.host_flag) {
+        __threadfence();
+        const int prev = atomicAdd(a.fail_count + 4, 1);
+        if (prev == a.nblocks - 1) {
+            __threadfence();
+            volatile int32_t* fc = a.fail_count;
+            volatile int32_t* hf = a.host_flag;
+            hf[0] = fc[0];
+            hf[1] = fc[1];
+            hf[2] = fc[2];
+            hf[3] = fc[3];
+            __threadfence_system();
+            hf[4] = a.seq;
+        }
+    }
 }
 
 }  // namespace b2f
