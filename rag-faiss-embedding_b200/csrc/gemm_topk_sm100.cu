@@ -555,13 +555,12 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                         if (cnt < la.cap) mylist[cnt] = make_uint2(__float_as_uint(key), (uint32_t)(rowc + j));
                         cnt++;
                         if (key < best[JSLOTS - 1]) {
-                            best[JSLOTS - 1] = key;
+                            // sorted insert without a dependency chain: new[i] = max(old[i-1], min(old[i], key))
+                            float nb[JSLOTS];
 #pragma unroll
-                            for (int i = JSLOTS - 1; i > 0; i--) {
-                                const float lo = fminf(best[i - 1], best[i]), hi = fmaxf(best[i - 1], best[i]);
-                                best[i - 1] = lo;
-                                best[i] = hi;
-                            }
+                            for (int i = 0; i < JSLOTS; i++) nb[i] = fmaxf(i > 0 ? best[i - 1] : -kInf, fminf(best[i], key));
+#pragma unroll
+                            for (int i = 0; i < JSLOTS; i++) best[i] = nb[i];
                         }
                     }
                 }
@@ -605,12 +604,12 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 const int have = cnt <= la.cap ? cnt : 0;  // an overflowed list is left as is (the query falls back)
                 int w = 0;
 #pragma unroll 1
-                for (int i0 = 0; i0 < have; i0 += 8) {
-                    uint2 e[8];
+                for (int i0 = 0; i0 < have; i0 += 16) {
+                    uint2 e[16];
 #pragma unroll
-                    for (int u = 0; u < 8; u++) e[u] = (i0 + u < have) ? mylist[i0 + u] : make_uint2(0x7f800000u, 0u);
+                    for (int u = 0; u < 16; u++) e[u] = (i0 + u < have) ? mylist[i0 + u] : make_uint2(0x7f800000u, 0u);
 #pragma unroll
-                    for (int u = 0; u < 8; u++)
+                    for (int u = 0; u < 16; u++)
                         if (i0 + u < have && __uint_as_float(e[u].x) <= thr) mylist[w++] = e[u];
                 }
                 la.counts[(int64_t)qrow * la.nl_stride + vsplit] = cnt > la.cap ? cnt : w;  // > cap marks an overflow
