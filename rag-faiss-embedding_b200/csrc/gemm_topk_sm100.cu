@@ -47,7 +47,7 @@ constexpr int BK = 64;         // bf16 elements per stage along d: 128 bytes = o
 constexpr int UMMA_K = 16;
 constexpr int STAGES_HEAP = 3;
 constexpr int STAGES_LIST = 4;
-constexpr int STAGES_QRES = 4;    // Q-resident variant: stages hold database blocks only (32 KB each)
+constexpr int STAGES_QRES = 3;    // Q-resident variant: stages hold database blocks only (32 KB each)
 constexpr int QRES_MAX_KB = 6;    // query tile kept resident in smem when dpad <= 384 (6 x 16 KB)
 constexpr int LIST_CAP_MIN = 128;  // entries per (query, split) candidate list: 128 / 256 / 512 by stream length
 constexpr int JSLOTS = 16;        // register slots for the split-local j-th best (j <= 16: LIST mode from 2 splits up)
@@ -166,7 +166,7 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank
 }
 // kind::f16 instruction descriptor for the pair: M = 256 (128 per CTA), N = 256
 constexpr uint32_t kIdescPair = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-constexpr int STAGES_PAIR = 8;        // pair variant: each CTA stages its 128-row half of the database block (16 KB)
+constexpr int STAGES_PAIR = 6;        // pair variant: each CTA stages its 128-row half of the database block (16 KB)
 
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -200,7 +200,9 @@ struct Smem {
     static constexpr size_t heapk_off = stages_off + (size_t)NST * stage_bytes;
     static constexpr size_t heapi_off = heapk_off + (size_t)EPI_THREADS * KP * 4;
     static constexpr size_t bias_off = heapi_off + (size_t)EPI_THREADS * KP * 4;
-    static constexpr size_t bar_off = bias_off + 2 * BN * 4;
+    // LIST mode (KP == 0): per-warp staging of one chunk's 32 accumulators per lane, [warp][column][lane]
+    static constexpr size_t xpose_off = bias_off + 2 * BN * 4;
+    static constexpr size_t bar_off = xpose_off + (KP == 0 ? (size_t)EPI_WARPS_LIST * 32 * 32 * 4 : 0);
     static constexpr int nbars = 2 * NST + 9;
     static constexpr size_t tmem_off = bar_off + nbars * 8;
     static constexpr size_t total = tmem_off + 16;
@@ -502,6 +504,7 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             for (int i = 0; i < JSLOTS; i++) best[i] = (i < JSLOTS - jv) ? -kInf : kInf;
             float thr = 3.0e38f, pub = kInf;  // refreshed before the first compare; never +inf (padding rows have key +inf)
             int cnt = 0;
+            uint32_t* xpose = reinterpret_cast<uint32_t*>(smem + L::xpose_off) + ew * 1024;  // this warp's staging area
             uint2* mylist = la.cand + ((int64_t)(active ? qrow : 0) * la.nl_stride + vsplit) * la.cap;
             // shared thresholds are laid out [virtual split][query] so that a warp's loads for one split coalesce
             float* gq = la.shared_thr + (active ? qrow : 0);
@@ -544,13 +547,21 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                     }
                 }
                 const uint32_t mask = active ? chunk_mask(r, tbc, thr) : 0u;
-                uint32_t um = __reduce_or_sync(kFull, mask);
-                while (um) {
-                    const int j = __ffs(um) - 1;
-                    um &= um - 1;
-                    const uint32_t v = pick(r, j);
-                    if (mask & (1u << j)) {
-                        const float sdot = __uint_as_float(v);
+                // Survivors are rare.  When some lane of the warp has one, every lane parks its 32 accumulators
+                // in the warp's shared-memory staging area ([column][lane]: conflict free) and then walks ITS OWN
+                // survivors, all lanes in parallel.  (The previous version walked the union of the lanes'
+                // survivors in a warp-uniform loop that picked the accumulator out of the registers with a
+                // branch table: ~440 cycles per survivor on a lone warp -- clock64 instrumentation showed it
+                // was half of the kernel time at nq = 32 and a quarter at nq = 1024.)
+                if (__any_sync(kFull, mask != 0u)) {
+                    uint32_t* st = xpose + lane;
+#pragma unroll
+                    for (int j = 0; j < 32; j++) st[j * 32] = r[j];
+                    uint32_t m = mask;
+                    while (m) {
+                        const int j = __ffs(m) - 1;
+                        m &= m - 1;
+                        const float sdot = __uint_as_float(st[j * 32]);
                         const float key = L2 ? fmaf(-2.f, sdot, tbc[j]) : tbc[j] - sdot;
                         if (cnt < la.cap) mylist[cnt] = make_uint2(__float_as_uint(key), (uint32_t)(rowc + j));
                         cnt++;
