@@ -14,7 +14,9 @@
  *   - `stream` is a cudaStream_t passed as void*; NULL = the index's own (non-blocking) stream; pass
  *     cudaStreamLegacy (0x1) to mean the legacy default stream.  With host buffers
  *     every call is synchronous on return (faiss semantics).  With device buffers the work is
- *     enqueued on `stream` and the call returns without synchronising.
+ *     enqueued on `stream` and the call returns without synchronising: nothing inside a search waits
+ *     for the GPU (uncertified queries are re-run by a kernel that reads their count on the device),
+ *     so back-to-back searches keep the GPU busy.  b2f_index_stats() settles all pending work.
  *   - the caller allocates D / I (as faiss's search_c does); the library owns all device storage
  *     behind the handle.
  *   - there is NO CPU fallback: every compute entry point fails with B2F_ENOGPU when no sm_100 device
@@ -100,6 +102,7 @@ typedef struct b2f_stats {
     double prof_total_ms_sum;
     int64_t prof_main_launches;
     int64_t prof_searches;
+    int64_t rescued_queries;   /* tensor path: queries certified only after re-ranking every list entry (no database pass) */
 } b2f_stats;
 
 /* ---- lifecycle -------------------------------------------------------------------------------

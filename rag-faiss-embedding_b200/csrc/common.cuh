@@ -154,16 +154,48 @@ void set_error(const char* fmt, ...);
 
 // ---- kernel launchers (one per .cu file) -------------------------------------------------------
 
-// K1: fp32 exact-difference streaming scan. q: [nq, d] device fp32, nq <= 8 per call.
-// Produces sorted per-CTA partial lists: pk/pi [nq][nparts][k]; returns nparts via *nparts_out
-// (fixed by the launch geometry; caller sizes the buffers with scan_max_parts()).
+// K1: fp32 exact-difference streaming scan + fused merge + faiss formatting, ONE cooperative launch for any
+// number of queries (walked in groups of <= 8 inside the kernel).
+struct ScanFuse {                  // device-side view (kernel argument)
+    float* D;                      // [*, k] faiss-formatted distances
+    int64_t* I;                    // [*, k] labels (+ id_offset)
+    int64_t id_offset;
+    const int32_t* qsel;           // optional: query slot i reads row qsel[i] of q and writes row qsel[i] of D / I
+    const int32_t* nsel_dev;       // optional: number of queries, read on the device (overrides nsel)
+    int nsel;
+    float* pk;                     // [2][NQ][parts][k] per-CTA partial lists (double buffered over query groups)
+    int32_t* pi;
+    float* mk;                     // [NQ][33][k] merge scratch
+    int32_t* mi;
+    int32_t* counters;             // optional [8]: the search's counters, published by this (final) kernel
+    unsigned long long* totals;    // optional [2]: running totals of the index (fallbacks, overflows)
+    int32_t* host_flag;            // optional mapped host memory [16]
+    int32_t seq;
+    int32_t nq_batch, certify;     // echoed to the host flag (adaptive slack)
+};
+struct ScanArgs {                  // host-side launch description
+    const float* rows_f32;         // fp32 rows, or
+    const __nv_bfloat16* rows_bf16;
+    int64_t pitch_bf16;
+    int64_t n;
+    int d, metric, k;
+    const float* q;                // [*, d] device fp32
+    const int32_t* qsel;           // optional (device)
+    const int32_t* nsel_dev;       // optional (device)
+    int nsel;
+    float* D;
+    int64_t* I;
+    int64_t id_offset;
+    void* scratch;                 // scan_scratch_bytes(k) bytes
+    int32_t* counters;
+    unsigned long long* totals;
+    int32_t* host_flag;
+    int32_t seq;
+    int32_t nq_batch, certify;
+};
 int scan_max_parts();
-// qsel (optional, device): query slot i reads row qsel[i] of q (certification fallback).
-int launch_scan_f32(const float* rows, int64_t n, int d, int metric, const float* q, const int32_t* qsel, int nq,
-                    int k, float* pk, int32_t* pi, int* nparts_out, cudaStream_t st);
-// same scan over bf16-stored rows (B2F_STORE_BF16), pitch in elements
-int launch_scan_bf16(const __nv_bfloat16* rows, int64_t pitch, int64_t n, int d, int metric, const float* q,
-                     const int32_t* qsel, int nq, int k, float* pk, int32_t* pi, int* nparts_out, cudaStream_t st);
+size_t scan_scratch_bytes(int k);
+int launch_scan(const ScanArgs& a, cudaStream_t st);
 
 // K3: merge nparts sorted lists per query into the best kout: pk/pi [nq][nparts][klist] -> ok/oi [nq][kout]
 int launch_merge_parts(const float* pk, const int32_t* pi, int nq, int nparts, int klist, int kout, float* ok,
@@ -212,12 +244,9 @@ struct RerankArgs {
     float* D;                       // optional fused finalize: faiss-formatted distances [nq, k]
     int64_t* I;                     //                          labels [nq, k] (+ id_offset)
     int64_t id_offset;
-    const int32_t* overflow;        // optional [nq]: 1 = candidate list overflowed (treated as uncertified)
-    int32_t* fail_list;             // queries that could not be certified
-    int32_t* fail_count;            // [0] uncertified queries, [1] of which list overflows, [2..3] u64 list entries, [4] blocks done
-    int32_t* host_flag;             // optional mapped host memory [8]: the last block copies the counters here, then seq
-    int32_t seq;                    // value written to host_flag[4] when every query of this launch is done
-    int32_t nblocks;                // blocks of this launch (= queries)
+    int32_t* fail_list;             // queries that could not be certified (q + q_base), re-run by the closing exact scan
+    int32_t* fail_count;            // [0] uncertified queries, [1] of which list overflows, [2..3] u64 list entries
+    int32_t q_base;                 // first query of this pass within the whole batch (query chunks)
 };
 int launch_rerank(const RerankArgs& a, cudaStream_t st);
 
@@ -239,14 +268,15 @@ struct TensorScanLists {  // LIST-mode scratch (device)
     float* shared_thr;    // [nlists][nq_pad]
     void* cand;           // [nq_pad * nlists][list_cap] x 8 bytes
     int32_t* counts;      // [nq_pad * nlists]
+    float* final_thr;     // [nq_pad * nlists]  the threshold each list was pruned against at the end of the stream
 };
 int plan_tensor_scan(int nq, int64_t n, int d, int kp, TensorScanPlan* plan);
 int launch_tensor_scan(const __nv_bfloat16* scan, int64_t dpad, const float* norms, int64_t n, int metric,
                        const __nv_bfloat16* qb, int nq, int nq_pad, const TensorScanPlan& plan, float* pk,
                        int32_t* pi, const TensorScanLists& lists, cudaStream_t st);
-// K3b: per query, the kp best of the variable-length lists -> ck/ci [nq][kp]; ovf[q]=1 on list overflow
-// ra (optional): when given, the kernel continues with the exact re-rank (K4) + finalize of each query
-int launch_merge_lists(const TensorScanLists& lists, int nq, const TensorScanPlan& plan, float* ck, int32_t* ci,
-                       int32_t* ovf, unsigned long long* total_entries, const RerankArgs* ra, cudaStream_t st);
+// K3b + K4 fused: per query, merge the variable-length lists, re-rank the kp best exactly, certify (retrying
+// with every list entry when the first attempt fails), write (D, I); uncertified queries go to ra.fail_list
+int launch_merge_lists(const TensorScanLists& lists, int nq, const TensorScanPlan& plan, unsigned long long* total_entries,
+                       const RerankArgs& ra, cudaStream_t st);
 
 }  // namespace b2f

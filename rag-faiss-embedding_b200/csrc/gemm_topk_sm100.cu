@@ -217,6 +217,7 @@ struct ListArgs {
     int kp;              // k': every query's lists together must cover the k' best
     int nl_stride;       // lists per query allocated (the largest per-tile list count)
     int cap;             // entries per list
+    float* final_thr;    // [nq_pad * nsplits]  threshold the list was pruned against at the end of the stream
 };
 
 // thread-private max-heap in shared memory, element j of thread t at [j * 128 + t].
@@ -624,6 +625,9 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                         if (i0 + u < have && __uint_as_float(e[u].x) <= thr) mylist[w++] = e[u];
                 }
                 la.counts[(int64_t)qrow * la.nl_stride + vsplit] = cnt > la.cap ? cnt : w;  // > cap marks an overflow
+                // every row of this virtual split with key <= thr is in the list: the merge certifies against the
+                // smallest of these over the query's lists
+                la.final_thr[(int64_t)qrow * la.nl_stride + vsplit] = thr;
             }
         } else {
             // ---- HEAP mode: thread-private max-heap of k' in shared memory ------------------------------
@@ -695,14 +699,22 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     }
 }
 
-// ---- K3b: per query, select the k' best of the S variable-length candidate lists ----------------------
+// ---- K3b + K4: per query, merge the candidate lists, re-rank exactly, certify, write (D, I) ---------------
 // One CTA per query.  Candidates become 64-bit composites (order-preserving key bits << 32 | row id) in
-// shared memory; the k'-th smallest is found by bisection (one __syncthreads per step: first over the 32
-// key bits, then -- only when equal keys straddle the cut -- over the 32 id bits), the k' survivors are
-// rank-sorted.  Output: ck/ci [nq][kp] ascending, padded with (FLT_MAX,-1).  ovf[q] = 1 when a list
-// overflowed (the query is then re-run by the exact scan).
-constexpr int MERGE_THREADS = kRerankThreads;  // 128: the fused kernel continues with the block-level re-rank
-constexpr int MERGE_MAX = 12288;  // composites held in shared memory (96 KB) at most
+// shared memory.  Up to RANK_MAX entries (the usual case after end-of-stream pruning) they are ranked
+// directly -- each element counts the composites below it and lands on its sorted slot; beyond that the
+// k'-th smallest is found by bisection (first over the 32 key bits, then, only when equal keys straddle the
+// cut, over the 32 id bits).  The k' best are re-ranked in exact fp32 arithmetic and certified against the
+// k'-th coarse key (rerank.cuh).
+//
+// Extended certification.  Thresholds only ever fall, so the lists hold EVERY row whose coarse key is <= T_c,
+// the smallest threshold any of the query's lists was finally pruned against -- typically 2-4x more rows than
+// k'.  When the k' best do not certify, all list entries are re-ranked and the bound becomes T_c: the query is
+// answered exactly from rows the tensor pass already found, without another pass over the database.
+constexpr int MERGE_THREADS = kRerankThreads;  // 256
+constexpr int MERGE_MAX = 4096;   // composites held in shared memory (32 KB) at most; more -> the query falls back
+constexpr int RANK_MAX = 1024;    // direct ranking and extended certification up to this many list entries
+constexpr int KP_MAX = 256;
 
 __device__ __forceinline__ int block_count_le(const unsigned long long* comp, int M, unsigned long long bound, int* s_cnt,
                                               int it, int tid, int lane) {
@@ -716,29 +728,33 @@ __device__ __forceinline__ int block_count_le(const unsigned long long* comp, in
 }
 
 __global__ void __launch_bounds__(MERGE_THREADS)
-merge_lists_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ counts, int nl_stride, int tile_queries,
-                   int ntile_units, int total_units, int halves, int kp, int list_cap, int cap_entries, float* __restrict__ ck, int32_t* __restrict__ ci, int32_t* __restrict__ ovf,
-                   unsigned long long* __restrict__ total_entries, RerankArgs ra, int fused) {
-    extern __shared__ __align__(16) unsigned long long comp[];  // [cap_entries] + survivors [kp] + sorted (key,id) [kp] + re-rank scratch [kp]
+merge_lists_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ counts, const float* __restrict__ final_thr,
+                   int nl_stride, int tile_queries, int ntile_units, int total_units, int halves, int kp, int list_cap,
+                   int cap_entries, unsigned long long* __restrict__ total_entries, const RerankArgs ra) {
+    extern __shared__ __align__(16) unsigned long long comp[];  // [max(cap_entries, RANK_MAX)], later the re-rank scratch
     __shared__ int s_off[2 * kNumSMs + 2];
     __shared__ int s_cnt[3];
     __shared__ int s_nsurv;
     __shared__ int s_ovf;
-    unsigned long long* surv = comp + cap_entries;
-    float* sk = reinterpret_cast<float*>(surv + kp);  // [kp] sorted coarse keys
-    int32_t* si = reinterpret_cast<int32_t*>(sk + kp);  // [kp]
-    float* ek = reinterpret_cast<float*>(si + kp);      // [kp] re-rank scratch
-    int32_t* ei = reinterpret_cast<int32_t*>(ek + kp);  // [kp]
+    __shared__ float s_tc;
+    const int cap_c = cap_entries > RANK_MAX ? cap_entries : RANK_MAX;
+    unsigned long long* surv = comp + cap_c;                       // [KP_MAX]
+    float* sk = reinterpret_cast<float*>(surv + KP_MAX);           // [RANK_MAX] coarse keys, ascending
+    int32_t* si = reinterpret_cast<int32_t*>(sk + RANK_MAX);       // [RANK_MAX]
+    float* ek = reinterpret_cast<float*>(comp);                    // [RANK_MAX] exact keys   (comp is dead by then)
+    int32_t* ei = reinterpret_cast<int32_t*>(ek + RANK_MAX);       // [RANK_MAX]
     const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // lists of this query: (database splits of its tile) x (column halves); see the kernel's my_nsplits
     const int tile = q / tile_queries;
     const int nsplits = (total_units / ntile_units + (tile < total_units % ntile_units ? 1 : 0)) * halves;
     if (warp == 0) {
-        // exclusive prefix sum of the (clamped) list lengths, 32 splits at a time
+        // exclusive prefix sum of the list lengths, 32 lists at a time; T_c = the smallest final threshold
         int run = 0, o = 0;
+        float tc = 3.0e38f;
         for (int s0 = 0; s0 < nsplits; s0 += 32) {
             const int s = s0 + lane;
             int c = s < nsplits ? counts[(int64_t)q * nl_stride + s] : 0;
+            if (s < nsplits) tc = fminf(tc, final_thr[(int64_t)q * nl_stride + s]);
             if (c > list_cap) {
                 c = list_cap;
                 o = 1;
@@ -753,18 +769,26 @@ merge_lists_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ c
             run += __shfl_sync(kFull, incl, 31);
         }
         o = __reduce_or_sync(kFull, o);
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) tc = fminf(tc, __shfl_xor_sync(kFull, tc, d));
         if (lane == 0) {
             s_off[nsplits] = run;
             if (total_entries) atomicAdd(total_entries, (unsigned long long)run);
             s_ovf = (o || run > cap_entries) ? 1 : 0;
             s_nsurv = 0;
             s_cnt[0] = 0;
+            s_tc = tc;
         }
     }
     __syncthreads();
-    const int M = s_off[nsplits] < cap_entries ? s_off[nsplits] : cap_entries;
+    if (s_ovf) {
+        // some candidates were dropped: only the exact scan can answer (it rewrites this query's D / I rows)
+        if (tid == 0) rerank_record_failure(ra, q, true);
+        return;
+    }
+    const int M = s_off[nsplits];
     // gather: flattened over all candidates so every thread has independent loads in flight; the owning
-    // list of element i is found by binary search in the prefix array (<= 8 steps in shared memory)
+    // list of element i is found by binary search in the prefix array (<= 9 steps in shared memory)
     for (int i0 = tid; i0 < M; i0 += 4 * MERGE_THREADS) {
         uint2 e[4];
 #pragma unroll
@@ -788,29 +812,33 @@ merge_lists_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ c
         }
     }
     __syncthreads();
-    if (M <= 768) {
-        // small merge input (the usual case after end-of-stream pruning): one pass of direct ranking, each
-        // element counts the composites below it and lands on its sorted slot -- no bisection, one barrier
-        for (int t = tid; t < kp; t += MERGE_THREADS) {
-            sk[t] = FLT_MAX;
-            si[t] = -1;
+    int nsorted;  // entries of sk / si that are filled (ascending)
+    if (M <= RANK_MAX) {
+        // direct ranking, up to four elements per thread sharing every broadcast read of comp[j]
+        unsigned long long mine[RANK_MAX / MERGE_THREADS];
+        int rank[RANK_MAX / MERGE_THREADS];
+#pragma unroll
+        for (int u = 0; u < RANK_MAX / MERGE_THREADS; u++) {
+            const int i = tid + u * MERGE_THREADS;
+            mine[u] = i < M ? comp[i] : ~0ull;
+            rank[u] = 0;
         }
-        __syncthreads();
-        for (int i = tid; i < M; i += MERGE_THREADS) {
-            const unsigned long long mine = comp[i];
-            int rank = 0;
-            for (int j = 0; j < M; j++) {
-                const unsigned long long o = comp[j];
-                rank += (o < mine || (o == mine && j < i)) ? 1 : 0;
-            }
-            if (rank < kp) {
-                sk[rank] = dec_key((uint32_t)(mine >> 32));
-                si[rank] = (int32_t)(uint32_t)(mine & 0xffffffffu);
+        for (int j = 0; j < M; j++) {
+            const unsigned long long o = comp[j];
+#pragma unroll
+            for (int u = 0; u < RANK_MAX / MERGE_THREADS; u++)
+                rank[u] += (o < mine[u] || (o == mine[u] && j < tid + u * MERGE_THREADS)) ? 1 : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < RANK_MAX / MERGE_THREADS; u++) {
+            if (tid + u * MERGE_THREADS < M) {
+                sk[rank[u]] = dec_key((uint32_t)(mine[u] >> 32));
+                si[rank[u]] = (int32_t)(uint32_t)(mine[u] & 0xffffffffu);
             }
         }
+        nsorted = M;
     } else {
-    unsigned long long T = ~0ull;
-    if (M > kp) {
+        unsigned long long T = ~0ull;
         int it = 0;
         // smallest 32-bit key K with count(key <= K) >= kp
         unsigned int lo = 0, hi = 0xffffffffu;
@@ -833,40 +861,36 @@ merge_lists_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ c
             }
             T = kbits | ilo;
         }
-    }
-    for (int i = tid; i < M; i += MERGE_THREADS) {
-        const unsigned long long v = comp[i];
-        if (v <= T) {
-            const int slot = atomicAdd(&s_nsurv, 1);
-            if (slot < kp) surv[slot] = v;
+        for (int i = tid; i < M; i += MERGE_THREADS) {
+            const unsigned long long v = comp[i];
+            if (v <= T) {
+                const int slot = atomicAdd(&s_nsurv, 1);
+                if (slot < kp) surv[slot] = v;
+            }
         }
-    }
-    __syncthreads();
-    const int ns = s_nsurv < kp ? s_nsurv : kp;
-    for (int t = tid; t < kp; t += MERGE_THREADS) {
-        if (t < ns) {
+        __syncthreads();
+        const int ns = s_nsurv < kp ? s_nsurv : kp;
+        for (int t = tid; t < ns; t += MERGE_THREADS) {
             const unsigned long long mine = surv[t];
             int rank = 0;  // ties broken by slot, so ranks are a permutation even if composites repeat
             for (int j = 0; j < ns; j++) rank += (surv[j] < mine || (surv[j] == mine && j < t)) ? 1 : 0;
             sk[rank] = dec_key((uint32_t)(mine >> 32));
             si[rank] = (int32_t)(uint32_t)(mine & 0xffffffffu);
-        } else {
-            sk[t] = FLT_MAX;
-            si[t] = -1;
         }
+        nsorted = ns;
     }
-    }
-    if (tid == 0) ovf[q] = s_ovf;
     __syncthreads();
-    if (!fused) {
-        for (int t = tid; t < kp; t += MERGE_THREADS) {
-            ck[(int64_t)q * kp + t] = sk[t];
-            ci[(int64_t)q * kp + t] = si[t];
-        }
-        return;
+    // K4: exact fp32 re-rank of the k' best + certification + faiss-formatted output
+    const float tc = s_tc;
+    const int nc1 = nsorted < kp ? nsorted : kp;
+    const float bound1 = (M > kp) ? fminf(sk[kp - 1], tc) : tc;
+    bool cert = rerank_block(ra, q, sk, si, nc1, bound1, M < kp, ek, ei);
+    if (!cert && ra.certify && M > kp && M <= RANK_MAX) {
+        // every list entry: rows outside the lists have coarse keys above T_c
+        cert = rerank_block(ra, q, sk, si, M, tc, false, ek, ei);
+        if (tid == 0 && cert) atomicAdd(ra.fail_count + 4, 1);  // diagnostics: queries rescued by the extended pass
     }
-    // fused K4: exact fp32 re-rank of the kp candidates + certification + faiss-formatted output
-    rerank_block(ra, q, sk, si, ek, ei);
+    if (tid == 0 && ra.certify && !cert) rerank_record_failure(ra, q, false);
 }
 
 // ---- host side --------------------------------------------------------------------------------------
@@ -1045,6 +1069,7 @@ int launch_tensor_scan(const __nv_bfloat16* scan, int64_t dpad, const float* nor
         la.kp = plan.kp;
         la.nl_stride = plan.nlists;
         la.cap = plan.list_cap;
+        la.final_thr = lists.final_thr;
         // lists.shared_thr was filled with 0x7f7f7f7f (3.39e38, "no information yet") by the query-prep kernel
         if (plan.pair_mode)
             return l2 ? k2::launch_k2<0, true, true, true, true>(mq, mx, norms, n, nq, kblocks, plan, pk, pi, la, st)
@@ -1065,22 +1090,26 @@ int launch_tensor_scan(const __nv_bfloat16* scan, int64_t dpad, const float* nor
     return B2F_EINVAL;
 }
 
-int launch_merge_lists(const TensorScanLists& lists, int nq, const TensorScanPlan& plan, float* ck, int32_t* ci,
-                       int32_t* ovf, unsigned long long* total_entries, const RerankArgs* ra, cudaStream_t st) {
+int launch_merge_lists(const TensorScanLists& lists, int nq, const TensorScanPlan& plan, unsigned long long* total_entries,
+                       const RerankArgs& ra, cudaStream_t st) {
     if (nq <= 0) return B2F_OK;
+    if (plan.kp > k2::KP_MAX || plan.nlists > 2 * kNumSMs) {
+        set_error("merge: k' = %d / %d lists per query not supported", plan.kp, plan.nlists);
+        return B2F_EINVAL;
+    }
     int cap_entries = plan.nlists * plan.list_cap;
     if (cap_entries > k2::MERGE_MAX) cap_entries = k2::MERGE_MAX;
-    const size_t smem = (size_t)(cap_entries + plan.kp) * 8 + (size_t)plan.kp * 16;
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    const int cap_c = cap_entries > k2::RANK_MAX ? cap_entries : k2::RANK_MAX;
+    const size_t smem = (size_t)cap_c * 8 + (size_t)k2::KP_MAX * 8 + (size_t)k2::RANK_MAX * 8;
+    static bool configured = false;
+    if (!configured) {
         B2F_CUDA(cudaFuncSetAttribute(k2::merge_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)((k2::MERGE_MAX + 256) * 8 + 256 * 16)));
-        configured = (size_t)(k2::MERGE_MAX + 256) * 8 + 256 * 16;
+                                      (int)((size_t)k2::MERGE_MAX * 8 + (size_t)k2::KP_MAX * 8 + (size_t)k2::RANK_MAX * 8)));
+        configured = true;
     }
-    k2::merge_lists_kernel<<<nq, k2::MERGE_THREADS, smem, st>>>(reinterpret_cast<const uint2*>(lists.cand), lists.counts,
+    k2::merge_lists_kernel<<<nq, k2::MERGE_THREADS, smem, st>>>(reinterpret_cast<const uint2*>(lists.cand), lists.counts, lists.final_thr,
                                                                plan.nlists, plan.pair_mode ? 2 * k2::BM : k2::BM, plan.tile_units, plan.units,
-                                                               k2::EPI_WARPS_LIST / 4, plan.kp, plan.list_cap, cap_entries, ck, ci, ovf, total_entries,
-                                                               ra ? *ra : RerankArgs{}, ra ? 1 : 0);
+                                                               k2::EPI_WARPS_LIST / 4, plan.kp, plan.list_cap, cap_entries, total_entries, ra);
     B2F_CUDA(cudaGetLastError());
     return B2F_OK;
 }

@@ -47,9 +47,24 @@ struct b2f_index {
     b2f_stats st{};
     float host_stats[2] = {0.f, 0.f};
     bool stats_dirty = true;
-    int32_t* host_flag = nullptr;     // mapped pinned memory: completion flag + counters written by the last block
+    int32_t* host_flag = nullptr;     // mapped pinned memory [16]: counters of the latest finished tensor-path search + its seq
     int32_t seq = 0;
+    int32_t harvested_seq = 0;        // last seq whose counters were folded into the host-side statistics
     int slack_boost = 0;              // extra candidates per query, raised when too many queries fail certification
+    unsigned long long* totals = nullptr;  // device [4]: fallback queries, overflowed queries, rescued queries (running totals)
+    cudaEvent_t ev_done = nullptr;    // recorded at the end of every search (searches return without synchronising)
+    cudaStream_t last_stream = nullptr;
+    bool search_recorded = false;
+    // profiling: a ring of event sets so that timing never forces a host synchronisation inside a search
+    struct ProfSlot {
+        cudaEvent_t t0 = nullptr, t1 = nullptr;
+        std::vector<cudaEvent_t> m;   // 2 per launch of the dominant kernel
+        int n_main = 0;
+        bool pending = false;
+    };
+    static constexpr int kProfSlots = 16;
+    ProfSlot prof[kProfSlots];
+    int prof_head = 0;
 };
 
 namespace {
@@ -226,56 +241,89 @@ int order_after(cudaStream_t waiter, cudaStream_t producer, b2f_index* ix) {
     return B2F_OK;
 }
 
-int largest_pow2_le(int x) {
-    int p = 1;
-    while (p * 2 <= x) p *= 2;
-    return p;
-}
-
-// ---- K1 pipeline: scan groups of <= 8 queries -------------------------------------------------
-// qsel_dev (optional): the list of query rows to process (nsel of them), results scattered to those rows.
-int run_scan(b2f_index* ix, const float* qd, const int32_t* qsel_dev, int nsel, int k, float* Dd, int64_t* Id,
-             int64_t id_offset, Bump& bump, cudaStream_t st, bool profile, size_t ev_base, int* n_main) {
-    const int dq = ix->storage == B2F_STORE_F32 ? (ix->d % 4 == 0 ? ix->d : ix->d) : (int)align_up(ix->d, 8);
-    int g = 8;
-    g = g < largest_pow2_le(1024 / k > 0 ? 1024 / k : 1) ? g : largest_pow2_le(1024 / k > 0 ? 1024 / k : 1);
-    const int by_smem = (int)(16384 / (dq > 0 ? dq : 1));
-    if (by_smem < 1) {
-        set_error("d=%d too large for the streaming scan", ix->d);
-        return B2F_EINVAL;
-    }
-    g = g < largest_pow2_le(by_smem) ? g : largest_pow2_le(by_smem);
-    const int maxparts = scan_max_parts();
-    float* pk = bump.take<float>((size_t)g * maxparts * k);
-    int32_t* pi = bump.take<int32_t>((size_t)g * maxparts * k);
-    float* mk = bump.take<float>((size_t)g * k);
-    int32_t* mi = bump.take<int32_t>((size_t)g * k);
-    for (int q0 = 0; q0 < nsel; q0 += g) {
-        const int nq = nsel - q0 < g ? nsel - q0 : g;
-        int nparts = 0;
-        const float* qptr = qsel_dev ? qd : qd + (int64_t)q0 * ix->d;
-        const int32_t* sel = qsel_dev ? qsel_dev + q0 : nullptr;
-        if (profile) B2F_CUDA(cudaEventRecord(get_event(ix, ev_base + 2 * (size_t)*n_main), st));
-        if (ix->storage == B2F_STORE_F32)
-            B2F_TRY(launch_scan_f32(ix->rows_f32, ix->ntotal, ix->d, ix->metric, qptr, sel, nq, k, pk, pi, &nparts, st));
-        else
-            B2F_TRY(launch_scan_bf16(ix->scan, ix->dpad, ix->ntotal, ix->d, ix->metric, qptr, sel, nq, k, pk, pi, &nparts, st));
-        if (profile) B2F_CUDA(cudaEventRecord(get_event(ix, ev_base + 2 * (size_t)*n_main + 1), st));
-        (*n_main)++;
-        B2F_TRY(launch_merge_parts(pk, pi, nq, nparts, k, k, mk, mi, st));
-        if (sel)
-            B2F_TRY(launch_finalize(mk, mi, nq, k, k, ix->metric, id_offset, sel, Dd, Id, st));
-        else
-            B2F_TRY(launch_finalize(mk, mi, nq, k, k, ix->metric, id_offset, nullptr, Dd + (int64_t)q0 * k, Id + (int64_t)q0 * k, st));
-        ix->st.launches += 3;
-        ix->st.last_launches += 3;
-    }
+// ---- K1: one cooperative launch (scan + merge + faiss formatting) for any number of queries ----------
+// qsel / nsel_dev (optional, device): the list of query rows to process and its length -- the tensor path's
+// uncertified queries, which the host never counts.  counters != null marks the closing kernel of a
+// tensor-path search: it also publishes the search's counters.
+int enqueue_scan(b2f_index* ix, const float* qd, const int32_t* qsel, const int32_t* nsel_dev, int nsel, int k, float* Dd,
+                 int64_t* Id, int64_t id_offset, void* scratch, int32_t* counters, int32_t seq, int nq_batch, int certify,
+                 cudaStream_t st) {
+    ScanArgs a{};
+    a.rows_f32 = ix->storage == B2F_STORE_F32 ? ix->rows_f32 : nullptr;
+    a.rows_bf16 = ix->scan;
+    a.pitch_bf16 = ix->dpad;
+    a.n = ix->ntotal;
+    a.d = ix->d;
+    a.metric = ix->metric;
+    a.k = k;
+    a.q = qd;
+    a.qsel = qsel;
+    a.nsel_dev = nsel_dev;
+    a.nsel = nsel;
+    a.D = Dd;
+    a.I = Id;
+    a.id_offset = id_offset;
+    a.scratch = scratch;
+    a.counters = counters;
+    a.totals = counters ? ix->totals : nullptr;
+    a.host_flag = counters ? ix->host_flag : nullptr;
+    a.seq = seq;
+    a.nq_batch = nq_batch;
+    a.certify = certify;
+    B2F_TRY(launch_scan(a, st));
+    ix->st.launches += 1;
+    ix->st.last_launches += 1;
     return B2F_OK;
 }
 
-size_t scan_ws_bytes(int k) {
-    const size_t g = 8, mp = (size_t)scan_max_parts();
-    return 2 * (g * mp * k * 4 + 256) + 2 * (g * k * 4 + 256) + 4096;
+// Folds the counters the latest finished tensor-path search left in mapped host memory into the host-side
+// view (never blocks; a search that is still running is simply picked up later).
+void harvest_flag(b2f_index* ix) {
+    volatile int32_t* hf = ix->host_flag;
+    const int32_t s = hf[4];
+    if (s == 0 || s == ix->harvested_seq) return;
+    std::atomic_thread_fence(std::memory_order_acquire);
+    const int32_t c0 = hf[0], c1 = hf[1], c2 = hf[2], c3 = hf[3], nqb = hf[6], certify = hf[7];
+    std::atomic_thread_fence(std::memory_order_acquire);
+    if (hf[4] != s) return;  // a later search is publishing right now: take that one next time
+    ix->harvested_seq = s;
+    ix->st.last_list_entries = (int64_t)(((uint64_t)(uint32_t)c3 << 32) | (uint32_t)c2);
+    // The slack that certification needs grows with the neighbour density at rank k (i.e. with the database
+    // size and the data distribution): when more than ~2% of a batch had to fall back, keep more candidates
+    // per query from now on.
+    if (certify && c0 - c1 > (nqb / 50 > 2 ? nqb / 50 : 2) && ix->slack_boost < 224) ix->slack_boost += 32;
+}
+
+void harvest_prof_slot(b2f_index* ix, b2f_index::ProfSlot& sl) {
+    if (!sl.pending) return;
+    sl.pending = false;
+    if (cudaEventSynchronize(sl.t1) != cudaSuccess) {
+        cudaGetLastError();
+        return;
+    }
+    float ms = 0.f, tot = 0.f;
+    for (int i = 0; i < sl.n_main; i++) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, sl.m[2 * (size_t)i], sl.m[2 * (size_t)i + 1]) == cudaSuccess) ms += t;
+    }
+    if (cudaEventElapsedTime(&tot, sl.t0, sl.t1) != cudaSuccess) tot = 0.f;
+    cudaGetLastError();
+    ix->st.last_main_ms = ms;
+    ix->st.last_total_ms = tot;
+    ix->st.last_main_launches = sl.n_main;
+    ix->st.prof_main_ms_sum += ms;
+    ix->st.prof_total_ms_sum += tot;
+    ix->st.prof_main_launches += sl.n_main;
+    ix->st.prof_searches += 1;
+}
+
+cudaEvent_t prof_main_event(b2f_index::ProfSlot& sl, size_t i) {
+    while (sl.m.size() <= i) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+        sl.m.push_back(e);
+    }
+    return sl.m[i];
 }
 
 // Candidates kept per query by the tensor pass.  The slack above k must cover the rows whose coarse
@@ -357,6 +405,8 @@ int b2f_index_create(int32_t d, int32_t metric, int32_t storage, int32_t device,
     if (e == cudaSuccess) e = cudaMemset(ix->stats, 0, 2 * sizeof(float));
     if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&ix->host_flag), 64, cudaHostAllocMapped | cudaHostAllocPortable);
     if (e == cudaSuccess) memset(ix->host_flag, 0, 64);
+    if (e == cudaSuccess) e = cudaMalloc(&ix->totals, 4 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(ix->totals, 0, 4 * sizeof(unsigned long long));
     if (e != cudaSuccess) {
         set_error("index init failed: %s", cudaGetErrorString(e));
         delete ix;
@@ -377,7 +427,14 @@ int b2f_index_destroy(b2f_index* ix) {
     cudaFree(ix->ws);
     if (ix->pinned) cudaFreeHost(ix->pinned);
     if (ix->host_flag) cudaFreeHost(ix->host_flag);
+    cudaFree(ix->totals);
     for (cudaEvent_t e : ix->ev) cudaEventDestroy(e);
+    if (ix->ev_done) cudaEventDestroy(ix->ev_done);
+    for (auto& sl : ix->prof) {
+        if (sl.t0) cudaEventDestroy(sl.t0);
+        if (sl.t1) cudaEventDestroy(sl.t1);
+        for (cudaEvent_t e : sl.m) cudaEventDestroy(e);
+    }
     if (ix->stream) cudaStreamDestroy(ix->stream);
     delete ix;
     return B2F_OK;
@@ -391,6 +448,7 @@ int b2f_index_reset(b2f_index* ix) {
     std::lock_guard<std::mutex> lk(ix->mu);
     DeviceGuard g(ix->device);
     ix->ntotal = 0;
+    if (ix->search_recorded) B2F_CUDA(cudaEventSynchronize(ix->ev_done));
     B2F_CUDA(cudaMemsetAsync(ix->stats, 0, 2 * sizeof(float), ix->stream));
     B2F_CUDA(cudaStreamSynchronize(ix->stream));
     ix->stats_dirty = true;
@@ -413,10 +471,25 @@ int32_t b2f_index_metric(const b2f_index* ix) { return ix ? ix->metric : -1; }
 int32_t b2f_index_storage(const b2f_index* ix) { return ix ? ix->storage : -1; }
 int32_t b2f_index_device(const b2f_index* ix) { return ix ? ix->device : -1; }
 
-int b2f_index_stats(const b2f_index* ix, b2f_stats* out) {
-    if (!ix || !out) {
+int b2f_index_stats(const b2f_index* cix, b2f_stats* out) {
+    if (!cix || !out) {
         set_error("NULL argument");
         return B2F_EINVAL;
+    }
+    // searches return without synchronising and keep their counters on the device: settle them first
+    b2f_index* ix = const_cast<b2f_index*>(cix);
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    if (g.ok && ix->totals) {
+        if (ix->search_recorded) B2F_CUDA(cudaEventSynchronize(ix->ev_done));
+        unsigned long long t[4] = {0, 0, 0, 0};
+        B2F_CUDA(cudaMemcpy(t, ix->totals, sizeof(t), cudaMemcpyDeviceToHost));
+        ix->st.fallback_queries = (int64_t)t[0];
+        ix->st.overflow_queries = (int64_t)t[1];
+        ix->st.rescued_queries = (int64_t)t[2];
+        harvest_flag(ix);
+        for (int i = 0; i < b2f_index::kProfSlots; i++)
+            harvest_prof_slot(ix, ix->prof[(ix->prof_head + i) % b2f_index::kProfSlots]);  // oldest first
     }
     *out = ix->st;
     return B2F_OK;
@@ -450,6 +523,7 @@ int b2f_index_add(b2f_index* ix, int64_t n, const float* x, int32_t mem, void* s
     }
     B2F_TRY(ensure_capacity(ix, ix->ntotal + n));
     cudaStream_t st = stream ? (cudaStream_t)stream : ix->stream;
+    if (ix->search_recorded && ix->last_stream != st) B2F_CUDA(cudaStreamWaitEvent(st, ix->ev_done, 0));
     if (mem == B2F_MEM_DEVICE) {
         B2F_TRY(add_device_rows(ix, x, n, st));
         ix->ntotal += n;
@@ -485,6 +559,7 @@ int b2f_index_add_synth(b2f_index* ix, uint64_t seed, int64_t row0, int64_t nrow
     DeviceGuard g(ix->device);
     B2F_TRY(ensure_capacity(ix, ix->ntotal + nrows));
     cudaStream_t st = ix->stream;
+    if (ix->search_recorded && ix->last_stream != st) B2F_CUDA(cudaStreamWaitEvent(st, ix->ev_done, 0));
     if (ix->storage == B2F_STORE_F32) {
         float* dst = ix->rows_f32 + ix->ntotal * ix->d;
         B2F_TRY(launch_synth(seed, row0, nrows, ix->d, normalize, dst, st));
@@ -518,6 +593,7 @@ int b2f_index_add_pooled(b2f_index* ix, const float* hidden, const int64_t* mask
     DeviceGuard g(ix->device);
     B2F_TRY(ensure_capacity(ix, ix->ntotal + B));
     cudaStream_t st = stream ? (cudaStream_t)stream : ix->stream;
+    if (ix->search_recorded && ix->last_stream != st) B2F_CUDA(cudaStreamWaitEvent(st, ix->ev_done, 0));
     float* rows_out = ix->storage == B2F_STORE_F32 ? ix->rows_f32 + ix->ntotal * ix->d : nullptr;
     B2F_TRY(launch_pool(hidden, mask, B, T, ix->d, pool, normalize, rows_out, ix->scan + ix->ntotal * ix->dpad, ix->dpad,
                         ix->norms + ix->ntotal, ix->stats, st));
@@ -591,8 +667,11 @@ int b2f_index_search(b2f_index* ix, int64_t nq64, const float* q, int64_t k64, f
     }
     cudaStream_t st = stream ? (cudaStream_t)stream : ix->stream;
     B2F_TRY(order_after(st, ix->stream, ix));
+    // searches return without synchronising: a search on another stream must not reuse the workspace early
+    if (ix->search_recorded && ix->last_stream != st) B2F_CUDA(cudaStreamWaitEvent(st, ix->ev_done, 0));
     const bool host = mem == B2F_MEM_HOST;
     const bool profile = P.profile != 0;
+    harvest_flag(ix);
 
     int algo = P.algo;
     const int scan_max = P.scan_max_nq > 0 ? P.scan_max_nq : 1;
@@ -614,20 +693,18 @@ int b2f_index_search(b2f_index* ix, int64_t nq64, const float* q, int64_t k64, f
     // ---- workspace -----------------------------------------------------------------------------
     size_t need = 8192;
     if (host) need += align_up((size_t)nq * ix->d * 4, 256) + align_up((size_t)nq * k * 4, 256) + align_up((size_t)nq * k * 8, 256);
-    need += scan_ws_bytes(k);
+    need += align_up(scan_scratch_bytes(k), 256) + 256;
     if (algo == B2F_ALGO_TENSOR) {
         const size_t nq_pad = (size_t)plan.nq_tiles * 128;
         need += align_up(nq_pad * ix->dpad * 2, 256) + 2 * align_up(nq_pad * 4, 256);
         if (plan.list_mode) {
-            need += align_up(nq_pad * plan.nlists * 4, 256) * 2;                       // shared thresholds + counts
+            need += align_up(nq_pad * plan.nlists * 4, 256) * 3;                       // shared thresholds + counts + final thresholds
             need += align_up(nq_pad * plan.nlists * (size_t)plan.list_cap * 8, 256);   // candidate lists
-            need += align_up((size_t)chunk_nq * 4, 256);                                // overflow flags
         } else {
             need += 2 * align_up(nq_pad * plan.nsplits * kp * 4, 256);  // partial lists
+            need += 2 * align_up((size_t)chunk_nq * kp * 4, 256);       // merged coarse
         }
-        need += 2 * align_up((size_t)chunk_nq * kp * 4, 256);       // merged coarse
-        need += 2 * align_up((size_t)chunk_nq * k * 4, 256);        // exact
-        need += align_up((size_t)chunk_nq * 4, 256) + 256;          // fail list + count
+        need += align_up((size_t)nq * 4, 256) + 256;                    // fail list + counters
     }
     B2F_TRY(ensure_ws(ix, need));
     Bump bump(ix->ws);
@@ -642,181 +719,136 @@ int b2f_index_search(b2f_index* ix, int64_t nq64, const float* q, int64_t k64, f
         B2F_CUDA(cudaMemcpyAsync(qbuf, q, (size_t)nq * ix->d * 4, cudaMemcpyHostToDevice, st));
         qd = qbuf;
     }
+    void* scan_scratch = bump.take<char>(scan_scratch_bytes(k));
     ix->st.searches++;
     ix->st.last_launches = 0;
     ix->st.last_algo = algo;
     ix->st.last_kprime = 0;
     int n_main = 0;
-    const size_t ev_tot = 1, ev_main = 3;
-    if (profile) B2F_CUDA(cudaEventRecord(get_event(ix, ev_tot), st));
+    b2f_index::ProfSlot* slot = nullptr;
+    if (profile) {
+        slot = &ix->prof[ix->prof_head % b2f_index::kProfSlots];
+        ix->prof_head++;
+        harvest_prof_slot(ix, *slot);  // blocks only when the host is a whole ring of searches ahead
+        if (!slot->t0) B2F_CUDA(cudaEventCreate(&slot->t0));
+        if (!slot->t1) B2F_CUDA(cudaEventCreate(&slot->t1));
+        B2F_CUDA(cudaEventRecord(slot->t0, st));
+    }
+    auto main_event = [&](int which) -> int {  // which: 0 = before, 1 = after the dominant kernel's launch
+        if (!slot) return B2F_OK;
+        cudaEvent_t e = prof_main_event(*slot, 2 * (size_t)n_main + which);
+        if (!e) {
+            set_error("cudaEventCreate failed");
+            return B2F_ECUDA;
+        }
+        B2F_CUDA(cudaEventRecord(e, st));
+        return B2F_OK;
+    };
 
     if (ix->ntotal == 0) {
         B2F_TRY(launch_finalize(nullptr, nullptr, nq, 0, k, ix->metric, P.id_offset, nullptr, Dd, Id, st));
         ix->st.launches++;
         ix->st.last_launches++;
     } else if (algo == B2F_ALGO_SCAN) {
-        B2F_TRY(run_scan(ix, qd, nullptr, nq, k, Dd, Id, P.id_offset, bump, st, profile, ev_main, &n_main));
+        B2F_TRY(main_event(0));
+        B2F_TRY(enqueue_scan(ix, qd, nullptr, nullptr, nq, k, Dd, Id, P.id_offset, scan_scratch, nullptr, 0, nq, 0, st));
+        B2F_TRY(main_event(1));
+        n_main++;
     } else {
         const int nq_pad = plan.nq_tiles * 128;
         ix->st.last_kprime = kp;
-        ix->st.last_list_entries = 0;
         __nv_bfloat16* qb = bump.take<__nv_bfloat16>((size_t)nq_pad * ix->dpad);
         float* qnorm = bump.take<float>(nq_pad);
         float* qerr = bump.take<float>(nq_pad);
         float* pk = nullptr;
         int32_t* pi = nullptr;
+        float* ck = nullptr;
+        int32_t* ci = nullptr;
         TensorScanLists lists{};
-        int32_t* ovf = nullptr;
         if (plan.list_mode) {
             lists.shared_thr = bump.take<float>((size_t)nq_pad * plan.nlists);
             lists.counts = bump.take<int32_t>((size_t)nq_pad * plan.nlists);
+            lists.final_thr = bump.take<float>((size_t)nq_pad * plan.nlists);
             lists.cand = bump.take<uint2>((size_t)nq_pad * plan.nlists * plan.list_cap);
-            ovf = bump.take<int32_t>(chunk_nq);
         } else {
             pk = bump.take<float>((size_t)nq_pad * plan.nsplits * kp);
             pi = bump.take<int32_t>((size_t)nq_pad * plan.nsplits * kp);
+            ck = bump.take<float>((size_t)chunk_nq * kp);
+            ci = bump.take<int32_t>((size_t)chunk_nq * kp);
         }
-        float* ck = bump.take<float>((size_t)chunk_nq * kp);
-        int32_t* ci = bump.take<int32_t>((size_t)chunk_nq * kp);
-        float* xk = bump.take<float>((size_t)chunk_nq * k);
-        int32_t* xi = bump.take<int32_t>((size_t)chunk_nq * k);
-        int32_t* fail_list = bump.take<int32_t>(chunk_nq);
-        int32_t* fail_count = bump.take<int32_t>(8);  // [0] uncertified, [1] overflowed, [2..3] u64 list entries, [4] blocks done
+        int32_t* fail_list = bump.take<int32_t>(nq);
+        // [0] uncertified queries, [1] of which list overflows, [2..3] u64 list entries, [4] rescued by the extended pass
+        int32_t* counters = bump.take<int32_t>(8);
         B2F_TRY(refresh_host_stats(ix, st));
         for (int c0 = 0; c0 < nq; c0 += chunk_nq) {
-        const int cn = nq - c0 < chunk_nq ? nq - c0 : chunk_nq;  // queries in this pass (the plan covers chunk_nq)
-        const float* qc = qd + (int64_t)c0 * ix->d;
-        float* Dc = Dd + (int64_t)c0 * k;
-        int64_t* Ic = Id + (int64_t)c0 * k;
-        // one launch: bf16 copy / norms of the queries, clear the 4 counters, reset the shared thresholds
-        B2F_TRY(launch_prep_queries(qc, cn, nq_pad, ix->d, qb, ix->dpad, qnorm, qerr, reinterpret_cast<uint32_t*>(fail_count), 8,
-                                    reinterpret_cast<uint32_t*>(lists.shared_thr),
-                                    plan.list_mode ? (int64_t)nq_pad * plan.nlists : 0, st));
-        if (profile) B2F_CUDA(cudaEventRecord(get_event(ix, ev_main + 2 * (size_t)n_main), st));
-        B2F_TRY(launch_tensor_scan(ix->scan, ix->dpad, ix->norms, ix->ntotal, ix->metric, qb, cn, nq_pad, plan, pk, pi, lists, st));
-        if (profile) B2F_CUDA(cudaEventRecord(get_event(ix, ev_main + 2 * (size_t)n_main + 1), st));
-        n_main++;
-        RerankArgs ra{};
-        ra.rows_f32 = ix->storage == B2F_STORE_F32 ? ix->rows_f32 : nullptr;
-        ra.rows_bf16 = ix->scan;
-        ra.pitch_bf16 = ix->dpad;
-        ra.q = qc;
-        ra.qnorm = qnorm;
-        ra.qerr = qerr;
-        ra.cand_key = ck;
-        ra.cand_id = ci;
-        ra.nq = cn;
-        ra.kp = kp;
-        ra.k = k;
-        ra.d = ix->d;
-        ra.metric = ix->metric;
-        ra.ntotal = ix->ntotal;
-        ra.max_row_norm = sqrtf(ix->host_stats[0]);
-        ra.max_row_err = ix->storage == B2F_STORE_F32 ? sqrtf(ix->host_stats[1]) : 0.f;
-        ra.certify = certify;
-        ra.overflow = ovf;
-        ra.out_key = xk;
-        ra.out_id = xi;
-        ra.D = Dc;   // the re-rank writes faiss-formatted results directly (no separate finalize launch)
-        ra.I = Ic;
-        ra.id_offset = P.id_offset;
-        ra.fail_list = fail_list;
-        ra.fail_count = fail_count;
-        ra.host_flag = ix->host_flag;
-        ra.seq = ++ix->seq;
-        ra.nblocks = cn;
-        if (plan.list_mode) {
-            // K3b + K4 + finalize fused: per query, merge the lists, re-rank exactly, certify, write (D, I)
-            B2F_TRY(launch_merge_lists(lists, cn, plan, ck, ci, ovf, reinterpret_cast<unsigned long long*>(fail_count + 2), &ra, st));
-            ix->st.launches += 3;
-            ix->st.last_launches += 3;
-        } else {
-            B2F_TRY(launch_merge_parts(pk, pi, cn, plan.nsplits, kp, kp, ck, ci, st));
-            B2F_TRY(launch_rerank(ra, st));
-            ix->st.launches += 4;
-            ix->st.last_launches += 4;
-        }
-        if (host) {  // overlaps the flag wait; redone below in the rare fallback case
-            B2F_CUDA(cudaMemcpyAsync(D + (int64_t)c0 * k, Dc, (size_t)cn * k * 4, cudaMemcpyDeviceToHost, st));
-            B2F_CUDA(cudaMemcpyAsync(I + (int64_t)c0 * k, Ic, (size_t)cn * k * 8, cudaMemcpyDeviceToHost, st));
-        }
-        if (certify || plan.list_mode) {
-            // Wait for the completion flag the last block writes into mapped host memory (a few microseconds
-            // after the kernel ends); fall back to a stream synchronize if the stream ends without it (fault).
-            volatile int32_t* hf = ix->host_flag;
-            int32_t hcount[4];
-            bool got = false;
-            for (long spin = 0;; spin++) {
-                if (hf[4] == ra.seq) {
-                    got = true;
-                    break;
-                }
-                if ((spin & 1023) == 1023) {
-                    const cudaError_t qe = cudaStreamQuery(st);
-                    if (qe != cudaErrorNotReady) {
-                        if (qe != cudaSuccess) B2F_CUDA(qe);
-                        if (hf[4] == ra.seq) got = true;
-                        break;
-                    }
-                }
-#if defined(__x86_64__)
-                __builtin_ia32_pause();
-#endif
+            const int cn = nq - c0 < chunk_nq ? nq - c0 : chunk_nq;  // queries in this pass (the plan covers chunk_nq)
+            const float* qc = qd + (int64_t)c0 * ix->d;
+            // one launch: bf16 copy / norms of the queries, reset the shared thresholds, clear the counters (first pass)
+            B2F_TRY(launch_prep_queries(qc, cn, nq_pad, ix->d, qb, ix->dpad, qnorm, qerr, reinterpret_cast<uint32_t*>(counters),
+                                        c0 == 0 ? 8 : 0, reinterpret_cast<uint32_t*>(lists.shared_thr),
+                                        plan.list_mode ? (int64_t)nq_pad * plan.nlists : 0, st));
+            B2F_TRY(main_event(0));
+            B2F_TRY(launch_tensor_scan(ix->scan, ix->dpad, ix->norms, ix->ntotal, ix->metric, qb, cn, nq_pad, plan, pk, pi, lists, st));
+            B2F_TRY(main_event(1));
+            n_main++;
+            RerankArgs ra{};
+            ra.rows_f32 = ix->storage == B2F_STORE_F32 ? ix->rows_f32 : nullptr;
+            ra.rows_bf16 = ix->scan;
+            ra.pitch_bf16 = ix->dpad;
+            ra.q = qc;
+            ra.qnorm = qnorm;
+            ra.qerr = qerr;
+            ra.cand_key = ck;
+            ra.cand_id = ci;
+            ra.nq = cn;
+            ra.kp = kp;
+            ra.k = k;
+            ra.d = ix->d;
+            ra.metric = ix->metric;
+            ra.ntotal = ix->ntotal;
+            ra.max_row_norm = sqrtf(ix->host_stats[0]);
+            ra.max_row_err = ix->storage == B2F_STORE_F32 ? sqrtf(ix->host_stats[1]) : 0.f;
+            ra.certify = certify;
+            ra.D = Dd + (int64_t)c0 * k;  // the re-rank writes faiss-formatted results directly (no finalize launch)
+            ra.I = Id + (int64_t)c0 * k;
+            ra.id_offset = P.id_offset;
+            ra.fail_list = fail_list;
+            ra.fail_count = counters;
+            ra.q_base = c0;
+            if (plan.list_mode) {
+                // K3b + K4 + finalize fused: per query, merge the lists, re-rank exactly, certify, write (D, I)
+                B2F_TRY(launch_merge_lists(lists, cn, plan, reinterpret_cast<unsigned long long*>(counters + 2), ra, st));
+                ix->st.launches += 3;
+                ix->st.last_launches += 3;
+            } else {
+                B2F_TRY(launch_merge_parts(pk, pi, cn, plan.nsplits, kp, kp, ck, ci, st));
+                B2F_TRY(launch_rerank(ra, st));
+                ix->st.launches += 4;
+                ix->st.last_launches += 4;
             }
-            if (!got) {
-                set_error("search: completion flag missing after the stream finished");
-                return B2F_ECUDA;
-            }
-            std::atomic_thread_fence(std::memory_order_acquire);
-            hcount[0] = hf[0];
-            hcount[1] = hf[1];
-            hcount[2] = hf[2];
-            hcount[3] = hf[3];
-            const int nfail = hcount[0];
-            ix->st.overflow_queries += hcount[1];
-            ix->st.last_list_entries += (int64_t)(((uint64_t)(uint32_t)hcount[3] << 32) | (uint32_t)hcount[2]);
-            // The slack that certification needs grows with the neighbour density at rank k (i.e. with the
-            // database size and the data distribution): when more than ~2% of a batch had to fall back,
-            // keep more candidates per query from now on.
-            if (certify && P.slack <= 0 && nfail - hcount[1] > (cn / 50 > 2 ? cn / 50 : 2) && kp + ix->slack_boost < 256)
-                ix->slack_boost += 32;
-            if (nfail > 0) {
-                ix->st.fallback_queries += nfail;
-                int dummy = 0;
-                Bump fb = bump;  // the fallback's scratch is carved after the tensor buffers, per chunk
-                B2F_TRY(run_scan(ix, qc, fail_list, nfail, k, Dc, Ic, P.id_offset, fb, st, false, 0, &dummy));
-                if (host) {
-                    B2F_CUDA(cudaMemcpyAsync(D + (int64_t)c0 * k, Dc, (size_t)cn * k * 4, cudaMemcpyDeviceToHost, st));
-                    B2F_CUDA(cudaMemcpyAsync(I + (int64_t)c0 * k, Ic, (size_t)cn * k * 8, cudaMemcpyDeviceToHost, st));
-                }
-            }
-        }
-        }  // chunk loop
+        }  // query chunks
+        // Closing kernel: the exact scan over the queries that could not be certified.  The count lives on the
+        // device -- with none (the usual case) the kernel publishes the counters and exits -- so the host never
+        // waits inside a search and consecutive searches run back to back on the GPU.
+        B2F_TRY(enqueue_scan(ix, qd, fail_list, counters, 0, k, Dd, Id, P.id_offset, scan_scratch, counters, ++ix->seq, nq,
+                             certify, st));
     }
-    if (profile) B2F_CUDA(cudaEventRecord(get_event(ix, ev_tot + 1), st));
+    if (slot) {
+        B2F_CUDA(cudaEventRecord(slot->t1, st));
+        slot->n_main = n_main;
+        slot->pending = true;
+    }
     if (host) {
-        if (!(algo == B2F_ALGO_TENSOR && ix->ntotal > 0)) {  // the tensor path already queued its copies per chunk
-            B2F_CUDA(cudaMemcpyAsync(D, Dd, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, st));
-            B2F_CUDA(cudaMemcpyAsync(I, Id, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, st));
-        }
-        B2F_CUDA(cudaStreamSynchronize(st));
+        B2F_CUDA(cudaMemcpyAsync(D, Dd, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, st));
+        B2F_CUDA(cudaMemcpyAsync(I, Id, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, st));
     }
-    if (profile) {
-        B2F_CUDA(cudaEventSynchronize(get_event(ix, ev_tot + 1)));
-        float ms = 0.f, tot = 0.f;
-        for (int i = 0; i < n_main; i++) {
-            float t = 0.f;
-            B2F_CUDA(cudaEventElapsedTime(&t, get_event(ix, ev_main + 2 * (size_t)i), get_event(ix, ev_main + 2 * (size_t)i + 1)));
-            ms += t;
-        }
-        B2F_CUDA(cudaEventElapsedTime(&tot, get_event(ix, ev_tot), get_event(ix, ev_tot + 1)));
-        ix->st.last_main_ms = ms;
-        ix->st.last_total_ms = tot;
-        ix->st.last_main_launches = n_main;
-        ix->st.prof_main_ms_sum += ms;
-        ix->st.prof_total_ms_sum += tot;
-        ix->st.prof_main_launches += n_main;
-        ix->st.prof_searches += 1;
+    if (!ix->ev_done) B2F_CUDA(cudaEventCreateWithFlags(&ix->ev_done, cudaEventDisableTiming));
+    B2F_CUDA(cudaEventRecord(ix->ev_done, st));
+    ix->last_stream = st;
+    ix->search_recorded = true;
+    if (host) {
+        B2F_CUDA(cudaStreamSynchronize(st));  // faiss semantics: results are in the caller's arrays on return
+        harvest_flag(ix);
     }
     return B2F_OK;
 }

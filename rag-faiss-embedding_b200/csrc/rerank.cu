@@ -23,13 +23,19 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankArgs a) {
     float* ek = smem;                                        // [kp] exact keys
     int32_t* ei = reinterpret_cast<int32_t*>(smem + a.kp);  // [kp]
     const int q = blockIdx.x;
-    rerank_block(a, q, a.cand_key + (int64_t)q * a.kp, a.cand_id + (int64_t)q * a.kp, ek, ei);
+    const float* ck = a.cand_key + (int64_t)q * a.kp;
+    const int32_t* ci = a.cand_id + (int64_t)q * a.kp;
+    int valid = 0;
+    for (int t = threadIdx.x; t < a.kp; t += kRerankThreads) valid += ci[t] >= 0 ? 1 : 0;
+    valid = __syncthreads_count(valid);  // kp <= 256 = block size: one candidate per thread
+    const bool cert = rerank_block(a, q, ck, ci, a.kp, ck[a.kp - 1], valid < a.kp, ek, ei);
+    if (threadIdx.x == 0 && a.certify && !cert) rerank_record_failure(a, q, false);
 }
 
 int launch_rerank(const RerankArgs& a, cudaStream_t st) {
     if (a.nq <= 0) return B2F_OK;
-    if (a.kp < a.k) {
-        set_error("rerank: kp %d < k %d", a.kp, a.k);
+    if (a.kp < a.k || a.kp > kRerankThreads) {
+        set_error("rerank: kp %d not in [k = %d, %d]", a.kp, a.k, kRerankThreads);
         return B2F_EINVAL;
     }
     rerank_kernel<<<a.nq, kRerankThreads, (size_t)a.kp * 8, st>>>(a);

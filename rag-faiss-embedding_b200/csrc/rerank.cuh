@@ -1,96 +1,128 @@
-// rerank.cuh -- K4 as a block-level device function (128 threads), shared by the standalone re-rank kernel
-// (HEAP mode) and the fused list-merge + re-rank kernel (LIST mode).  See rerank.cu for the bound.
+// rerank.cuh -- K4 as a block-level device function, shared by the standalone re-rank kernel (HEAP mode)
+// and the fused list-merge + re-rank kernel (LIST mode).  See rerank.cu for the bound.
 #pragma once
 #include "common.cuh"
 
 namespace b2f {
 
-constexpr int kRerankThreads = 128;
+constexpr int kRerankThreads = 256;
 
-// ck/ci: the query's kp coarse candidates, ascending by coarse key (shared or global memory).
-// ek/ei: kp floats / ints of shared scratch.  All 128 threads of the block must call.
-__device__ __forceinline__ void rerank_block(const RerankArgs& a, int q, const float* ck, const int32_t* ci, float* ek,
-                                             int32_t* ei) {
-    __shared__ float s_tau;
-    __shared__ int s_nvalid;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const float* qv = a.q + (int64_t)q * a.d;
-    const bool l2 = a.metric == B2F_METRIC_L2;
-    if (threadIdx.x == 0) {
-        s_tau = FLT_MAX;
-        s_nvalid = 0;
-    }
-    __syncthreads();
-    // 8 lanes per candidate, 4 candidates per warp, 16 per pass: every lane has independent 16-byte
-    // loads in flight, so a pass costs about one DRAM round trip instead of eight.
-    const int sub = lane >> 3, sl = lane & 7;
-    const bool vec_f32 = a.rows_f32 && (a.d & 3) == 0;
-    const bool vec_b16 = !a.rows_f32 && (a.d & 7) == 0;
-    for (int c0 = warp * 4; c0 < a.kp; c0 += (kRerankThreads / 32) * 4) {
-        const int c = c0 + sub;
-        int32_t id = c < a.kp ? ci[c] : -1;
-        if ((int64_t)id >= a.ntotal) id = -1;  // never dereference a label outside the index
-        float acc = 0.f;
-        if (id >= 0) {
-            if (vec_f32) {
-                const float* x = a.rows_f32 + (int64_t)id * a.d;
-                for (int j = sl * 4; j < a.d; j += 32) {
-                    const float4 xv = *reinterpret_cast<const float4*>(x + j);
-                    const float4 qq = *reinterpret_cast<const float4*>(qv + j);
+// Exact fp32 key (L2: squared distance in exact-difference form; IP: negated dot product) of row `id` for the
+// query vector qv, computed by the 8 lanes of a lane group (sl = lane & 7); every lane returns the total.
+// The loads of a row are issued four 16-byte chunks at a time, so a lane group keeps 512 bytes in flight.
+__device__ __forceinline__ float exact_key_8lanes(const RerankArgs& a, const float* __restrict__ qv, int32_t id, int sl, bool l2) {
+    float acc = 0.f;
+    if (id >= 0) {
+        if (a.rows_f32 && (a.d & 3) == 0) {
+            const float* x = a.rows_f32 + (int64_t)id * a.d;
+            for (int j0 = sl * 4; j0 < a.d; j0 += 128) {
+                float4 xv[4], qq[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int j = j0 + 32 * u;
+                    xv[u] = j < a.d ? __ldg(reinterpret_cast<const float4*>(x + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int j = j0 + 32 * u;
+                    qq[u] = j < a.d ? __ldg(reinterpret_cast<const float4*>(qv + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
                     if (l2) {
-                        const float t0 = xv.x - qq.x, t1 = xv.y - qq.y, t2 = xv.z - qq.z, t3 = xv.w - qq.w;
+                        const float t0 = xv[u].x - qq[u].x, t1 = xv[u].y - qq[u].y, t2 = xv[u].z - qq[u].z, t3 = xv[u].w - qq[u].w;
                         acc = fmaf(t0, t0, acc); acc = fmaf(t1, t1, acc); acc = fmaf(t2, t2, acc); acc = fmaf(t3, t3, acc);
                     } else {
-                        acc = fmaf(xv.x, qq.x, acc); acc = fmaf(xv.y, qq.y, acc); acc = fmaf(xv.z, qq.z, acc); acc = fmaf(xv.w, qq.w, acc);
-                    }
-                }
-            } else if (vec_b16) {
-                const __nv_bfloat16* x = a.rows_bf16 + (int64_t)id * a.pitch_bf16;
-                for (int j = sl * 8; j < a.d; j += 64) {
-                    const uint4 w = *reinterpret_cast<const uint4*>(x + j);
-                    const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-                    for (int h = 0; h < 4; h++) {
-                        const float x0 = __uint_as_float(ww[h] << 16), x1 = __uint_as_float(ww[h] & 0xffff0000u);
-                        const float q0 = qv[j + 2 * h], q1 = qv[j + 2 * h + 1];
-                        if (l2) {
-                            const float t0 = x0 - q0, t1 = x1 - q1;
-                            acc = fmaf(t0, t0, acc); acc = fmaf(t1, t1, acc);
-                        } else {
-                            acc = fmaf(x0, q0, acc); acc = fmaf(x1, q1, acc);
-                        }
-                    }
-                }
-            } else {
-                for (int j = sl; j < a.d; j += 8) {
-                    const float xv = a.rows_f32 ? a.rows_f32[(int64_t)id * a.d + j]
-                                                : __bfloat162float(a.rows_bf16[(int64_t)id * a.pitch_bf16 + j]);
-                    if (l2) {
-                        const float t = xv - qv[j];
-                        acc = fmaf(t, t, acc);
-                    } else {
-                        acc = fmaf(xv, qv[j], acc);
+                        acc = fmaf(xv[u].x, qq[u].x, acc); acc = fmaf(xv[u].y, qq[u].y, acc);
+                        acc = fmaf(xv[u].z, qq[u].z, acc); acc = fmaf(xv[u].w, qq[u].w, acc);
                     }
                 }
             }
+        } else if (!a.rows_f32 && (a.d & 7) == 0) {
+            const __nv_bfloat16* x = a.rows_bf16 + (int64_t)id * a.pitch_bf16;
+            for (int j0 = sl * 8; j0 < a.d; j0 += 128) {
+                uint4 w[2];
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    const int j = j0 + 64 * u;
+                    w[u] = j < a.d ? __ldg(reinterpret_cast<const uint4*>(x + j)) : make_uint4(0u, 0u, 0u, 0u);
+                }
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    const int j = j0 + 64 * u;
+                    if (j < a.d) {
+                        const uint32_t ww[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
+                        const float4 qa = __ldg(reinterpret_cast<const float4*>(qv + j));
+                        const float4 qb = __ldg(reinterpret_cast<const float4*>(qv + j + 4));
+                        const float qq[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+#pragma unroll
+                        for (int h = 0; h < 4; h++) {
+                            const float x0 = __uint_as_float(ww[h] << 16), x1 = __uint_as_float(ww[h] & 0xffff0000u);
+                            if (l2) {
+                                const float t0 = x0 - qq[2 * h], t1 = x1 - qq[2 * h + 1];
+                                acc = fmaf(t0, t0, acc); acc = fmaf(t1, t1, acc);
+                            } else {
+                                acc = fmaf(x0, qq[2 * h], acc); acc = fmaf(x1, qq[2 * h + 1], acc);
+                            }
+                        }
+                    }
+                }
+            }
+        } else {
+            for (int j = sl; j < a.d; j += 8) {
+                const float xv = a.rows_f32 ? a.rows_f32[(int64_t)id * a.d + j]
+                                            : __bfloat162float(a.rows_bf16[(int64_t)id * a.pitch_bf16 + j]);
+                if (l2) {
+                    const float t = xv - qv[j];
+                    acc = fmaf(t, t, acc);
+                } else {
+                    acc = fmaf(xv, qv[j], acc);
+                }
+            }
         }
-        acc += __shfl_xor_sync(kFull, acc, 4);
-        acc += __shfl_xor_sync(kFull, acc, 2);
-        acc += __shfl_xor_sync(kFull, acc, 1);
-        if (sl == 0 && c < a.kp) {
-            const bool ok = id >= 0 && !(acc != acc);  // NaN never enters (faiss heap semantics)
-            ek[c] = ok ? (l2 ? acc : -acc) : FLT_MAX;
+    }
+    acc += __shfl_xor_sync(kFull, acc, 4);
+    acc += __shfl_xor_sync(kFull, acc, 2);
+    acc += __shfl_xor_sync(kFull, acc, 1);
+    return l2 ? acc : -acc;
+}
+
+// ck/ci: the query's candidates (shared or global memory); nc of them are re-ranked.
+// bound: a coarse key that every row OUTSIDE the nc candidates is known to reach or exceed.
+// all_rows: the candidates are every row of the index (nothing to certify against).
+// ek/ei: nc floats / ints of shared scratch.  All kRerankThreads threads of the block must call.
+// Writes the best k (exact) to the outputs and returns whether the result is certified exact
+// (block-uniform).  Nothing is recorded about a failure here: the caller decides (it may retry with
+// more candidates first).
+__device__ __forceinline__ bool rerank_block(const RerankArgs& a, int q, const float* ck, const int32_t* ci, int nc, float bound,
+                                             bool all_rows, float* ek, int32_t* ei) {
+    __shared__ float s_tau;
+    __shared__ int s_cert;
+    const int lane = threadIdx.x & 31;
+    const float* qv = a.q + (int64_t)q * a.d;
+    const bool l2 = a.metric == B2F_METRIC_L2;
+    if (threadIdx.x == 0) s_tau = FLT_MAX;
+    __syncthreads();
+    // 8 lanes per candidate, 32 candidates per pass of the block
+    const int sl = lane & 7;
+    for (int c0 = 0; c0 < nc; c0 += kRerankThreads / 8) {
+        const int c = c0 + (threadIdx.x >> 3);
+        int32_t id = c < nc ? ci[c] : -1;
+        if ((int64_t)id >= a.ntotal) id = -1;  // never dereference a label outside the index
+        const float key = exact_key_8lanes(a, qv, id, sl, l2);
+        if (sl == 0 && c < nc) {
+            const bool ok = id >= 0 && !(key != key);  // NaN never enters (faiss heap semantics)
+            ek[c] = ok ? key : FLT_MAX;
             ei[c] = ok ? id : -1;
-            if (id >= 0) atomicAdd(&s_nvalid, 1);
         }
     }
     __syncthreads();
-    // rank sort by (key, id, slot); ranks are a permutation of [0, kp)
-    for (int t = threadIdx.x; t < a.kp; t += kRerankThreads) {
+    // rank sort by (key, id, slot); ranks are a permutation of [0, nc); only the first k ranks are emitted
+    for (int t = threadIdx.x; t < nc; t += kRerankThreads) {
         const float mk = ek[t];
         const int32_t mi = ei[t];
         int rank = 0;
-        for (int j = 0; j < a.kp; j++) {
+        for (int j = 0; j < nc; j++) {
             const float ok_ = ek[j];
             const int32_t oi_ = ei[j];
             rank += (cand_less(ok_, oi_, mk, mi) || (ok_ == mk && oi_ == mi && j < t)) ? 1 : 0;
@@ -107,18 +139,23 @@ __device__ __forceinline__ void rerank_block(const RerankArgs& a, int q, const f
         }
         if (rank == a.k - 1) s_tau = mk;
     }
-    // kp < k cannot happen (host guarantees kp >= k)
+    // fewer candidates than k: pad (faiss: label -1, distance +-FLT_MAX)
+    for (int t = nc + threadIdx.x; t < a.k; t += kRerankThreads) {
+        if (a.D) {
+            a.D[(int64_t)q * a.k + t] = l2 ? FLT_MAX : -FLT_MAX;
+            a.I[(int64_t)q * a.k + t] = -1;
+        } else {
+            a.out_key[(int64_t)q * a.k + t] = FLT_MAX;
+            a.out_id[(int64_t)q * a.k + t] = -1;
+        }
+    }
     __syncthreads();
-    const bool overflowed = a.overflow && a.overflow[q];
-    if (threadIdx.x == 0 && (a.certify || overflowed)) {
+    if (threadIdx.x == 0) {
         bool certified;
-        if (overflowed) {
-            certified = false;  // some candidates were dropped: only the exact scan can answer
-        } else if (s_nvalid < a.kp) {
+        if (all_rows) {
             certified = true;  // every row of the index is already a candidate
         } else {
-            const float tau = s_tau;                               // exact k-th best key
-            const float ckp = ck[a.kp - 1];  // k'-th coarse key (without |q~|^2)
+            const float tau = s_tau;  // exact k-th best key (FLT_MAX when fewer than k valid candidates)
             const float qn2 = a.qnorm[q];
             const float qn = sqrtf(qn2);
             const float eq = a.qerr[q];
@@ -128,39 +165,27 @@ __device__ __forceinline__ void rerank_block(const RerankArgs& a, int q, const f
             if (l2) {
                 // c = |q~|^2 + |x~|^2 - 2<q~,x~>: the two norms are fp32 sums as well
                 const float nu = gam * (2.f * qn * a.max_row_norm + qn2 + a.max_row_norm * a.max_row_norm);
-                const float c = ckp + qn2 - nu;
+                const float c = bound + qn2 - nu;
                 const float L = sqrtf(fmaxf(c, 0.f)) - eq - a.max_row_err;
                 certified = L > 0.f && L * L * (1.f - 4e-7f) > tau;
             } else {
-                // keys are negated inner products: non-candidates have <q,x> <= -ckp + slack
+                // keys are negated inner products: non-candidates have <q,x> <= -bound + slack
                 const float nu = gam * qn * a.max_row_norm;
-                const float U = -ckp + nu + (qn + eq) * a.max_row_err + a.max_row_norm * eq;
+                const float U = -bound + nu + (qn + eq) * a.max_row_err + a.max_row_norm * eq;
                 certified = U < -tau;
             }
         }
-        if (!certified) {
-            const int slot = atomicAdd(a.fail_count, 1);
-            a.fail_list[slot] = q;
-            if (overflowed) atomicAdd(a.fail_count + 1, 1);
-        }
+        s_cert = certified ? 1 : 0;
     }
-    // Completion flag: the last block to finish publishes the counters to mapped host memory, so the host
-    // learns "done, n failures" by polling one cache line instead of a D2H copy + stream synchronize.
-    if (threadIdx.x == 0 && a.host_flag) {
-        __threadfence();
-        const int prev = atomicAdd(a.fail_count + 4, 1);
-        if (prev == a.nblocks - 1) {
-            __threadfence();
-            volatile int32_t* fc = a.fail_count;
-            volatile int32_t* hf = a.host_flag;
-            hf[0] = fc[0];
-            hf[1] = fc[1];
-            hf[2] = fc[2];
-            hf[3] = fc[3];
-            __threadfence_system();
-            hf[4] = a.seq;
-        }
-    }
+    __syncthreads();
+    return s_cert != 0;
+}
+
+// Records an uncertified query for the exact scan that closes the search.
+__device__ __forceinline__ void rerank_record_failure(const RerankArgs& a, int q, bool overflowed) {
+    const int slot = atomicAdd(a.fail_count, 1);
+    a.fail_list[slot] = q + a.q_base;
+    if (overflowed) atomicAdd(a.fail_count + 1, 1);
 }
 
 }  // namespace b2f

@@ -12,7 +12,17 @@
 // sorted list in shared memory guarded by a register threshold; after the first few hundred rows
 // almost nothing passes the threshold, so selection costs ~nothing and the distance matrix never
 // exists anywhere.  Algorithmic bytes per launch: n * d * sizeof(row element).
+//
+// One cooperative launch serves any number of queries: the kernel walks them in groups of NQ, and after
+// each group a grid-wide barrier lets one CTA per query merge the per-CTA partial lists and write the
+// faiss-formatted (D, I) rows -- no separate merge / finalize launches.  The query list can live on the
+// device (qsel + a count the kernel reads itself): that is how the tensor path's uncertified queries are
+// re-run without the host ever learning how many there were (no synchronisation inside a search).
+#include <cooperative_groups.h>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace b2f {
 
@@ -62,8 +72,8 @@ struct ScalarRow {  // d % 4 != 0: rows are not 16-byte aligned, one element per
 
 template <int NQ, bool L2, typename RowT, typename Vec>
 __global__ void __launch_bounds__(kScanThreads)
-scan_kernel(const RowT* __restrict__ rows, int64_t pitch, int64_t n, int d, int dq, const float* __restrict__ q,
-            const int32_t* __restrict__ qsel, int nq_valid, int k, float* __restrict__ pk, int32_t* __restrict__ pi) {
+scan_kernel(const RowT* __restrict__ rows, int64_t pitch, int64_t n, int d, int dq, const float* __restrict__ q, int k,
+            const ScanFuse f) {
     constexpr int R = kRowsPerGroup;
     constexpr int V = R * NQ;
     constexpr int VN = Vec::N;
@@ -73,25 +83,55 @@ scan_kernel(const RowT* __restrict__ rows, int64_t pitch, int64_t n, int d, int 
     int32_t* li = reinterpret_cast<int32_t*>(lk + kScanWarps * NQ * k);  // [warps][NQ][k]
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    cg::grid_group grid = cg::this_grid();
+    const int32_t* __restrict__ qsel = f.qsel;
+    // the number of queries is grid-uniform: either a launch argument or a counter earlier kernels left behind
+    const int nsel = f.nsel_dev ? *reinterpret_cast<const volatile int32_t*>(f.nsel_dev) : f.nsel;
+    if (f.counters && blockIdx.x == 0 && threadIdx.x == 0) {
+        // last kernel of a tensor-path search: fold its counters into the index totals and publish them to
+        // mapped host memory (diagnostics only -- nothing waits for this)
+        const int32_t c0 = f.counters[0], c1 = f.counters[1], c4 = f.counters[4];
+        if (f.totals) {
+            if (c0) atomicAdd(f.totals, (unsigned long long)c0);
+            if (c1) atomicAdd(f.totals + 1, (unsigned long long)c1);
+            if (c4) atomicAdd(f.totals + 2, (unsigned long long)c4);
+        }
+        if (f.host_flag) {
+            volatile int32_t* hf = f.host_flag;
+            hf[0] = c0;
+            hf[1] = c1;
+            hf[2] = f.counters[2];
+            hf[3] = f.counters[3];
+            hf[5] = c4;
+            hf[6] = f.nq_batch;
+            hf[7] = f.certify;
+            __threadfence_system();
+            hf[4] = f.seq;
+        }
+    }
+    const int nparts = (int)gridDim.x;
+    const int nchunk = dq / VN;
+    const int64_t ngroups = (n + R - 1) / R;
+    const int64_t W = (int64_t)gridDim.x * kScanWarps;
+    float* wlk = lk + warp * NQ * k;
+    int32_t* wli = li + warp * NQ * k;
+    const int myq = lane & (NQ - 1);
+
+    for (int g0 = 0, gi = 0; g0 < nsel; g0 += NQ, gi++) {
+    const int nq_valid = nsel - g0 < NQ ? nsel - g0 : NQ;
+    __syncthreads();  // the previous group's in-CTA merge has finished with the shared lists
     for (int i = threadIdx.x; i < NQ * dq; i += kScanThreads) {
         const int qi = i / dq, c = i - qi * dq;
-        sq[i] = (qi < nq_valid && c < d) ? q[(int64_t)(qsel ? qsel[qi] : qi) * d + c] : 0.f;
+        sq[i] = (qi < nq_valid && c < d) ? q[(int64_t)(qsel ? qsel[g0 + qi] : g0 + qi) * d + c] : 0.f;
     }
     for (int i = threadIdx.x; i < kScanWarps * NQ * k; i += kScanThreads) {
         lk[i] = FLT_MAX;
         li[i] = -1;
     }
     __syncthreads();
-
-    float* wlk = lk + warp * NQ * k;
-    int32_t* wli = li + warp * NQ * k;
-    const int myq = lane & (NQ - 1);
     float thr_k = FLT_MAX;
     int32_t thr_i = -1;
 
-    const int nchunk = dq / VN;
-    const int64_t ngroups = (n + R - 1) / R;
-    const int64_t W = (int64_t)gridDim.x * kScanWarps;
     for (int64_t g = (int64_t)blockIdx.x * kScanWarps + warp; g < ngroups; g += W) {
         const int64_t row0 = g * R;
         float acc[V];
@@ -167,72 +207,163 @@ scan_kernel(const RowT* __restrict__ rows, int64_t pitch, int64_t n, int d, int 
     }
     __syncthreads();
     // in-CTA merge: warp w < NQ merges the 8 per-warp lists of query w into this CTA's partial list
+    // (double buffered over groups: the merge of group g may still be reading while group g+1 is written)
+    float* pk = f.pk + (size_t)(gi & 1) * NQ * nparts * k;
+    int32_t* pi = f.pi + (size_t)(gi & 1) * NQ * nparts * k;
     if (warp < NQ && warp < nq_valid) {
-        const int64_t o = ((int64_t)warp * gridDim.x + blockIdx.x) * k;
+        const int64_t o = ((int64_t)warp * nparts + blockIdx.x) * k;
         warp_merge_lists(lk + warp * k, li + warp * k, kScanWarps, k, (int64_t)NQ * k, k, pk + o, pi + o, lane);
     }
+    grid.sync();
+    // one CTA per query: two-level merge of the nparts partial lists (32 lists per warp, then the <= 32
+    // intermediate lists), written straight to the caller's buffers in faiss conventions
+    for (int qi = blockIdx.x; qi < nq_valid; qi += nparts) {
+        const float* qk = pk + (int64_t)qi * nparts * k;
+        const int32_t* qid = pi + (int64_t)qi * nparts * k;
+        const int nl1 = (nparts + kWarp - 1) / kWarp;
+        float* mk = f.mk + (int64_t)qi * (kWarp + 1) * k;
+        int32_t* mi = f.mi + (int64_t)qi * (kWarp + 1) * k;
+        float* fk = mk + (int64_t)kWarp * k;   // final list
+        int32_t* fi = mi + (int64_t)kWarp * k;
+        if (nl1 == 1) {
+            if (warp == 0) warp_merge_lists(qk, qid, nparts, k, k, k, fk, fi, lane);
+        } else {
+            for (int g = warp; g < nl1; g += kScanWarps) {
+                const int first = g * kWarp;
+                const int cnt = nparts - first < kWarp ? nparts - first : kWarp;
+                warp_merge_lists(qk + (int64_t)first * k, qid + (int64_t)first * k, cnt, k, k, k, mk + (int64_t)g * k, mi + (int64_t)g * k, lane);
+            }
+            __syncthreads();
+            if (warp == 0) warp_merge_lists(mk, mi, nl1, k, k, k, fk, fi, lane);
+        }
+        __syncthreads();
+        const int64_t orow = qsel ? qsel[g0 + qi] : g0 + qi;
+        for (int j = threadIdx.x; j < k; j += kScanThreads) {
+            const float key = fk[j];
+            const int32_t id = fi[j];
+            const int64_t o = orow * k + j;
+            if (id < 0) {
+                f.D[o] = L2 ? FLT_MAX : -FLT_MAX;
+                f.I[o] = -1;
+            } else {
+                f.D[o] = L2 ? key : -key;
+                f.I[o] = (int64_t)id + f.id_offset;
+            }
+        }
+        __syncthreads();
+    }
+    }  // query groups
 }
-
-static int g_scan_blocks_per_sm = 2;
 
 int scan_max_parts() { return kNumSMs * 4; }
 
+// queries per pass the per-warp lists allow (8 warps x NQ x k x 8 bytes of shared memory): NQ * k <= 1024
+static int scan_nq_cap(int k) {
+    int p = 1;
+    const int lim = 1024 / k > 0 ? 1024 / k : 1;
+    while (p * 2 <= lim && p < 8) p *= 2;
+    return p;
+}
+static size_t scan_pbytes(int k) { return 2 * (size_t)scan_nq_cap(k) * scan_max_parts() * (size_t)k * 4 + 256; }
+static size_t scan_mbytes(int k) { return (size_t)scan_nq_cap(k) * (kWarp + 1) * (size_t)k * 4 + 256; }
+
+size_t scan_scratch_bytes(int k) {
+    // pk/pi: [2][NQ][max parts][k] double-buffered partial lists; mk/mi: [NQ][33][k] merge scratch
+    return 2 * scan_pbytes(k) + 2 * scan_mbytes(k);
+}
+
 template <int NQ, bool L2, typename RowT, typename Vec>
-static int launch_one(const RowT* rows, int64_t pitch, int64_t n, int d, const float* q, const int32_t* qsel, int nq, int k, float* pk,
-                      int32_t* pi, int* nparts_out, cudaStream_t st) {
-    const int dq = ((d + Vec::N - 1) / Vec::N) * Vec::N;
-    const size_t smem = (size_t)NQ * dq * 4 + (size_t)kScanWarps * NQ * k * 8;
+static int launch_one(const RowT* rows, int64_t pitch, const ScanArgs& a, cudaStream_t st) {
+    const int dq = ((a.d + Vec::N - 1) / Vec::N) * Vec::N;
+    const size_t smem = (size_t)NQ * dq * 4 + (size_t)kScanWarps * NQ * a.k * 8;
     auto kern = scan_kernel<NQ, L2, RowT, Vec>;
-    static bool configured = false;
-    static int occ = 1;
     static size_t configured_smem = 0;
-    if (!configured || smem > configured_smem) {
+    if (configured_smem == 0 || smem > configured_smem) {
         B2F_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 65536 ? smem : 65536)));
         configured_smem = smem > 65536 ? smem : 65536;
-        configured = true;
     }
-    B2F_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kScanThreads, smem));
+    // occupancy per (kernel, smem) is cached: the query costs microseconds and sits on the search path
+    static size_t occ_smem = ~(size_t)0;
+    static int occ = 1;
+    if (occ_smem != smem) {
+        B2F_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kScanThreads, smem));
+        occ_smem = smem;
+    }
     if (occ < 1) {
         set_error("scan kernel does not fit: smem %zu", smem);
         return B2F_EINVAL;
     }
-    if (occ > 4) occ = 4;
-    g_scan_blocks_per_sm = occ;
-    const int64_t ngroups = (n + kRowsPerGroup - 1) / kRowsPerGroup;
+    const int use = occ > 4 ? 4 : occ;
+    const int64_t ngroups = (a.n + kRowsPerGroup - 1) / kRowsPerGroup;
     int64_t want = (ngroups + kScanWarps - 1) / kScanWarps;
-    int blocks = (int)(want < (int64_t)kNumSMs * occ ? want : (int64_t)kNumSMs * occ);
+    int blocks = (int)(want < (int64_t)kNumSMs * use ? want : (int64_t)kNumSMs * use);
     if (blocks < 1) blocks = 1;
-    *nparts_out = blocks;
-    kern<<<blocks, kScanThreads, smem, st>>>(rows, pitch, n, d, dq, q, qsel, nq, k, pk, pi);
-    B2F_CUDA(cudaGetLastError());
+    ScanFuse f{};
+    f.D = a.D;
+    f.I = a.I;
+    f.id_offset = a.id_offset;
+    f.qsel = a.qsel;
+    f.nsel_dev = a.nsel_dev;
+    f.nsel = a.nsel;
+    char* sc = static_cast<char*>(a.scratch);
+    const size_t pbytes = scan_pbytes(a.k), mbytes = scan_mbytes(a.k);
+    f.pk = reinterpret_cast<float*>(sc);
+    f.pi = reinterpret_cast<int32_t*>(sc + pbytes);
+    f.mk = reinterpret_cast<float*>(sc + 2 * pbytes);
+    f.mi = reinterpret_cast<int32_t*>(sc + 2 * pbytes + mbytes);
+    f.counters = a.counters;
+    f.totals = a.totals;
+    f.host_flag = a.host_flag;
+    f.seq = a.seq;
+    f.nq_batch = a.nq_batch;
+    f.certify = a.certify;
+    const RowT* rows_ = rows;
+    int64_t pitch_ = pitch, n_ = a.n;
+    int d_ = a.d, dq_ = dq, k_ = a.k;
+    const float* q_ = a.q;
+    void* args[] = {(void*)&rows_, (void*)&pitch_, (void*)&n_, (void*)&d_, (void*)&dq_, (void*)&q_, (void*)&k_, (void*)&f};
+    // cooperative: every CTA is resident (the grid is sized from the occupancy query), so grid.sync() is legal
+    B2F_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)blocks), dim3(kScanThreads), args, smem, st));
     return B2F_OK;
 }
 
 template <typename RowT, typename Vec>
-static int dispatch(const RowT* rows, int64_t pitch, int64_t n, int d, int metric, const float* q, const int32_t* qsel, int nq, int k,
-                    float* pk, int32_t* pi, int* nparts_out, cudaStream_t st) {
-    const bool l2 = metric == B2F_METRIC_L2;
-#define B2F_SCAN_CASE(NQ)                                                                                     \
-    return l2 ? launch_one<NQ, true, RowT, Vec>(rows, pitch, n, d, q, qsel, nq, k, pk, pi, nparts_out, st)          \
-              : launch_one<NQ, false, RowT, Vec>(rows, pitch, n, d, q, qsel, nq, k, pk, pi, nparts_out, st)
-    if (nq <= 1) { B2F_SCAN_CASE(1); }
-    if (nq <= 2) { B2F_SCAN_CASE(2); }
-    if (nq <= 4) { B2F_SCAN_CASE(4); }
-    if (nq <= 8) { B2F_SCAN_CASE(8); }
+static int dispatch(const RowT* rows, int64_t pitch, const ScanArgs& a, cudaStream_t st) {
+    const bool l2 = a.metric == B2F_METRIC_L2;
+    // queries per pass: bounded by the per-warp lists (8 warps x NQ x k x 8 bytes) and the query tile in smem
+    int g = 8;
+    auto pow2_le = [](int x) { int p = 1; while (p * 2 <= x) p *= 2; return p; };
+    const int by_k = scan_nq_cap(a.k);
+    const int dq = ((a.d + Vec::N - 1) / Vec::N) * Vec::N;
+    const int by_smem = 16384 / (dq > 0 ? dq : 1);
+    if (by_smem < 1) {
+        set_error("d=%d too large for the streaming scan", a.d);
+        return B2F_EINVAL;
+    }
+    if (g > by_k) g = by_k;
+    if (g > pow2_le(by_smem)) g = pow2_le(by_smem);
+    // device-side query count (the tensor path's fallback): usually 0..2 queries -> a 4-wide register tile
+    const int want = a.nsel_dev ? 4 : a.nsel;
+#define B2F_SCAN_CASE(NQ)                                                       \
+    return l2 ? launch_one<NQ, true, RowT, Vec>(rows, pitch, a, st)         \
+              : launch_one<NQ, false, RowT, Vec>(rows, pitch, a, st)
+    if (want <= 1 || g == 1) { B2F_SCAN_CASE(1); }
+    if (want <= 2 || g == 2) { B2F_SCAN_CASE(2); }
+    if (want <= 4 || g == 4) { B2F_SCAN_CASE(4); }
+    B2F_SCAN_CASE(8);
 #undef B2F_SCAN_CASE
-    set_error("scan: nq %d > 8 per launch", nq);
-    return B2F_EINVAL;
 }
 
-int launch_scan_f32(const float* rows, int64_t n, int d, int metric, const float* q, const int32_t* qsel, int nq, int k,
-                    float* pk, int32_t* pi, int* nparts_out, cudaStream_t st) {
-    if (d % 4 == 0) return dispatch<float, RowVec<float>>(rows, d, n, d, metric, q, qsel, nq, k, pk, pi, nparts_out, st);
-    return dispatch<float, ScalarRow>(rows, d, n, d, metric, q, qsel, nq, k, pk, pi, nparts_out, st);
-}
-
-int launch_scan_bf16(const __nv_bfloat16* rows, int64_t pitch, int64_t n, int d, int metric, const float* q,
-                     const int32_t* qsel, int nq, int k, float* pk, int32_t* pi, int* nparts_out, cudaStream_t st) {
-    return dispatch<__nv_bfloat16, RowVec<__nv_bfloat16>>(rows, pitch, n, d, metric, q, qsel, nq, k, pk, pi, nparts_out, st);
+int launch_scan(const ScanArgs& a, cudaStream_t st) {
+    if (a.k <= 0 || a.k > 1024) {
+        set_error("scan: k=%d out of range", a.k);
+        return B2F_EINVAL;
+    }
+    if (a.rows_f32) {
+        if (a.d % 4 == 0) return dispatch<float, RowVec<float>>(a.rows_f32, a.d, a, st);
+        return dispatch<float, ScalarRow>(a.rows_f32, a.d, a, st);
+    }
+    return dispatch<__nv_bfloat16, RowVec<__nv_bfloat16>>(a.rows_bf16, a.pitch_bf16, a, st);
 }
 
 }  // namespace b2f
