@@ -26,6 +26,15 @@ __host__ __device__ __forceinline__ bool cand_less(float ka, int32_t ia, float k
     return ka < kb || (ka == kb && (uint32_t)ia < (uint32_t)ib);
 }
 
+// Order-preserving float <-> uint32 map (64-bit (key,id) composites, atomicMin on keys)
+__device__ __forceinline__ uint32_t enc_key(float f) {
+    const uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float dec_key(uint32_t e) {
+    return __uint_as_float((e & 0x80000000u) ? (e & 0x7fffffffu) : ~e);
+}
+
 // ---- warp-level helpers ------------------------------------------------------------------------
 
 // Sum V values across the warp with V-1 + (5 - log2 V) * V shuffles instead of 5 * V: after the
@@ -84,6 +93,8 @@ __device__ __forceinline__ void warp_sorted_insert(float* lk, int32_t* li, int k
 
 // Merge up to 32 ascending lists (list l starts at keys + l*stride, length len) into the k best,
 // written by lane 0 to (ok, oi).  One warp.  Lists may contain (FLT_MAX,-1) padding.
+// CG: read the lists with ld.global.cg (they were written by other SMs during this kernel: bypass L1).
+template <bool CG = false>
 __device__ __forceinline__ void warp_merge_lists(const float* keys, const int32_t* ids, int nlists, int len,
                                                  int64_t stride, int k, float* ok, int32_t* oi, int lane) {
     int pos = 0;
@@ -91,8 +102,8 @@ __device__ __forceinline__ void warp_merge_lists(const float* keys, const int32_
     int32_t hi = -1;
     const bool have = lane < nlists;
     if (have && len > 0) {
-        hk = keys[(int64_t)lane * stride];
-        hi = ids[(int64_t)lane * stride];
+        hk = CG ? __ldcg(keys + (int64_t)lane * stride) : keys[(int64_t)lane * stride];
+        hi = CG ? __ldcg(ids + (int64_t)lane * stride) : ids[(int64_t)lane * stride];
     }
     for (int o = 0; o < k; o++) {
         float bk = hk;
@@ -116,8 +127,8 @@ __device__ __forceinline__ void warp_merge_lists(const float* keys, const int32_
         if (lane == bl && have) {
             pos++;
             if (pos < len) {
-                hk = keys[(int64_t)lane * stride + pos];
-                hi = ids[(int64_t)lane * stride + pos];
+                hk = CG ? __ldcg(keys + (int64_t)lane * stride + pos) : keys[(int64_t)lane * stride + pos];
+                hi = CG ? __ldcg(ids + (int64_t)lane * stride + pos) : ids[(int64_t)lane * stride + pos];
             } else {
                 hk = FLT_MAX;
                 hi = -1;
@@ -172,6 +183,8 @@ struct ScanFuse {                  // device-side view (kernel argument)
     int32_t* host_flag;            // optional mapped host memory [16]
     int32_t seq;
     int32_t nq_batch, certify;     // echoed to the host flag (adaptive slack)
+    uint32_t* tub;                 // persistent [2][3][8]: per-query upper bound of the k-th best key (min over CTAs), all-ones when idle
+    int32_t parity;                // launch parity: this launch uses tub[parity] and re-arms tub[parity ^ 1]
 };
 struct ScanArgs {                  // host-side launch description
     const float* rows_f32;         // fp32 rows, or
@@ -192,7 +205,10 @@ struct ScanArgs {                  // host-side launch description
     int32_t* host_flag;
     int32_t seq;
     int32_t nq_batch, certify;
+    uint32_t* tub;
+    int32_t parity;
 };
+constexpr int kScanTubWords = 2 * 3 * 8;
 int scan_max_parts();
 size_t scan_scratch_bytes(int k);
 int launch_scan(const ScanArgs& a, cudaStream_t st);

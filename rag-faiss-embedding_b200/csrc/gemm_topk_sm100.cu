@@ -257,14 +257,6 @@ __device__ __noinline__ float heap_push(float* hk, int32_t* hi, int tid, float k
     return hk[tid];
 }
 
-// Order-preserving float <-> uint32 map (for the 64-bit (key,id) composites of the list merge)
-__device__ __forceinline__ uint32_t enc_key(float f) {
-    const uint32_t b = __float_as_uint(f);
-    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
-}
-__device__ __forceinline__ float dec_key(uint32_t e) {
-    return __uint_as_float((e & 0x80000000u) ? (e & 0x7fffffffu) : ~e);
-}
 
 template <int KP, bool L2, bool LIST, bool QRES, bool PAIR>
 __global__ void __launch_bounds__(k2_threads(LIST), 1)
@@ -555,18 +547,25 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 // branch table: ~440 cycles per survivor on a lone warp -- clock64 instrumentation showed it
                 // was half of the kernel time at nq = 32 and a quarter at nq = 1024.)
                 if (__any_sync(kFull, mask != 0u)) {
-                    uint32_t* st = xpose + lane;
+                    // park: lane-major rows of 32 words, written as eight 16-byte stores whose chunk index is
+                    // XOR-swizzled with the lane so that every quarter-warp covers all 32 banks (8 store
+                    // instructions instead of 32; the tile period is set by the slowest of the pair's 16 epilogue
+                    // warps, i.e. by these events)
+                    uint32_t* st = xpose + lane * 32;
 #pragma unroll
-                    for (int j = 0; j < 32; j++) st[j * 32] = r[j];
+                    for (int c4 = 0; c4 < 8; c4++)
+                        *reinterpret_cast<uint4*>(st + ((c4 ^ (lane & 7)) << 2)) = make_uint4(r[4 * c4], r[4 * c4 + 1], r[4 * c4 + 2], r[4 * c4 + 3]);
                     uint32_t m = mask;
                     while (m) {
                         const int j = __ffs(m) - 1;
                         m &= m - 1;
-                        const float sdot = __uint_as_float(st[j * 32]);
+                        const float sdot = __uint_as_float(st[((((j >> 2) ^ (lane & 7)) << 2)) + (j & 3)]);
                         const float key = L2 ? fmaf(-2.f, sdot, tbc[j]) : tbc[j] - sdot;
                         if (cnt < la.cap) mylist[cnt] = make_uint2(__float_as_uint(key), (uint32_t)(rowc + j));
                         cnt++;
-                        if (key < best[JSLOTS - 1]) {
+                        if (jv == 1) {
+                            best[JSLOTS - 1] = fminf(best[JSLOTS - 1], key);  // one row per virtual split: a running minimum
+                        } else if (key < best[JSLOTS - 1]) {
                             // sorted insert without a dependency chain: new[i] = max(old[i-1], min(old[i], key))
                             float nb[JSLOTS];
 #pragma unroll
@@ -734,50 +733,70 @@ merge_lists_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ c
     extern __shared__ __align__(16) unsigned long long comp[];  // [max(cap_entries, RANK_MAX)], later the re-rank scratch
     __shared__ int s_off[2 * kNumSMs + 2];
     __shared__ int s_cnt[3];
-    __shared__ int s_nsurv;
+    __shared__ int s_nsurv, s_nrest;
+    __shared__ int s_hist[MERGE_THREADS], s_wsum[MERGE_THREADS / 32], s_sel[2];
     __shared__ int s_ovf;
-    __shared__ float s_tc;
+    __shared__ unsigned int s_tc_enc;
     const int cap_c = cap_entries > RANK_MAX ? cap_entries : RANK_MAX;
     unsigned long long* surv = comp + cap_c;                       // [KP_MAX]
     float* sk = reinterpret_cast<float*>(surv + KP_MAX);           // [RANK_MAX] coarse keys, ascending
     int32_t* si = reinterpret_cast<int32_t*>(sk + RANK_MAX);       // [RANK_MAX]
+    unsigned short* owner = reinterpret_cast<unsigned short*>(si + RANK_MAX);  // [cap_entries] list of every gathered entry
     float* ek = reinterpret_cast<float*>(comp);                    // [RANK_MAX] exact keys   (comp is dead by then)
     int32_t* ei = reinterpret_cast<int32_t*>(ek + RANK_MAX);       // [RANK_MAX]
     const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // lists of this query: (database splits of its tile) x (column halves); see the kernel's my_nsplits
     const int tile = q / tile_queries;
     const int nsplits = (total_units / ntile_units + (tile < total_units % ntile_units ? 1 : 0)) * halves;
-    if (warp == 0) {
-        // exclusive prefix sum of the list lengths, 32 lists at a time; T_c = the smallest final threshold
-        int run = 0, o = 0;
+    // list lengths and final thresholds: one parallel sweep (up to 296 lists), then a warp-level prefix sum
+    if (tid == 0) {
+        s_tc_enc = 0xffffffffu;
+        s_ovf = 0;
+        s_nsurv = 0;
+        s_nrest = 0;
+        s_cnt[0] = 0;
+    }
+    __syncthreads();
+    {
         float tc = 3.0e38f;
-        for (int s0 = 0; s0 < nsplits; s0 += 32) {
-            const int s = s0 + lane;
-            int c = s < nsplits ? counts[(int64_t)q * nl_stride + s] : 0;
-            if (s < nsplits) tc = fminf(tc, final_thr[(int64_t)q * nl_stride + s]);
+        int o = 0;
+        for (int s2 = tid; s2 < nsplits; s2 += MERGE_THREADS) {
+            int c = counts[(int64_t)q * nl_stride + s2];
+            tc = fminf(tc, final_thr[(int64_t)q * nl_stride + s2]);
             if (c > list_cap) {
                 c = list_cap;
                 o = 1;
             }
+            s_off[s2 + 1] = c;
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) tc = fminf(tc, __shfl_xor_sync(kFull, tc, d));
+        o = __reduce_or_sync(kFull, o);
+        if (lane == 0) {
+            atomicMin(&s_tc_enc, enc_key(tc));
+            if (o) s_ovf = 1;
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        int run = 0;
+        for (int s0 = 0; s0 < nsplits; s0 += 32) {
+            const int s2 = s0 + lane;
+            const int c = s2 < nsplits ? s_off[s2 + 1] : 0;
             int incl = c;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 const int up = __shfl_up_sync(kFull, incl, d);
                 if (lane >= d) incl += up;
             }
-            if (s < nsplits) s_off[s] = run + incl - c;
+            __syncwarp();
+            if (s2 < nsplits) s_off[s2 + 1] = run + incl;  // s_off[s] = entries before list s; s_off[nsplits] = total
             run += __shfl_sync(kFull, incl, 31);
         }
-        o = __reduce_or_sync(kFull, o);
-#pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) tc = fminf(tc, __shfl_xor_sync(kFull, tc, d));
         if (lane == 0) {
-            s_off[nsplits] = run;
+            s_off[0] = 0;
             if (total_entries) atomicAdd(total_entries, (unsigned long long)run);
-            s_ovf = (o || run > cap_entries) ? 1 : 0;
-            s_nsurv = 0;
-            s_cnt[0] = 0;
-            s_tc = tc;
+            if (run > cap_entries) s_ovf = 1;
         }
     }
     __syncthreads();
@@ -787,8 +806,13 @@ merge_lists_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ c
         return;
     }
     const int M = s_off[nsplits];
-    // gather: flattened over all candidates so every thread has independent loads in flight; the owning
-    // list of element i is found by binary search in the prefix array (<= 9 steps in shared memory)
+    // gather the lists into one array of composites: flattened over all candidates so every thread has independent
+    // loads in flight; the owning list of element i comes from a map filled by one thread per list
+    for (int l = tid; l < nsplits; l += MERGE_THREADS) {
+        const int o = s_off[l], e = s_off[l + 1];
+        for (int i = o; i < e; i++) owner[i] = (unsigned short)l;
+    }
+    __syncthreads();
     for (int i0 = tid; i0 < M; i0 += 4 * MERGE_THREADS) {
         uint2 e[4];
 #pragma unroll
@@ -796,13 +820,8 @@ merge_lists_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ c
             const int i = i0 + u * MERGE_THREADS;
             e[u] = make_uint2(0u, 0u);
             if (i < M) {
-                int lo = 0, hi = nsplits - 1;
-                while (lo < hi) {
-                    const int mid = (lo + hi + 1) >> 1;
-                    if (s_off[mid] <= i) lo = mid;
-                    else hi = mid - 1;
-                }
-                e[u] = cand[((int64_t)q * nl_stride + lo) * list_cap + (i - s_off[lo])];
+                const int l = owner[i];
+                e[u] = cand[((int64_t)q * nl_stride + l) * list_cap + (i - s_off[l])];
             }
         }
 #pragma unroll
@@ -812,41 +831,60 @@ merge_lists_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ c
         }
     }
     __syncthreads();
-    int nsorted;  // entries of sk / si that are filled (ascending)
-    if (M <= RANK_MAX) {
-        // direct ranking, up to four elements per thread sharing every broadcast read of comp[j]
-        unsigned long long mine[RANK_MAX / MERGE_THREADS];
-        int rank[RANK_MAX / MERGE_THREADS];
-#pragma unroll
-        for (int u = 0; u < RANK_MAX / MERGE_THREADS; u++) {
-            const int i = tid + u * MERGE_THREADS;
-            mine[u] = i < M ? comp[i] : ~0ull;
-            rank[u] = 0;
+    // Selection.  sk / si [0, min(k', M)): the k' best, ascending; [k', M) (when M <= RANK_MAX): the other list
+    // entries in no particular order -- only the extended certification looks at them.
+    if (M <= MERGE_THREADS) {
+        // one element per thread: count the composites below it (distinct: row ids) and land on the sorted slot
+        if (tid < M) {
+            const unsigned long long mine = comp[tid];
+            int rank = 0;
+            for (int j = 0; j < M; j++) rank += comp[j] < mine ? 1 : 0;
+            sk[rank] = dec_key((uint32_t)(mine >> 32));
+            si[rank] = (int32_t)(uint32_t)(mine & 0xffffffffu);
         }
-        for (int j = 0; j < M; j++) {
-            const unsigned long long o = comp[j];
-#pragma unroll
-            for (int u = 0; u < RANK_MAX / MERGE_THREADS; u++)
-                rank[u] += (o < mine[u] || (o == mine[u] && j < tid + u * MERGE_THREADS)) ? 1 : 0;
-        }
-#pragma unroll
-        for (int u = 0; u < RANK_MAX / MERGE_THREADS; u++) {
-            if (tid + u * MERGE_THREADS < M) {
-                sk[rank[u]] = dec_key((uint32_t)(mine[u] >> 32));
-                si[rank[u]] = (int32_t)(uint32_t)(mine[u] & 0xffffffffu);
-            }
-        }
-        nsorted = M;
     } else {
         unsigned long long T = ~0ull;
         int it = 0;
-        // smallest 32-bit key K with count(key <= K) >= kp
-        unsigned int lo = 0, hi = 0xffffffffu;
-        while (lo < hi) {
-            const unsigned int mid = lo + ((hi - lo) >> 1);
-            const int total = block_count_le(comp, M, ((unsigned long long)mid << 32) | 0xffffffffull, s_cnt, it++, tid, lane);
-            if (total >= kp) hi = mid;
-            else lo = mid + 1;
+        // K = key of the k'-th smallest composite: radix select over the 32 key bits, 8 bits per pass (256-bin
+        // histogram in shared memory, warp-aggregated increments, block-wide scan) -- 4 passes instead of 32
+        // bisection steps
+        unsigned int lo = 0;
+        int need = kp;
+#pragma unroll 1
+        for (int pass = 0; pass < 4; pass++) {
+            const int shift = 24 - 8 * pass;
+            s_hist[tid] = 0;  // MERGE_THREADS == 256 bins
+            __syncthreads();
+            for (int i0 = 0; i0 < M; i0 += MERGE_THREADS) {
+                const int i = i0 + tid;
+                const unsigned int key = i < M ? (unsigned int)(comp[i] >> 32) : 0u;
+                const bool in = i < M && (pass == 0 || (key >> (shift + 8)) == (lo >> (shift + 8)));
+                const unsigned int bin = (key >> shift) & 255u;
+                const unsigned int peers = __match_any_sync(kFull, in ? bin : 256u + (unsigned)lane);
+                if (in && lane == __ffs(peers) - 1) atomicAdd(&s_hist[bin], __popc(peers));
+            }
+            __syncthreads();
+            // inclusive scan of the 256 bins: warp scans + the 8 warp totals
+            const int h = s_hist[tid];
+            int incl = h;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int up = __shfl_up_sync(kFull, incl, d);
+                if (lane >= d) incl += up;
+            }
+            if (lane == 31) s_wsum[warp] = incl;
+            __syncthreads();
+            int base = 0;
+            for (int w = 0; w < warp; w++) base += s_wsum[w];
+            incl += base;
+            if (incl >= need && incl - h < need) {  // exactly one bin
+                s_sel[0] = tid;
+                s_sel[1] = need - (incl - h);
+            }
+            __syncthreads();
+            lo |= (unsigned int)s_sel[0] << shift;
+            need = s_sel[1];
+            __syncthreads();
         }
         const unsigned long long kbits = (unsigned long long)lo << 32;
         T = kbits | 0xffffffffull;
@@ -866,23 +904,28 @@ merge_lists_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ c
             if (v <= T) {
                 const int slot = atomicAdd(&s_nsurv, 1);
                 if (slot < kp) surv[slot] = v;
+            } else if (M <= RANK_MAX) {
+                const int slot = kp + atomicAdd(&s_nrest, 1);
+                if (slot < RANK_MAX) {
+                    sk[slot] = dec_key((uint32_t)(v >> 32));
+                    si[slot] = (int32_t)(uint32_t)(v & 0xffffffffu);
+                }
             }
         }
         __syncthreads();
-        const int ns = s_nsurv < kp ? s_nsurv : kp;
+        const int ns = s_nsurv < kp ? s_nsurv : kp;   // == kp (composites are distinct and M > kp)
         for (int t = tid; t < ns; t += MERGE_THREADS) {
             const unsigned long long mine = surv[t];
-            int rank = 0;  // ties broken by slot, so ranks are a permutation even if composites repeat
-            for (int j = 0; j < ns; j++) rank += (surv[j] < mine || (surv[j] == mine && j < t)) ? 1 : 0;
+            int rank = 0;
+            for (int j = 0; j < ns; j++) rank += surv[j] < mine ? 1 : 0;
             sk[rank] = dec_key((uint32_t)(mine >> 32));
             si[rank] = (int32_t)(uint32_t)(mine & 0xffffffffu);
         }
-        nsorted = ns;
     }
     __syncthreads();
     // K4: exact fp32 re-rank of the k' best + certification + faiss-formatted output
-    const float tc = s_tc;
-    const int nc1 = nsorted < kp ? nsorted : kp;
+    const float tc = dec_key(s_tc_enc);
+    const int nc1 = M < kp ? M : kp;
     const float bound1 = (M > kp) ? fminf(sk[kp - 1], tc) : tc;
     bool cert = rerank_block(ra, q, sk, si, nc1, bound1, M < kp, ek, ei);
     if (!cert && ra.certify && M > kp && M <= RANK_MAX) {
@@ -1097,14 +1140,20 @@ int launch_merge_lists(const TensorScanLists& lists, int nq, const TensorScanPla
         set_error("merge: k' = %d / %d lists per query not supported", plan.kp, plan.nlists);
         return B2F_EINVAL;
     }
+    // composites staged in shared memory: the lists arrive pruned against the final threshold, which leaves
+    // about k' + (2..3) x lists entries per query; 4x that (at least RANK_MAX) keeps the CTA small enough for
+    // a whole batch to be resident at once.  A query with more entries is counted as an overflow (exact scan).
     int cap_entries = plan.nlists * plan.list_cap;
+    const int expect = 4 * (plan.kp + 3 * plan.nlists);
+    if (cap_entries > expect) cap_entries = expect;
+    if (cap_entries < k2::RANK_MAX) cap_entries = k2::RANK_MAX;
     if (cap_entries > k2::MERGE_MAX) cap_entries = k2::MERGE_MAX;
     const int cap_c = cap_entries > k2::RANK_MAX ? cap_entries : k2::RANK_MAX;
-    const size_t smem = (size_t)cap_c * 8 + (size_t)k2::KP_MAX * 8 + (size_t)k2::RANK_MAX * 8;
+    const size_t smem = (size_t)cap_c * 8 + (size_t)k2::KP_MAX * 8 + (size_t)k2::RANK_MAX * 8 + (size_t)cap_entries * 2;
     static bool configured = false;
     if (!configured) {
         B2F_CUDA(cudaFuncSetAttribute(k2::merge_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)((size_t)k2::MERGE_MAX * 8 + (size_t)k2::KP_MAX * 8 + (size_t)k2::RANK_MAX * 8)));
+                                      (int)((size_t)k2::MERGE_MAX * 10 + (size_t)k2::KP_MAX * 8 + (size_t)k2::RANK_MAX * 8)));
         configured = true;
     }
     k2::merge_lists_kernel<<<nq, k2::MERGE_THREADS, smem, st>>>(reinterpret_cast<const uint2*>(lists.cand), lists.counts, lists.final_thr,

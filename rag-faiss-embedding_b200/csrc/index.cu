@@ -49,6 +49,7 @@ struct b2f_index {
     bool stats_dirty = true;
     int32_t* host_flag = nullptr;     // mapped pinned memory [16]: counters of the latest finished tensor-path search + its seq
     int32_t seq = 0;
+    uint32_t scan_launches = 0;       // launch parity of the scan's cross-CTA bounds
     int32_t harvested_seq = 0;        // last seq whose counters were folded into the host-side statistics
     int slack_boost = 0;              // extra candidates per query, raised when too many queries fail certification
     unsigned long long* totals = nullptr;  // device [4]: fallback queries, overflowed queries, rescued queries (running totals)
@@ -270,6 +271,8 @@ int enqueue_scan(b2f_index* ix, const float* qd, const int32_t* qsel, const int3
     a.seq = seq;
     a.nq_batch = nq_batch;
     a.certify = certify;
+    a.tub = reinterpret_cast<uint32_t*>(ix->totals + 4);
+    a.parity = (int32_t)(ix->scan_launches++ & 1);
     B2F_TRY(launch_scan(a, st));
     ix->st.launches += 1;
     ix->st.last_launches += 1;
@@ -405,8 +408,9 @@ int b2f_index_create(int32_t d, int32_t metric, int32_t storage, int32_t device,
     if (e == cudaSuccess) e = cudaMemset(ix->stats, 0, 2 * sizeof(float));
     if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&ix->host_flag), 64, cudaHostAllocMapped | cudaHostAllocPortable);
     if (e == cudaSuccess) memset(ix->host_flag, 0, 64);
-    if (e == cudaSuccess) e = cudaMalloc(&ix->totals, 4 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&ix->totals, 4 * sizeof(unsigned long long) + kScanTubWords * 4);
     if (e == cudaSuccess) e = cudaMemset(ix->totals, 0, 4 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(ix->totals + 4, 0xff, kScanTubWords * 4);  // the scan's cross-CTA bounds, idle = all ones
     if (e != cudaSuccess) {
         set_error("index init failed: %s", cudaGetErrorString(e));
         delete ix;

@@ -29,6 +29,7 @@ namespace b2f {
 constexpr int kScanWarps = 8;
 constexpr int kScanThreads = kScanWarps * kWarp;
 constexpr int kRowsPerGroup = 4;
+constexpr int kGatherCap = 1024;   // survivors of the cross-CTA threshold ranked directly in shared memory
 
 template <typename RowT>
 struct RowVec;
@@ -81,6 +82,9 @@ scan_kernel(const RowT* __restrict__ rows, int64_t pitch, int64_t n, int d, int 
     float* sq = smem;                                                   // [NQ][dq]
     float* lk = sq + NQ * dq;                                           // [warps][NQ][k]
     int32_t* li = reinterpret_cast<int32_t*>(lk + kScanWarps * NQ * k);  // [warps][NQ][k]
+    // [kGatherCap] (key, id) composites of the final selection, 8-byte aligned behind the lists
+    unsigned long long* gath = reinterpret_cast<unsigned long long*>(smem + (((size_t)NQ * dq + 2 * (size_t)kScanWarps * NQ * k + 1) & ~(size_t)1));
+    __shared__ int s_m;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     cg::grid_group grid = cg::this_grid();
@@ -109,6 +113,8 @@ scan_kernel(const RowT* __restrict__ rows, int64_t pitch, int64_t n, int d, int 
             hf[4] = f.seq;
         }
     }
+    // re-arm the other launch parity's bounds (last used by the previous launch, next used by the next one)
+    if (blockIdx.x == 0 && threadIdx.x < 24) f.tub[(f.parity ^ 1) * 24 + threadIdx.x] = 0xffffffffu;
     const int nparts = (int)gridDim.x;
     const int nchunk = dq / VN;
     const int64_t ngroups = (n + R - 1) / R;
@@ -207,47 +213,98 @@ scan_kernel(const RowT* __restrict__ rows, int64_t pitch, int64_t n, int d, int 
     }
     __syncthreads();
     // in-CTA merge: warp w < NQ merges the 8 per-warp lists of query w into this CTA's partial list
-    // (double buffered over groups: the merge of group g may still be reading while group g+1 is written)
+    // (double buffered over groups: the selection of group g may still be reading while group g+1 is written)
     float* pk = f.pk + (size_t)(gi & 1) * NQ * nparts * k;
     int32_t* pi = f.pi + (size_t)(gi & 1) * NQ * nparts * k;
+    // Each CTA's k-th best is an upper bound of the query's global k-th best; the smallest of them (atomicMin
+    // on the order-preserving encoding) leaves only ~k + a few rows alive across all CTAs.  Three slots
+    // rotate over the groups: slot (gi+1)%3 was last read two groups ago and is re-armed here.
+    uint32_t* tub = f.tub + f.parity * 24 + (gi % 3) * 8;
+    if (gi >= 2 && blockIdx.x == 0 && threadIdx.x < 8) f.tub[f.parity * 24 + ((gi + 1) % 3) * 8 + threadIdx.x] = 0xffffffffu;
     if (warp < NQ && warp < nq_valid) {
         const int64_t o = ((int64_t)warp * nparts + blockIdx.x) * k;
         warp_merge_lists(lk + warp * k, li + warp * k, kScanWarps, k, (int64_t)NQ * k, k, pk + o, pi + o, lane);
+        __syncwarp();
+        if (lane == 0) atomicMin(tub + warp, enc_key(pk[o + k - 1]));  // FLT_MAX when this CTA saw fewer than k rows
     }
     grid.sync();
-    // one CTA per query: two-level merge of the nparts partial lists (32 lists per warp, then the <= 32
-    // intermediate lists), written straight to the caller's buffers in faiss conventions
+    // one CTA per query: gather the rows at or below the bound from all partial lists (sorted: stop at the
+    // first one above it), rank them directly, write the best k in faiss conventions
     for (int qi = blockIdx.x; qi < nq_valid; qi += nparts) {
         const float* qk = pk + (int64_t)qi * nparts * k;
         const int32_t* qid = pi + (int64_t)qi * nparts * k;
-        const int nl1 = (nparts + kWarp - 1) / kWarp;
-        float* mk = f.mk + (int64_t)qi * (kWarp + 1) * k;
-        int32_t* mi = f.mi + (int64_t)qi * (kWarp + 1) * k;
-        float* fk = mk + (int64_t)kWarp * k;   // final list
-        int32_t* fi = mi + (int64_t)kWarp * k;
-        if (nl1 == 1) {
-            if (warp == 0) warp_merge_lists(qk, qid, nparts, k, k, k, fk, fi, lane);
-        } else {
-            for (int g = warp; g < nl1; g += kScanWarps) {
-                const int first = g * kWarp;
-                const int cnt = nparts - first < kWarp ? nparts - first : kWarp;
-                warp_merge_lists(qk + (int64_t)first * k, qid + (int64_t)first * k, cnt, k, k, k, mk + (int64_t)g * k, mi + (int64_t)g * k, lane);
+        const int64_t orow = qsel ? qsel[g0 + qi] : g0 + qi;
+        const float T = dec_key(__ldcg(tub + qi));
+        if (threadIdx.x == 0) s_m = 0;
+        __syncthreads();
+        for (int l = threadIdx.x; l < nparts; l += kScanThreads) {
+            for (int j = 0; j < k; j++) {
+                const float key = __ldcg(qk + (int64_t)l * k + j);
+                const int32_t id = __ldcg(qid + (int64_t)l * k + j);
+                if (id < 0 || !(key <= T)) break;
+                const int slot = atomicAdd(&s_m, 1);
+                if (slot < kGatherCap) gath[slot] = ((unsigned long long)enc_key(key) << 32) | (uint32_t)id;
             }
-            __syncthreads();
-            if (warp == 0) warp_merge_lists(mk, mi, nl1, k, k, k, fk, fi, lane);
         }
         __syncthreads();
-        const int64_t orow = qsel ? qsel[g0 + qi] : g0 + qi;
-        for (int j = threadIdx.x; j < k; j += kScanThreads) {
-            const float key = fk[j];
-            const int32_t id = fi[j];
-            const int64_t o = orow * k + j;
-            if (id < 0) {
-                f.D[o] = L2 ? FLT_MAX : -FLT_MAX;
-                f.I[o] = -1;
+        const int M = s_m;
+        if (M <= kGatherCap) {
+            unsigned long long mine[kGatherCap / kScanThreads];
+            int rank[kGatherCap / kScanThreads];
+#pragma unroll
+            for (int u = 0; u < kGatherCap / kScanThreads; u++) {
+                const int i = threadIdx.x + u * kScanThreads;
+                mine[u] = i < M ? gath[i] : ~0ull;
+                rank[u] = 0;
+            }
+            for (int j = 0; j < M; j++) {
+                const unsigned long long o = gath[j];
+#pragma unroll
+                for (int u = 0; u < kGatherCap / kScanThreads; u++) rank[u] += o < mine[u] ? 1 : 0;  // composites are distinct (row ids)
+            }
+#pragma unroll
+            for (int u = 0; u < kGatherCap / kScanThreads; u++) {
+                if (threadIdx.x + u * kScanThreads < M && rank[u] < k) {
+                    const float key = dec_key((uint32_t)(mine[u] >> 32));
+                    const int64_t o = orow * k + rank[u];
+                    f.D[o] = L2 ? key : -key;
+                    f.I[o] = (int64_t)(uint32_t)(mine[u] & 0xffffffffu) + f.id_offset;
+                }
+            }
+            for (int j = M + threadIdx.x; j < k; j += kScanThreads) {  // fewer than k rows in the index
+                f.D[orow * k + j] = L2 ? FLT_MAX : -FLT_MAX;
+                f.I[orow * k + j] = -1;
+            }
+        } else {
+            // (ties / tiny shards with k close to the shard size) two-level merge of the sorted partial lists
+            const int nl1 = (nparts + kWarp - 1) / kWarp;
+            float* mk = f.mk + (int64_t)qi * (kWarp + 1) * k;
+            int32_t* mi = f.mi + (int64_t)qi * (kWarp + 1) * k;
+            float* fk = mk + (int64_t)kWarp * k;   // final list
+            int32_t* fi = mi + (int64_t)kWarp * k;
+            if (nl1 == 1) {
+                if (warp == 0) warp_merge_lists<true>(qk, qid, nparts, k, k, k, fk, fi, lane);
             } else {
-                f.D[o] = L2 ? key : -key;
-                f.I[o] = (int64_t)id + f.id_offset;
+                for (int g = warp; g < nl1; g += kScanWarps) {
+                    const int first = g * kWarp;
+                    const int cnt = nparts - first < kWarp ? nparts - first : kWarp;
+                    warp_merge_lists<true>(qk + (int64_t)first * k, qid + (int64_t)first * k, cnt, k, k, k, mk + (int64_t)g * k, mi + (int64_t)g * k, lane);
+                }
+                __syncthreads();
+                if (warp == 0) warp_merge_lists<true>(mk, mi, nl1, k, k, k, fk, fi, lane);
+            }
+            __syncthreads();
+            for (int j = threadIdx.x; j < k; j += kScanThreads) {
+                const float key = __ldcg(fk + j);
+                const int32_t id = __ldcg(fi + j);
+                const int64_t o = orow * k + j;
+                if (id < 0) {
+                    f.D[o] = L2 ? FLT_MAX : -FLT_MAX;
+                    f.I[o] = -1;
+                } else {
+                    f.D[o] = L2 ? key : -key;
+                    f.I[o] = (int64_t)id + f.id_offset;
+                }
             }
         }
         __syncthreads();
@@ -275,7 +332,7 @@ size_t scan_scratch_bytes(int k) {
 template <int NQ, bool L2, typename RowT, typename Vec>
 static int launch_one(const RowT* rows, int64_t pitch, const ScanArgs& a, cudaStream_t st) {
     const int dq = ((a.d + Vec::N - 1) / Vec::N) * Vec::N;
-    const size_t smem = (size_t)NQ * dq * 4 + (size_t)kScanWarps * NQ * a.k * 8;
+    const size_t smem = (((size_t)NQ * dq + 2 * (size_t)kScanWarps * NQ * a.k + 1) & ~(size_t)1) * 4 + (size_t)kGatherCap * 8;
     auto kern = scan_kernel<NQ, L2, RowT, Vec>;
     static size_t configured_smem = 0;
     if (configured_smem == 0 || smem > configured_smem) {
@@ -317,6 +374,8 @@ static int launch_one(const RowT* rows, int64_t pitch, const ScanArgs& a, cudaSt
     f.seq = a.seq;
     f.nq_batch = a.nq_batch;
     f.certify = a.certify;
+    f.tub = a.tub;
+    f.parity = a.parity;
     const RowT* rows_ = rows;
     int64_t pitch_ = pitch, n_ = a.n;
     int d_ = a.d, dq_ = dq, k_ = a.k;
