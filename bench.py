@@ -57,6 +57,10 @@ WORKLOADS = {
                       label="synthetic 10Mx768 flat inner-product (normalized), batch 4096, k=100 (BASELINE configs[2])"),
     "c4shard": dict(n=12_500_000, d=384, nq=4096, k=10, metric=1, normalize=False, storage="bf16",
                     label="synthetic 12.5Mx384 bf16 flat L2 per GPU (config 4 shard), 4096 queries, k=10"),
+    "c4shard_nq1": dict(n=12_500_000, d=384, nq=1, k=10, metric=1, normalize=False, storage="bf16",
+                        label="synthetic 12.5Mx384 bf16 flat L2 per GPU (config 4 shard), 1 query, k=10"),
+    "c4shard_nq32": dict(n=12_500_000, d=384, nq=32, k=10, metric=1, normalize=False, storage="bf16",
+                         label="synthetic 12.5Mx384 bf16 flat L2 per GPU (config 4 shard), 32 queries, k=10"),
 }
 SEED_DB, SEED_Q = 1234, 5678
 
@@ -237,7 +241,7 @@ def main():
     storage = b2f.STORE_BF16 if wl["storage"] == "bf16" else b2f.STORE_F32
 
     n, d, nq, k = wl["n"], wl["d"], wl["nq"], wl["k"]
-    shard_per_gpu = args.workload == "c4shard"
+    shard_per_gpu = args.workload.startswith("c4shard")
     if shard_per_gpu:   # per-GPU shard of config 4: every rank holds n rows, batch fixed
         lo, hi = rank * n, (rank + 1) * n
         n_global = n * world
@@ -353,7 +357,8 @@ def main():
                     "frac": round(ach / peaks["tf"], 4), "traffic": None}
         else:
             nlaunch = max(st["last_main_launches"], 1)
-            bytes_ = rows_local * dpad * elem + min(nq, 8 if used_algo == b2f.ALGO_SCAN else nq) * d * 4
+            passes = (nq + 7) // 8 if used_algo == b2f.ALGO_SCAN else 1   # the scan walks the queries in groups of <= 8
+            bytes_ = (rows_local * dpad * elem + min(nq, 8 if used_algo == b2f.ALGO_SCAN else nq) * d * 4) * passes
             ach = bytes_ / (kernel_ms * 1e-3) / 1e9
             roof = {"bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm"], "unit": "GB/s",
                     "frac": round(ach / peaks["hbm"], 4), "traffic": None, "launches_per_step": nlaunch}
@@ -381,7 +386,7 @@ def main():
                        "storage": wl["storage"], "algo": {1: "scan", 2: "tensor"}.get(used_algo, "?"),
                        "kprime": st["last_kprime"], "fallback_queries": st["fallback_queries"], "overflow_queries": st["overflow_queries"], "filter_survivors_per_query": round(st["last_list_entries"] / max(nq, 1), 1),
                        "l2_policy": "inputs larger than L2 (bf16 scan copy %.0f MB per GPU, L2 126 MB)" % (rows_local * dpad * 2 / 1e6),
-                       "sharding": ("rows in contiguous ranges over %d GPUs, batch %d = %d x N replicated; one NCCL all-gather + CUDA merge per step"
+                       "sharding": ("rows in contiguous ranges over %d GPUs, batch %d = %d x N replicated; one packed NCCL all-gather (12 nq k bytes per rank) + CUDA merge per step"
                                     % (world, nq, wl["nq"])) if world > 1 else "single GPU"},
             "roofline": roof,
             "e2e": {"value": round(nq / (e2e_ms * 1e-3), 1), "unit": "queries/sec", "ms_per_step": round(e2e_ms, 4),

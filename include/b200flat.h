@@ -150,6 +150,11 @@ B2F_API int b2f_index_read(const char* path, int32_t storage, int32_t device, b2
  * Keeps faiss ordering and -1 padding.  Device buffers only.                                    */
 B2F_API int b2f_merge_topk(int32_t metric, int64_t nq, int64_t k, int32_t nparts, const float* D_parts,
                    const int64_t* I_parts, float* D, int64_t* I, int32_t device, void* stream);
+/* Same merge over parts that are `part_stride_bytes` apart (D_parts / I_parts point at part 0): lets each rank
+ * ship its distances and labels in ONE packed all-gather message instead of two.                      */
+B2F_API int b2f_merge_topk_strided(int32_t metric, int64_t nq, int64_t k, int32_t nparts, const float* D_parts,
+                   const int64_t* I_parts, int64_t part_stride_bytes, float* D, int64_t* I, int32_t device,
+                   void* stream);
 
 /* ---- fused encoder epilogue (replaces vectorization.py:44-47, rag_datastore_manager.py:129-132:
  *      last_hidden_state[:,0].cpu().numpy() -> list -> np.array) ---------------------------------

@@ -220,9 +220,10 @@ int launch_merge_parts(const float* pk, const int32_t* pi, int nq, int nparts, i
 // qsel (optional) scatters row r of the input to output row qsel[r].
 int launch_finalize(const float* keys, const int32_t* ids, int nq, int kin, int k, int metric, int64_t id_offset,
                     const int32_t* qsel, float* D, int64_t* I, cudaStream_t st);
-// multi-GPU merge of [nparts][nq][k] faiss-formatted lists
-int launch_merge_faiss(int metric, int64_t nq, int64_t k, int nparts, const float* Dp, const int64_t* Ip, float* D,
-                       int64_t* I, cudaStream_t st);
+// multi-GPU merge of nparts faiss-formatted [nq][k] lists; part p of the distances / labels sits p * stride bytes
+// after part 0 (dense [nparts][nq][k] arrays, or one packed message per rank)
+int launch_merge_faiss(int metric, int64_t nq, int64_t k, int nparts, const float* Dp, const int64_t* Ip,
+                       int64_t stride_d_bytes, int64_t stride_i_bytes, float* D, int64_t* I, cudaStream_t st);
 
 // K5: ingest. src fp32 [n,d] (device) -> rows fp32 (optional), bf16 scan copy (pitch dpad), norms.
 // stats (device, 2 floats): running max |bf16(x)|^2 and max |x - bf16(x)|^2 (certification bound).

@@ -629,6 +629,17 @@ int b2f_synth_rows(uint64_t seed, int64_t row0, int64_t nrows, int32_t d, int32_
     return launch_synth(seed, row0, nrows, d, normalize, out, (cudaStream_t)stream);
 }
 
+int b2f_merge_topk_strided(int32_t metric, int64_t nq, int64_t k, int32_t nparts, const float* D_parts, const int64_t* I_parts,
+                           int64_t part_stride_bytes, float* D, int64_t* I, int32_t device, void* stream) {
+    if (nq < 0 || k <= 0 || !D_parts || !I_parts || !D || !I || part_stride_bytes <= 0 || (part_stride_bytes & 7)) {
+        set_error("merge_topk: bad arguments");
+        return B2F_EINVAL;
+    }
+    B2F_TRY(check_device(device));
+    DeviceGuard g(device);
+    return launch_merge_faiss(metric, nq, k, nparts, D_parts, I_parts, part_stride_bytes, part_stride_bytes, D, I, (cudaStream_t)stream);
+}
+
 int b2f_merge_topk(int32_t metric, int64_t nq, int64_t k, int32_t nparts, const float* D_parts, const int64_t* I_parts,
                    float* D, int64_t* I, int32_t device, void* stream) {
     if (nq < 0 || k <= 0 || !D_parts || !I_parts || !D || !I) {
@@ -637,7 +648,7 @@ int b2f_merge_topk(int32_t metric, int64_t nq, int64_t k, int32_t nparts, const 
     }
     B2F_TRY(check_device(device));
     DeviceGuard g(device);
-    return launch_merge_faiss(metric, nq, k, nparts, D_parts, I_parts, D, I, (cudaStream_t)stream);
+    return launch_merge_faiss(metric, nq, k, nparts, D_parts, I_parts, nq * k * 4, nq * k * 8, D, I, (cudaStream_t)stream);
 }
 
 // ---- search ----------------------------------------------------------------------------------------

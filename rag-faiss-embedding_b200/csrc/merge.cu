@@ -92,13 +92,14 @@ int launch_finalize(const float* keys, const int32_t* ids, int nq, int kin, int 
 // Dp/Ip: [nparts][nq][k] faiss-formatted per-shard results -> D/I [nq][k].  One warp per query,
 // lane l walks list l.  Ties go to the lower label, -1 padding loses to everything.
 __global__ void merge_faiss_kernel(int l2, int64_t nq, int k, int nparts, const float* __restrict__ Dp,
-                                   const int64_t* __restrict__ Ip, float* __restrict__ D, int64_t* __restrict__ I) {
+                                   const int64_t* __restrict__ Ip, int64_t stride_d_bytes, int64_t stride_i_bytes,
+                                   float* __restrict__ D, int64_t* __restrict__ I) {
     const int lane = threadIdx.x & 31;
     const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (q >= nq) return;
     const bool have = lane < nparts;
-    const float* dl = Dp + ((int64_t)lane * nq + q) * k;
-    const int64_t* il = Ip + ((int64_t)lane * nq + q) * k;
+    const float* dl = reinterpret_cast<const float*>(reinterpret_cast<const char*>(Dp) + (have ? lane : 0) * stride_d_bytes) + q * k;
+    const int64_t* il = reinterpret_cast<const int64_t*>(reinterpret_cast<const char*>(Ip) + (have ? lane : 0) * stride_i_bytes) + q * k;
     int pos = 0;
     float hk = FLT_MAX;
     int64_t hi = -1;
@@ -135,8 +136,8 @@ __global__ void merge_faiss_kernel(int l2, int64_t nq, int k, int nparts, const 
     }
 }
 
-int launch_merge_faiss(int metric, int64_t nq, int64_t k, int nparts, const float* Dp, const int64_t* Ip, float* D,
-                       int64_t* I, cudaStream_t st) {
+int launch_merge_faiss(int metric, int64_t nq, int64_t k, int nparts, const float* Dp, const int64_t* Ip,
+                       int64_t stride_d_bytes, int64_t stride_i_bytes, float* D, int64_t* I, cudaStream_t st) {
     if (nq <= 0 || k <= 0) return B2F_OK;
     if (nparts < 1 || nparts > kWarp) {
         set_error("merge_topk: nparts %d not in [1,32]", nparts);
@@ -144,7 +145,7 @@ int launch_merge_faiss(int metric, int64_t nq, int64_t k, int nparts, const floa
     }
     const int wpb = 4;
     merge_faiss_kernel<<<(unsigned)((nq + wpb - 1) / wpb), wpb * kWarp, 0, st>>>(metric == B2F_METRIC_L2, nq, (int)k,
-                                                                                nparts, Dp, Ip, D, I);
+                                                                                nparts, Dp, Ip, stride_d_bytes, stride_i_bytes, D, I);
     B2F_CUDA(cudaGetLastError());
     return B2F_OK;
 }

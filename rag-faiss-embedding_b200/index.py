@@ -196,6 +196,21 @@ class IndexFlat:
                                            C.MEM_HOST, None, ctypes.byref(p)))
         return D, I
 
+    def search_tensors_into(self, x, k: int, D, I, *, params: Optional[C.SearchParams] = None):
+        """Device-buffer search into caller-owned CUDA tensors D [n,k] float32 / I [n,k] int64 (contiguous); lets a
+        caller place both results inside one message buffer.  Enqueued on the current torch stream."""
+        import torch
+
+        _assert(k > 0, "k must be > 0")
+        _assert(x.is_cuda and x.dim() == 2 and x.shape[1] == self.d, f"dimension mismatch: got {tuple(x.shape)}, d={self.d}")
+        _assert(D.is_cuda and I.is_cuda and D.dtype == torch.float32 and I.dtype == torch.int64
+                and D.is_contiguous() and I.is_contiguous() and tuple(D.shape) == (x.shape[0], k) == tuple(I.shape),
+                "D / I must be contiguous CUDA tensors [n, k] of float32 / int64")
+        x = x.to(torch.float32).contiguous()
+        p = params if params is not None else self._params
+        C.check(self._lib.b2f_index_search(self._h, x.shape[0], x.data_ptr(), k, D.data_ptr(), I.data_ptr(),
+                                           C.MEM_DEVICE, _torch_stream(x), ctypes.byref(p)))
+
     def search_into(self, x: np.ndarray, k: int, D: np.ndarray, I: np.ndarray):
         """Host-buffer search into caller-owned (ideally pinned) arrays: the raw C-ABI call."""
         C.check(self._lib.b2f_index_search(self._h, x.shape[0], x.ctypes.data, k, D.ctypes.data, I.ctypes.data,

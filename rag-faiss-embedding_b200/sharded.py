@@ -148,8 +148,40 @@ class ShardedIndexFlat:
             return D, self.segments.to_global_numpy(I)
         return D, self.segments.to_global_torch(I)
 
+    def _search_packed(self, x, k: int):
+        """CUDA path of search(): every rank writes its (D, I) into ONE message buffer, one all-gather ships it
+        (12 * nq * k bytes per rank), the CUDA merge kernel reads the gathered messages in place."""
+        import torch
+
+        nq = int(x.shape[0])
+        off_i = (nq * k * 4 + 15) // 16 * 16
+        part = (off_i + nq * k * 8 + 15) // 16 * 16
+        send = torch.empty(part, dtype=torch.uint8, device=x.device)
+        D = send[: nq * k * 4].view(torch.float32).view(nq, k)
+        I = send[off_i: off_i + nq * k * 8].view(torch.int64).view(nq, k)
+        off = self.segments.single_offset()
+        if off is not None:
+            self.local.set_search_params(id_offset=off)
+            self.local.search_tensors_into(x, k, D, I)
+        else:
+            Dl, Il = self.local.search(x, k)
+            D.copy_(Dl)
+            I.copy_(self.segments.to_global_torch(Il))
+        recv = torch.empty(self.world * part, dtype=torch.uint8, device=x.device)
+        self._dist.all_gather_into_tensor(recv, send, group=self.group)   # the one exchange step of the path
+        Dm = torch.empty((nq, k), dtype=torch.float32, device=x.device)
+        Im = torch.empty((nq, k), dtype=torch.int64, device=x.device)
+        stream = int(torch.cuda.current_stream(x.device).cuda_stream) or 1  # 0x1 = cudaStreamLegacy
+        C.check(C.load().b2f_merge_topk_strided(int(self.metric_type), nq, k, self.world, recv.data_ptr(),
+                                                recv.data_ptr() + off_i, part, Dm.data_ptr(), Im.data_ptr(),
+                                                x.device.index or 0, ctypes.c_void_p(stream)))
+        return Dm, Im
+
     def search(self, x, k: int):
         """Replicated queries -> identical merged (D, I) on every rank."""
+        if (self.world > 1 and self._merge is merge_topk and hasattr(x, "is_cuda") and x.is_cuda
+                and hasattr(self.local, "search_tensors_into")):
+            return self._search_packed(x, k)
         D, I = self.search_local(x, k)
         if self.world == 1:
             return D, I
