@@ -78,50 +78,76 @@ def load_peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    """Samples SM clocks / throttle reasons during the timed regions: NVML every ~2 ms (nvidia-smi every
+    100 ms as the fallback when the NVML binding is missing)."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
+    NVML_BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
-        self.samples = []
+        self.sm, self.mx, self.reasons = [], [], set()
         self._stop = threading.Event()
         self._t = None
+        self.source = "nvidia-smi"
 
-    def _run(self):
+    def _run_nvml(self, nv, h):
+        mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.mx.append(mx)
+                bits = int(get_reasons(h))
+                for name, bit in self.NVML_BITS.items():
+                    if bits & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.002)
+
+    def _run_smi(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         while not self._stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}",
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
                 parts = [p.strip() for p in out.strip().split(",")]
                 if len(parts) >= 8:
-                    self.samples.append(parts)
+                    self.sm.append(float(parts[0]))
+                    self.mx.append(float(parts[1]))
+                    for name, val in zip(names, parts[4:8]):
+                        if val.lower().startswith("active"):
+                            self.reasons.add(name)
             except Exception:
                 pass
             self._stop.wait(0.1)
 
     def start(self):
-        self._t = threading.Thread(target=self._run, daemon=True)
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            # NVML enumerates physical devices: map through CUDA_VISIBLE_DEVICES when it lists plain indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            idx = self.gpu
+            if vis and all(t.strip().isdigit() for t in vis.split(",")):
+                idx = int(vis.split(",")[self.gpu])
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.source = "nvml"
+            self._t = threading.Thread(target=self._run_nvml, args=(nv, h), daemon=True)
+        except Exception:
+            self._t = threading.Thread(target=self._run_smi, daemon=True)
         self._t.start()
 
     def stop(self):
         self._stop.set()
         if self._t:
             self._t.join(timeout=6)
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
-            try:
-                sm.append(float(s[0]))
-                mx.append(float(s[1]))
-            except ValueError:
-                continue
-            for name, val in zip(names, s[4:8]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_min_mhz": min(self.sm) if self.sm else None,
+                "sm_max_mhz": max(self.mx) if self.mx else None, "reasons": sorted(self.reasons), "samples": len(self.sm),
+                "source": self.source}
 
 
 def cpu_baseline(wl, budget_s=20.0, threads=0):
@@ -171,7 +197,7 @@ def run_reference(args, wl, rank, world):
 
     n_cpu = min(wl["n"], 1_000_000)
     xb = orc.c_synth_rows(SEED_DB, 0, n_cpu, wl["d"], wl["normalize"])
-    nq_s = wl["nq"] if wl["nq"] < 20 else min(wl["nq"], 256)
+    nq_s = wl["nq"] if wl["nq"] < 20 else min(wl["nq"], 1024)   # one step = up to 1024 queries (~1 s of sgemm on 16 cores)
     xq = orc.c_synth_rows(SEED_Q, 0, nq_s, wl["d"], wl["normalize"])
 
     def step():

@@ -73,7 +73,8 @@ typedef struct b2f_index b2f_index;
 
 typedef struct b2f_search_params {
     int32_t algo;          /* B2F_ALGO_* */
-    int32_t scan_max_nq;   /* AUTO: largest nq served by the streaming scan (0 = default 1: the reference's nq) */
+    int32_t scan_max_nq;   /* AUTO: largest nq served by the streaming scan (0 = default: 1, the reference's nq,
+                              for fp32 storage; none for bf16 storage, where the tensor path is always faster) */
     int32_t slack;         /* tensor path: extra coarse candidates per query kept for the exact re-rank
                               (0 = default: k' = min(max(k + 22, 2k), cap)) */
     int32_t certify;       /* tensor path: 1 (default when 0 is passed via NULL params) = prove from the

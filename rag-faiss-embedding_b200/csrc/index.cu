@@ -689,7 +689,11 @@ int b2f_index_search(b2f_index* ix, int64_t nq64, const float* q, int64_t k64, f
     harvest_flag(ix);
 
     int algo = P.algo;
-    const int scan_max = P.scan_max_nq > 0 ? P.scan_max_nq : 1;
+    // AUTO: fp32 storage serves the reference's own batch size (nq = 1) with the fp32 streaming scan -- the
+    // reference's arithmetic, 90% of HBM on the fp32 rows.  bf16 storage has nothing to gain from it (both paths
+    // read the same bf16 rows; the tensor path streams them at the full HBM rate, the CUDA-core scan at half
+    // of it because of the unpacking), so every batch size goes to the tensor path there.
+    const int scan_max = P.scan_max_nq > 0 ? P.scan_max_nq : (ix->storage == B2F_STORE_BF16 ? 0 : 1);
     int kp = tensor_kprime(k, P.slack);
     if (kp > 0 && P.slack <= 0 && ix->slack_boost > 0) {  // adaptive slack learned from earlier searches on this index
         int boosted = ((kp + ix->slack_boost + 7) / 8) * 8;

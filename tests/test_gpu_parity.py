@@ -280,6 +280,11 @@ def test_bf16_storage(m, algo_name):
     ix.set_search_params(algo=m.ALGO_SCAN if algo_name == "scan" else m.ALGO_TENSOR)
     D, I = ix.search(xq, k)
     _check(D, I, *orc.np_search_f64(xb_r, xq, k, 1), 1)
+    # AUTO on bf16 storage: every batch size (the reference's nq = 1 included) goes to the tensor path
+    ix.set_search_params(algo=m.ALGO_AUTO)
+    D1, I1 = ix.search(xq[:1], k)
+    _check(D1, I1, *orc.np_search_f64(xb_r, xq[:1], k, 1), 1)
+    assert ix.stats()["last_algo"] == m.ALGO_TENSOR
 
 
 # ---- torch tensor handoff, pooling kernel, synthetic generator, merge kernel ---------------------------
