@@ -53,7 +53,8 @@ extern "C" {
 /* search algorithm selector (b2f_search_params.algo) */
 #define B2F_ALGO_AUTO 0   /* nq <= scan_max_nq -> streaming scan, else tensor path */
 #define B2F_ALGO_SCAN 1   /* K1: fp32 exact-difference streaming scan on CUDA cores (any nq, in groups) */
-#define B2F_ALGO_TENSOR 2 /* K2: tcgen05/TMEM bf16 contraction + fused top-k, then exact fp32 re-rank */
+#define B2F_ALGO_TENSOR 2 /* K2: tcgen05/TMEM bf16 contraction + fused top-k, then exact fp32 re-rank (shapes it cannot
+                             plan -- k' > 256, a few-row database -- are served by the scan; b2f_stats.last_algo tells) */
 
 /* pooling modes of the fused encoder epilogue */
 #define B2F_POOL_CLS 0  /* last_hidden_state[:, 0]  (the reference: vectorization.py:44) */

@@ -227,8 +227,12 @@ int launch_merge_faiss(int metric, int64_t nq, int64_t k, int nparts, const floa
 
 // K5: ingest. src fp32 [n,d] (device) -> rows fp32 (optional), bf16 scan copy (pitch dpad), norms.
 // stats (device, 2 floats): running max |bf16(x)|^2 and max |x - bf16(x)|^2 (certification bound).
+// mu (optional, device [d]): the scan copy / norms / stats are taken of the centred rows x - mu; ip_bias: store
+// -mu.x instead of |x~'|^2 in norms (inner-product indexes: the row's bias in the tensor pass).
 int launch_ingest(const float* src, int64_t n, int d, float* rows_f32, __nv_bfloat16* scan, int64_t dpad,
-                  float* norms, float* stats, cudaStream_t st);
+                  float* norms, float* stats, const float* mu, int ip_bias, cudaStream_t st);
+// mu[c] = mean of column c over the m rows of src
+int launch_mean_rows(const float* src, int64_t m, int d, float* mu, cudaStream_t st);
 // K7: pooling (+normalise) of encoder output, optionally fused with the ingest writes.
 int launch_pool(const float* hidden, const int64_t* mask, int64_t B, int64_t T, int d, int pool, int normalize,
                 float* out_f32, __nv_bfloat16* scan, int64_t dpad, float* norms, float* stats, cudaStream_t st);
@@ -238,7 +242,8 @@ int launch_synth(uint64_t seed, int64_t row0, int64_t nrows, int d, int normaliz
 // also clears `zero_words` 32-bit words at `zero` and fills `fill_words` words at `fill` with 0x7f7f7f7f
 // (the "no information yet" value of the shared thresholds), saving two memset launches per search
 int launch_prep_queries(const float* q, int nq, int nq_pad, int d, __nv_bfloat16* qb, int64_t dpad, float* qnorm,
-                        float* qerr, uint32_t* zero, int zero_words, uint32_t* fill, int64_t fill_words, cudaStream_t st);
+                        float* qerr, float* qconst, const float* mu, uint32_t* zero, int zero_words, uint32_t* fill,
+                        int64_t fill_words, cudaStream_t st);
 int launch_bf16_to_f32(const __nv_bfloat16* src, int64_t pitch, int64_t n, int d, float* dst, cudaStream_t st);
 
 // K4: exact fp32 re-rank of coarse candidates + certification.
@@ -248,7 +253,9 @@ struct RerankArgs {
     int64_t pitch_bf16;
     const float* q;                 // [nq, d] fp32
     const float* qnorm;             // |q|^2
-    const float* qerr;              // |q - bf16(q)|
+    const float* qerr;              // |q' - bf16(q')|   (q' = q - mu)
+    const float* qconst;            // q.mu - mu.mu (0 without centring): true inner product = centred one + mu.x + qconst
+    float mu_norm;                  // |mu|
     const float* cand_key;          // [nq, kp] coarse keys (sorted ascending)
     const int32_t* cand_id;         // [nq, kp]
     int nq, kp, k, d, metric;

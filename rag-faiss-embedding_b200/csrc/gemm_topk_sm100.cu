@@ -432,7 +432,7 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             for (int j = 0; j < BN / 32; j++) {
                 const int64_t row = row0 + j * 32 + lane;
                 float b = __int_as_float(0x7f800000);  // +inf: rows past the end never pass the threshold
-                if (row < n) b = L2 ? __ldg(norms + row) : 0.f;
+                if (row < n) b = __ldg(norms + row);  // L2: |x~'|^2; IP: -mu.x (0 without centring)
                 bias[acc * BN + j * 32 + lane] = b;
             }
             __syncwarp();

@@ -47,6 +47,9 @@ struct b2f_index {
     b2f_stats st{};
     float host_stats[2] = {0.f, 0.f};
     bool stats_dirty = true;
+    float* centre = nullptr;          // [d] device: centre of the scan copy (fp32 storage; see ingest_kernel), fixed at the first add
+    bool mu_set = false;
+    float mu_norm = 0.f;              // |mu| (host copy, refreshed with host_stats)
     int32_t* host_flag = nullptr;     // mapped pinned memory [16]: counters of the latest finished tensor-path search + its seq
     int32_t seq = 0;
     uint32_t scan_launches = 0;       // launch parity of the scan's cross-CTA bounds
@@ -224,7 +227,12 @@ cudaEvent_t get_event(b2f_index* ix, size_t i) {
 int refresh_host_stats(b2f_index* ix, cudaStream_t st) {
     if (!ix->stats_dirty) return B2F_OK;
     B2F_CUDA(cudaMemcpyAsync(ix->host_stats, ix->stats, 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    std::vector<float> m((size_t)ix->d, 0.f);
+    if (ix->mu_set) B2F_CUDA(cudaMemcpyAsync(m.data(), ix->centre, (size_t)ix->d * sizeof(float), cudaMemcpyDeviceToHost, st));
     B2F_CUDA(cudaStreamSynchronize(st));
+    double s2 = 0.0;
+    for (float v : m) s2 += (double)v * v;
+    ix->mu_norm = (float)(sqrt(s2) * (1.0 + 1e-6));
     ix->stats_dirty = false;
     return B2F_OK;
 }
@@ -342,15 +350,49 @@ int tensor_kprime(int k, int slack) {
     return kp <= 256 ? kp : 0;
 }
 
-// Largest query chunk (<= nq) the tensor path can take in one pass: big k' with a big batch leaves too few
-// database splits per query tile for the shared-threshold lists, so the batch is processed in chunks.
+// Query chunking of the tensor path.  Two reasons to process a batch in several passes:
+//  (1) feasibility -- big k' with a big batch leaves too few database splits per query tile for the shared-
+//      threshold lists;
+//  (2) balance -- units (CTAs / CTA pairs, one wave) are dealt over the query tiles, and the pass lasts as long
+//      as the tiles with the FEWEST splits: 4096 queries = 16 pair tiles over 74 pairs gives 4 or 5 splits, so
+//      every unit of a 4-split tile works through 1/4 of the database while the ideal share is 16/74 = 1/4.6.
+//      Two passes of 8 pair tiles (9 or 10 splits) cost 2/9 instead of 1/4: 11% less time for one more launch.
+// The planner evaluates 1..8 equal passes with a small cost model (tensor time of the slowest unit, floored by
+// the HBM time of one database pass, plus a fixed per-pass overhead) and returns the chunk size of the cheapest.
 int plan_tensor_chunked(int nq, int64_t n, int d, int kp, TensorScanPlan* plan) {
-    int chunk = nq;
+    int feasible = nq;
     while (true) {
-        if (plan_tensor_scan(chunk, n, d, kp, plan) == B2F_OK) return chunk;
-        if (chunk <= 128) return 0;
-        chunk = ((chunk / 2 + 127) / 128) * 128;
+        if (plan_tensor_scan(feasible, n, d, kp, plan) == B2F_OK) break;
+        if (feasible <= 128) return 0;
+        feasible = ((feasible / 2 + 127) / 128) * 128;
     }
+    const double dpad = (double)((d + 63) / 64 * 64);
+    const double kSmRate = 10.0e12, kHbm = 6.0e12, kPassOverhead = 20e-6;
+    const double t_hbm = (double)n * dpad * 2.0 / kHbm;
+    int best_chunk = feasible;
+    double best_cost = 1e30;
+    const char* nb = getenv("B200FLAT_NO_BALANCE");   // diagnostics: "1" = feasibility chunking only
+    const int max_m = (nb && nb[0] == '1') ? 1 : 8;
+    for (int m = 1; m <= max_m; m++) {
+        int chunk = (nq + m - 1) / m;
+        chunk = (chunk + 255) / 256 * 256;   // whole pair tiles
+        if (chunk > feasible) {
+            if (m == 1) chunk = feasible;
+            else continue;
+        }
+        if (chunk < 256 && m > 1) break;
+        TensorScanPlan p{};
+        if (plan_tensor_scan(chunk, n, d, kp, &p) != B2F_OK) continue;
+        const int passes = (nq + chunk - 1) / chunk;
+        const double t_mma = (double)n / p.nsplits * 128.0 * dpad * 2.0 / kSmRate;  // slowest unit, per SM
+        const double cost = passes * ((t_mma > t_hbm ? t_mma : t_hbm) + kPassOverhead);
+        if (cost < best_cost * 0.97) {  // a new pass has to buy at least 3%
+            best_cost = cost;
+            best_chunk = chunk;
+        }
+    }
+    if (plan_tensor_scan(best_chunk, n, d, kp, plan) != B2F_OK) return 0;
+    return best_chunk;
 }
 
 }  // namespace
@@ -406,6 +448,8 @@ int b2f_index_create(int32_t d, int32_t metric, int32_t storage, int32_t device,
     cudaError_t e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc(&ix->stats, 2 * sizeof(float));
     if (e == cudaSuccess) e = cudaMemset(ix->stats, 0, 2 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&ix->centre, (size_t)d * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemset(ix->centre, 0, (size_t)d * sizeof(float));
     if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&ix->host_flag), 64, cudaHostAllocMapped | cudaHostAllocPortable);
     if (e == cudaSuccess) memset(ix->host_flag, 0, 64);
     if (e == cudaSuccess) e = cudaMalloc(&ix->totals, 4 * sizeof(unsigned long long) + kScanTubWords * 4);
@@ -428,6 +472,7 @@ int b2f_index_destroy(b2f_index* ix) {
     cudaFree(ix->scan);
     cudaFree(ix->norms);
     cudaFree(ix->stats);
+    cudaFree(ix->centre);
     cudaFree(ix->ws);
     if (ix->pinned) cudaFreeHost(ix->pinned);
     if (ix->host_flag) cudaFreeHost(ix->host_flag);
@@ -452,6 +497,7 @@ int b2f_index_reset(b2f_index* ix) {
     std::lock_guard<std::mutex> lk(ix->mu);
     DeviceGuard g(ix->device);
     ix->ntotal = 0;
+    ix->mu_set = false;
     if (ix->search_recorded) B2F_CUDA(cudaEventSynchronize(ix->ev_done));
     B2F_CUDA(cudaMemsetAsync(ix->stats, 0, 2 * sizeof(float), ix->stream));
     B2F_CUDA(cudaStreamSynchronize(ix->stream));
@@ -500,15 +546,33 @@ int b2f_index_stats(const b2f_index* cix, b2f_stats* out) {
 }
 
 // ---- add -------------------------------------------------------------------------------------------
+static bool centring_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("B200FLAT_NO_CENTER");
+        v = (e && e[0] == '1') ? 0 : 1;
+    }
+    return v == 1;
+}
+
 static int add_device_rows(b2f_index* ix, const float* src_dev, int64_t n, cudaStream_t st) {
     // src_dev: [n, d] fp32 on the device (may alias the tail of rows_f32)
     float* rows_out = nullptr;
     if (ix->storage == B2F_STORE_F32) {
         float* dst = ix->rows_f32 + ix->ntotal * ix->d;
         if (src_dev != dst) rows_out = dst;
+        // The scan copy is taken around the mean of the first rows the index sees (at most 65536), fixed from then
+        // on: any centre is correct, a representative one makes the bf16 pass far more decisive on embeddings
+        // that share a large common component.  (bf16 storage keeps mu = 0: there the scan copy IS the data.)
+        if (!ix->mu_set && ix->ntotal == 0 && centring_enabled()) {
+            B2F_TRY(launch_mean_rows(src_dev, n < 65536 ? n : 65536, ix->d, ix->centre, st));
+            ix->mu_set = true;
+            ix->st.launches++;
+        }
     }
     B2F_TRY(launch_ingest(src_dev, n, ix->d, rows_out, ix->scan + ix->ntotal * ix->dpad, ix->dpad,
-                          ix->norms + ix->ntotal, ix->stats, st));
+                          ix->norms + ix->ntotal, ix->stats, ix->mu_set ? ix->centre : nullptr,
+                          ix->metric == B2F_METRIC_INNER_PRODUCT ? 1 : 0, st));
     ix->st.launches++;
     return B2F_OK;
 }
@@ -598,10 +662,18 @@ int b2f_index_add_pooled(b2f_index* ix, const float* hidden, const int64_t* mask
     B2F_TRY(ensure_capacity(ix, ix->ntotal + B));
     cudaStream_t st = stream ? (cudaStream_t)stream : ix->stream;
     if (ix->search_recorded && ix->last_stream != st) B2F_CUDA(cudaStreamWaitEvent(st, ix->ev_done, 0));
-    float* rows_out = ix->storage == B2F_STORE_F32 ? ix->rows_f32 + ix->ntotal * ix->d : nullptr;
-    B2F_TRY(launch_pool(hidden, mask, B, T, ix->d, pool, normalize, rows_out, ix->scan + ix->ntotal * ix->dpad, ix->dpad,
-                        ix->norms + ix->ntotal, ix->stats, st));
-    ix->st.launches++;
+    if (ix->storage == B2F_STORE_F32) {
+        // pooled rows land in their final place; the derived data (centred bf16 copy, norms / biases, stats) comes
+        // from the same ingest kernel every other add uses (it needs the index's centre, fixed at the first add)
+        float* dst = ix->rows_f32 + ix->ntotal * ix->d;
+        B2F_TRY(launch_pool(hidden, mask, B, T, ix->d, pool, normalize, dst, nullptr, 0, nullptr, nullptr, st));
+        ix->st.launches++;
+        B2F_TRY(add_device_rows(ix, dst, B, st));
+    } else {
+        B2F_TRY(launch_pool(hidden, mask, B, T, ix->d, pool, normalize, nullptr, ix->scan + ix->ntotal * ix->dpad, ix->dpad,
+                            ix->norms + ix->ntotal, ix->stats, st));
+        ix->st.launches++;
+    }
     ix->ntotal += B;
     ix->stats_dirty = true;
     return B2F_OK;
@@ -703,10 +775,9 @@ int b2f_index_search(b2f_index* ix, int64_t nq64, const float* q, int64_t k64, f
     const int chunk_nq = (kp > 0 && ix->ntotal > 0) ? plan_tensor_chunked(nq, ix->ntotal, ix->d, kp, &plan) : 0;
     const bool tensor_ok = chunk_nq > 0;
     if (algo == B2F_ALGO_AUTO) algo = (nq <= scan_max || !tensor_ok) ? B2F_ALGO_SCAN : B2F_ALGO_TENSOR;
-    if (algo == B2F_ALGO_TENSOR && !tensor_ok && ix->ntotal > 0) {
-        set_error("tensor path unavailable for k=%d (k' = %d) on this shape", k, kp);
-        return B2F_EINVAL;
-    }
+    // an explicit TENSOR request on a shape the tensor path cannot plan (k' > 256, or a database of a few rows with
+    // k' other than 32 / 64) is served by the exact scan, like AUTO would; stats().last_algo tells
+    if (algo == B2F_ALGO_TENSOR && !tensor_ok) algo = B2F_ALGO_SCAN;
     const int certify = P.certify >= 0 ? 1 : 0;
 
     // ---- workspace -----------------------------------------------------------------------------
@@ -715,7 +786,7 @@ int b2f_index_search(b2f_index* ix, int64_t nq64, const float* q, int64_t k64, f
     need += align_up(scan_scratch_bytes(k), 256) + 256;
     if (algo == B2F_ALGO_TENSOR) {
         const size_t nq_pad = (size_t)plan.nq_tiles * 128;
-        need += align_up(nq_pad * ix->dpad * 2, 256) + 2 * align_up(nq_pad * 4, 256);
+        need += align_up(nq_pad * ix->dpad * 2, 256) + 3 * align_up(nq_pad * 4, 256);
         if (plan.list_mode) {
             need += align_up(nq_pad * plan.nlists * 4, 256) * 3;                       // shared thresholds + counts + final thresholds
             need += align_up(nq_pad * plan.nlists * (size_t)plan.list_cap * 8, 256);   // candidate lists
@@ -779,6 +850,7 @@ int b2f_index_search(b2f_index* ix, int64_t nq64, const float* q, int64_t k64, f
         __nv_bfloat16* qb = bump.take<__nv_bfloat16>((size_t)nq_pad * ix->dpad);
         float* qnorm = bump.take<float>(nq_pad);
         float* qerr = bump.take<float>(nq_pad);
+        float* qconst = bump.take<float>(nq_pad);
         float* pk = nullptr;
         int32_t* pi = nullptr;
         float* ck = nullptr;
@@ -803,7 +875,8 @@ int b2f_index_search(b2f_index* ix, int64_t nq64, const float* q, int64_t k64, f
             const int cn = nq - c0 < chunk_nq ? nq - c0 : chunk_nq;  // queries in this pass (the plan covers chunk_nq)
             const float* qc = qd + (int64_t)c0 * ix->d;
             // one launch: bf16 copy / norms of the queries, reset the shared thresholds, clear the counters (first pass)
-            B2F_TRY(launch_prep_queries(qc, cn, nq_pad, ix->d, qb, ix->dpad, qnorm, qerr, reinterpret_cast<uint32_t*>(counters),
+            B2F_TRY(launch_prep_queries(qc, cn, nq_pad, ix->d, qb, ix->dpad, qnorm, qerr, qconst, ix->mu_set ? ix->centre : nullptr,
+                                        reinterpret_cast<uint32_t*>(counters),
                                         c0 == 0 ? 8 : 0, reinterpret_cast<uint32_t*>(lists.shared_thr),
                                         plan.list_mode ? (int64_t)nq_pad * plan.nlists : 0, st));
             B2F_TRY(main_event(0));
@@ -817,6 +890,8 @@ int b2f_index_search(b2f_index* ix, int64_t nq64, const float* q, int64_t k64, f
             ra.q = qc;
             ra.qnorm = qnorm;
             ra.qerr = qerr;
+            ra.qconst = qconst;
+            ra.mu_norm = ix->mu_norm;
             ra.cand_key = ck;
             ra.cand_id = ci;
             ra.nq = cn;

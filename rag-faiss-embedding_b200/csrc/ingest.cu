@@ -19,28 +19,63 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // Writes one element group of a row to every derived store and returns (bf16(x)^2, (x-bf16(x))^2).
 __device__ __forceinline__ void emit_elem(float x, int64_t row, int col, int d, float* rows_f32,
-                                          __nv_bfloat16* scan, int64_t dpad, float& nn, float& ee) {
+                                          __nv_bfloat16* scan, int64_t dpad, float& nn, float& ee, float m = 0.f) {
     if (rows_f32) rows_f32[row * d + col] = x;
-    const __nv_bfloat16 b = __float2bfloat16_rn(x);
+    const float xc = x - m;  // the scan copy holds the CENTRED row (see ingest_kernel)
+    const __nv_bfloat16 b = __float2bfloat16_rn(xc);
     const float xb = __bfloat162float(b);
     if (scan) scan[row * dpad + col] = b;
     nn = fmaf(xb, xb, nn);
-    const float e = x - xb;
+    const float e = xc - xb;
     ee = fmaf(e, e, ee);
 }
 
-// stats[0] = max |bf16(x)|^2, stats[1] = max |x - bf16(x)|^2 over every row ever ingested
+// mu[c] += (1/m) * sum of column c over rows [0, m): the centre the scan copy is taken around.
+__global__ void __launch_bounds__(256) mean_rows_kernel(const float* __restrict__ src, int64_t m, int d, float* __restrict__ mu) {
+    const int64_t r0 = (int64_t)blockIdx.x * 64, r1 = r0 + 64 < m ? r0 + 64 : m;
+    const float inv = 1.f / (float)m;
+    for (int c = threadIdx.x; c < d; c += blockDim.x) {
+        float a = 0.f;
+        for (int64_t r = r0; r < r1; r++) a += src[r * d + c];
+        atomicAdd(mu + c, a * inv);
+    }
+}
+
+int launch_mean_rows(const float* src, int64_t m, int d, float* mu, cudaStream_t st) {
+    if (m <= 0) return B2F_OK;
+    B2F_CUDA(cudaMemsetAsync(mu, 0, (size_t)d * 4, st));
+    mean_rows_kernel<<<(unsigned)((m + 63) / 64), 256, 0, st>>>(src, m, d, mu);
+    B2F_CUDA(cudaGetLastError());
+    return B2F_OK;
+}
+
+// Centring.  With mu given, the scan copy is x~' = bf16(x - mu): distances are translation invariant
+// (|q - x| = |(q - mu) - (x - mu)|), inner products split as q.x = (q - mu).(x - mu) + mu.x + (q.mu - mu.mu), so the
+// tensor pass works on the centred vectors and the row term mu.x rides along as the per-row bias (L2: |x~'|^2,
+// IP: -mu.x).  Embeddings share a large common component (the reference's own index: |x| ~ 7.7 with relative
+// neighbour gaps of 1e-4; a random-init encoder: all cosines > 0.95), and bf16 rounding error scales with the
+// magnitude of what is rounded: centred, the certification bound is 5-30x tighter on such data.
+// stats[0] = max |x~'|^2, stats[1] = max |x' - x~'|^2 over every row ever ingested
 __global__ void __launch_bounds__(256)
 ingest_kernel(const float* __restrict__ src, int64_t n, int d, float* __restrict__ rows_f32,
-              __nv_bfloat16* __restrict__ scan, int64_t dpad, float* __restrict__ norms, float* __restrict__ stats) {
+              __nv_bfloat16* __restrict__ scan, int64_t dpad, float* __restrict__ norms, float* __restrict__ stats,
+              const float* __restrict__ mu, int ip_bias) {
     const int lane = threadIdx.x & 31;
     const int64_t wpg = (int64_t)gridDim.x * (blockDim.x >> 5);
+    // running maxima of the warp's rows: ONE atomic pair per warp at the end (two atomics per row on the same
+    // two addresses serialised the whole kernel: 2.8 ms for 1M rows, 21% of HBM)
+    float max_nn = 0.f, max_ee = 0.f;
     for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < n; row += wpg) {
-        float nn = 0.f, ee = 0.f;
+        float nn = 0.f, ee = 0.f, mx = 0.f;
         if ((d & 3) == 0) {
             for (int c = lane * 4; c < d; c += 128) {
-                const float4 x = ldg_stream(reinterpret_cast<const float4*>(src + row * d + c));
+                float4 x = ldg_stream(reinterpret_cast<const float4*>(src + row * d + c));
                 if (rows_f32) *reinterpret_cast<float4*>(rows_f32 + row * d + c) = x;
+                if (mu) {
+                    const float4 m4 = __ldg(reinterpret_cast<const float4*>(mu + c));
+                    mx = fmaf(m4.x, x.x, mx); mx = fmaf(m4.y, x.y, mx); mx = fmaf(m4.z, x.z, mx); mx = fmaf(m4.w, x.w, mx);
+                    x.x -= m4.x; x.y -= m4.y; x.z -= m4.z; x.w -= m4.w;
+                }
                 const __nv_bfloat162 lo = __floats2bfloat162_rn(x.x, x.y), hi = __floats2bfloat162_rn(x.z, x.w);
                 if (scan) {
                     uint2 pk;
@@ -54,29 +89,34 @@ ingest_kernel(const float* __restrict__ src, int64_t n, int d, float* __restrict
                 ee = fmaf(e0, e0, ee); ee = fmaf(e1, e1, ee); ee = fmaf(e2, e2, ee); ee = fmaf(e3, e3, ee);
             }
         } else {
-            for (int c = lane; c < d; c += 32) emit_elem(src[row * d + c], row, c, d, rows_f32, scan, dpad, nn, ee);
+            for (int c = lane; c < d; c += 32) {
+                const float x = src[row * d + c], m = mu ? mu[c] : 0.f;
+                mx = fmaf(m, x, mx);
+                emit_elem(x, row, c, d, rows_f32, scan, dpad, nn, ee, m);
+            }
         }
         if (scan)
             for (int c = d + lane; c < dpad; c += 32) scan[row * dpad + c] = __float2bfloat16_rn(0.f);
         nn = warp_sum(nn);
         ee = warp_sum(ee);
-        if (lane == 0) {
-            if (norms) norms[row] = nn;
-            if (stats) {
-                atomic_max_nonneg(stats, nn);
-                atomic_max_nonneg(stats + 1, ee);
-            }
-        }
+        if (ip_bias) mx = warp_sum(mx);
+        if (lane == 0 && norms) norms[row] = ip_bias ? -mx : nn;   // the row's bias in the tensor pass
+        max_nn = fmaxf(max_nn, nn);
+        max_ee = fmaxf(max_ee, ee);
+    }
+    if (lane == 0 && stats) {
+        atomic_max_nonneg(stats, max_nn);
+        atomic_max_nonneg(stats + 1, max_ee);
     }
 }
 
 int launch_ingest(const float* src, int64_t n, int d, float* rows_f32, __nv_bfloat16* scan, int64_t dpad, float* norms,
-                  float* stats, cudaStream_t st) {
+                  float* stats, const float* mu, int ip_bias, cudaStream_t st) {
     if (n <= 0) return B2F_OK;
     const int wpb = 8;
     int64_t blocks = (n + wpb - 1) / wpb;
     if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-    ingest_kernel<<<(unsigned)blocks, wpb * 32, 0, st>>>(src, n, d, rows_f32, scan, dpad, norms, stats);
+    ingest_kernel<<<(unsigned)blocks, wpb * 32, 0, st>>>(src, n, d, rows_f32, scan, dpad, norms, stats, mu, ip_bias);
     B2F_CUDA(cudaGetLastError());
     return B2F_OK;
 }
@@ -100,20 +140,56 @@ pool_kernel(const float* __restrict__ hidden, const int64_t* __restrict__ mask, 
         cnt = fmaxf(c, 1e-9f);
     }
     float ss = 0.f;
-    for (int c = threadIdx.x; c < d; c += blockDim.x) {
-        float v;
-        if (pool == B2F_POOL_CLS) {
-            v = h[c];
-        } else {
-            float acc = 0.f;
-            for (int64_t t = 0; t < T; t++) {
-                const float m = mask ? (float)mask[b * T + t] : 1.f;
-                if (m != 0.f) acc = fmaf(m, h[t * d + c], acc);
+    if (pool == B2F_POOL_MEAN && (d & 3) == 0 && d / 4 <= (int)blockDim.x) {
+        // 16-byte loads: a thread owns one group of four columns and every nth-th token (d = 384: 96 column
+        // groups x 2 token phases), four tokens in flight; the partial sums of the phases meet in shared
+        // memory (psum [nth][d] behind srow).  Masked-out tokens are skipped, as in the scalar path.
+        float* psum = srow + d;
+        const int ncg = d / 4, nth = (int)blockDim.x / ncg;
+        const int cg = (int)threadIdx.x % ncg, th = (int)threadIdx.x / ncg;
+        if (th < nth) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int64_t t0 = th; t0 < T; t0 += 4 * nth) {
+                float4 v[4];
+                float mk[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int64_t t = t0 + (int64_t)u * nth;
+                    mk[u] = t < T ? (mask ? (float)mask[b * T + t] : 1.f) : 0.f;
+                    v[u] = mk[u] != 0.f ? ldg_stream(reinterpret_cast<const float4*>(h + t * d + cg * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    acc.x = fmaf(mk[u], v[u].x, acc.x); acc.y = fmaf(mk[u], v[u].y, acc.y);
+                    acc.z = fmaf(mk[u], v[u].z, acc.z); acc.w = fmaf(mk[u], v[u].w, acc.w);
+                }
             }
-            v = acc / cnt;
+            *reinterpret_cast<float4*>(psum + th * d + cg * 4) = acc;
         }
-        srow[c] = v;
-        ss = fmaf(v, v, ss);
+        __syncthreads();
+        for (int c = threadIdx.x; c < d; c += blockDim.x) {
+            float a = 0.f;
+            for (int p2 = 0; p2 < nth; p2++) a += psum[p2 * d + c];
+            const float v = a / cnt;
+            srow[c] = v;
+            ss = fmaf(v, v, ss);
+        }
+    } else {
+        for (int c = threadIdx.x; c < d; c += blockDim.x) {
+            float v;
+            if (pool == B2F_POOL_CLS) {
+                v = h[c];
+            } else {
+                float acc = 0.f;
+                for (int64_t t = 0; t < T; t++) {
+                    const float m = mask ? (float)mask[b * T + t] : 1.f;
+                    if (m != 0.f) acc = fmaf(m, h[t * d + c], acc);
+                }
+                v = acc / cnt;
+            }
+            srow[c] = v;
+            ss = fmaf(v, v, ss);
+        }
     }
     ss = warp_sum(ss);
     if ((threadIdx.x & 31) == 0) red[0][threadIdx.x >> 5] = ss;
@@ -154,7 +230,15 @@ int launch_pool(const float* hidden, const int64_t* mask, int64_t B, int64_t T, 
         set_error("pool: d=%d too large", d);
         return B2F_EINVAL;
     }
-    pool_kernel<<<(unsigned)B, 256, (size_t)d * 4, st>>>(hidden, mask, T, d, pool, normalize, out_f32, scan, dpad, norms, stats);
+    // srow [d] + the mean path's partial sums [256 / (d/4)][d]
+    const int nth = (d % 4 == 0 && d / 4 <= 256) ? 256 / (d / 4) : 0;
+    const size_t smem = (size_t)d * 4 * (1 + (pool == B2F_POOL_MEAN ? nth : 0));
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        B2F_CUDA(cudaFuncSetAttribute(pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        configured = 160 * 1024;
+    }
+    pool_kernel<<<(unsigned)B, 256, smem, st>>>(hidden, mask, T, d, pool, normalize, out_f32, scan, dpad, norms, stats);
     B2F_CUDA(cudaGetLastError());
     return B2F_OK;
 }
@@ -214,11 +298,12 @@ int launch_synth(uint64_t seed, int64_t row0, int64_t nrows, int d, int normaliz
 }
 
 // ---- query preparation for the tensor path -------------------------------------------------------
-// qb: [nq_pad, dpad] bf16 (zero padded), qnorm[r] = |bf16(q_r)|^2, qerr[r] = |q_r - bf16(q_r)|
+// q' = q - mu (mu may be null); qb: [nq_pad, dpad] bf16(q') (zero padded), qnorm[r] = |bf16(q'_r)|^2,
+// qerr[r] = |q'_r - bf16(q'_r)|, qconst[r] = q_r.mu - mu.mu (turns centred inner products back into true ones)
 __global__ void __launch_bounds__(256)
 prep_queries_kernel(const float* __restrict__ q, int nq, int nq_pad, int d, __nv_bfloat16* __restrict__ qb, int64_t dpad,
-                    float* __restrict__ qnorm, float* __restrict__ qerr, uint32_t* __restrict__ zero, int zero_words,
-                    uint32_t* __restrict__ fill, int64_t fill_words) {
+                    float* __restrict__ qnorm, float* __restrict__ qerr, float* __restrict__ qconst, const float* __restrict__ mu,
+                    uint32_t* __restrict__ zero, int zero_words, uint32_t* __restrict__ fill, int64_t fill_words) {
     {
         const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gn = (int64_t)gridDim.x * blockDim.x;
         for (int64_t i = gt; i < zero_words; i += gn) zero[i] = 0u;
@@ -227,28 +312,35 @@ prep_queries_kernel(const float* __restrict__ q, int nq, int nq_pad, int d, __nv
     const int lane = threadIdx.x & 31;
     const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (r >= nq_pad) return;
-    float nn = 0.f, ee = 0.f;
+    float nn = 0.f, ee = 0.f, qc = 0.f;
     for (int c = lane; c < dpad; c += 32) {
-        float x = (r < nq && c < d) ? q[(int64_t)r * d + c] : 0.f;
+        const bool in = r < nq && c < d;
+        const float m = (mu && in) ? mu[c] : 0.f;
+        const float x0 = in ? q[(int64_t)r * d + c] : 0.f;
+        const float x = x0 - m;
         const __nv_bfloat16 b = __float2bfloat16_rn(x);
         const float xb = __bfloat162float(b);
         qb[(int64_t)r * dpad + c] = b;
         nn = fmaf(xb, xb, nn);
         ee = fmaf(x - xb, x - xb, ee);
+        qc = fmaf(m, x, qc);   // (q - mu).mu = q.mu - mu.mu
     }
     nn = warp_sum(nn);
     ee = warp_sum(ee);
+    qc = warp_sum(qc);
     if (lane == 0 && r < nq) {
         qnorm[r] = nn;
         qerr[r] = sqrtf(ee);
+        qconst[r] = qc;
     }
 }
 
 int launch_prep_queries(const float* q, int nq, int nq_pad, int d, __nv_bfloat16* qb, int64_t dpad, float* qnorm,
-                        float* qerr, uint32_t* zero, int zero_words, uint32_t* fill, int64_t fill_words, cudaStream_t st) {
+                        float* qerr, float* qconst, const float* mu, uint32_t* zero, int zero_words, uint32_t* fill,
+                        int64_t fill_words, cudaStream_t st) {
     if (nq_pad <= 0) return B2F_OK;
-    prep_queries_kernel<<<(nq_pad + 7) / 8, 256, 0, st>>>(q, nq, nq_pad, d, qb, dpad, qnorm, qerr, zero, zero_words, fill,
-                                                          fill_words);
+    prep_queries_kernel<<<(nq_pad + 7) / 8, 256, 0, st>>>(q, nq, nq_pad, d, qb, dpad, qnorm, qerr, qconst, mu, zero, zero_words,
+                                                          fill, fill_words);
     B2F_CUDA(cudaGetLastError());
     return B2F_OK;
 }

@@ -169,9 +169,13 @@ __device__ __forceinline__ bool rerank_block(const RerankArgs& a, int q, const f
                 const float L = sqrtf(fmaxf(c, 0.f)) - eq - a.max_row_err;
                 certified = L > 0.f && L * L * (1.f - 4e-7f) > tau;
             } else {
-                // keys are negated inner products: non-candidates have <q,x> <= -bound + slack
-                const float nu = gam * qn * a.max_row_norm;
-                const float U = -bound + nu + (qn + eq) * a.max_row_err + a.max_row_norm * eq;
+                // keys are negated (centred inner product + mu.x): <q,x> = -key + qconst + rounding terms, so
+                // non-candidates have <q,x> <= -bound + qconst + slack.  The fp32 sums mu.x and q.mu carry their own
+                // accumulation error (|mu| (|x| + |q|) gamma).
+                const float cq = a.qconst ? a.qconst[q] : 0.f;
+                const float xmax = a.max_row_norm + a.max_row_err + a.mu_norm;   // >= |x| of any row
+                const float nu = gam * (qn * a.max_row_norm + a.mu_norm * (xmax + qn + eq + a.mu_norm));
+                const float U = -bound + cq + nu + (qn + eq) * a.max_row_err + a.max_row_norm * eq;
                 certified = U < -tau;
             }
         }

@@ -228,6 +228,94 @@ def test_tensor_list_overflow_falls_back(m):
     assert ix.stats()["fallback_queries"] > 0
 
 
+def test_random_shapes_both_paths(m):
+    """Seeded sweep over ragged shapes (d not a multiple of 8 / 64, n around tile boundaries, k from 1 to 100,
+    batches around the 128-query tile), three data distributions (N(0,1); mean-shifted fixture-like rows with
+    tiny relative gaps; heavy duplicates = exact-distance ties), L2 and IP, both GPU paths against the oracle."""
+    rng = np.random.default_rng(2024)
+    for case in range(18):
+        d = int(rng.choice([1, 7, 30, 64, 100, 128, 250, 384, 520]))
+        n = int(rng.choice([1, 33, 255, 256, 257, 1000, 4099, 20000, 70001]))
+        nq = int(rng.choice([1, 2, 9, 31, 127, 128, 129, 300]))
+        k = int(rng.choice([1, 3, 10, 37, 100]))
+        metric = int(rng.integers(0, 2))
+        kind = case % 3
+        if kind == 0:
+            xb = rng.standard_normal((n, d)).astype(np.float32)
+            xq = rng.standard_normal((nq, d)).astype(np.float32)
+        elif kind == 1:
+            xb = (rng.standard_normal((n, d)) * 0.2 + 0.4).astype(np.float32)
+            xq = (rng.standard_normal((nq, d)) * 0.2 + 0.4).astype(np.float32)
+        else:
+            base = rng.standard_normal((max(n // 7, 1), d)).astype(np.float32)
+            xb = base[rng.integers(0, base.shape[0], n)]
+            xq = base[rng.integers(0, base.shape[0], nq)] + (rng.standard_normal((nq, d)) * 1e-3).astype(np.float32)
+        D_ref, I_ref = orc.np_search_f64(xb, xq, k, metric)
+        ix = _make(m, xb, metric)
+        for algo in (m.ALGO_SCAN, m.ALGO_TENSOR):
+            if algo == m.ALGO_TENSOR and k > 100:
+                continue
+            D, I = ix.set_search_params(algo=algo).search(xq, k)
+            r = orc.recall_and_errors(D, I, D_ref, I_ref, metric, rel_tol=REL)
+            assert r["recall"] == 1.0 and r["id_mismatch"] == 0 and r["padding_ok"] and r["max_rel_err"] <= REL, \
+                (case, dict(n=n, d=d, nq=nq, k=k, metric=metric, kind=kind, algo=algo), r)
+
+
+def test_many_fallbacks_with_query_chunks(m):
+    """Adversarial row order (every later row closer to the queries than all earlier ones: every candidate list
+    overflows) in a batch big enough to be processed in more than one tensor pass (k' = 192 caps a pass at 3072
+    queries): the closing exact scan must pick up the failures of every pass -- thousands of queries, walked in
+    groups inside one launch -- and scatter them to the right rows."""
+    rng = np.random.default_rng(11)
+    n, d, nq, k = 20000, 64, 3300, 100
+    q0 = rng.standard_normal(d).astype(np.float32)
+    dirs = rng.standard_normal((n, d)).astype(np.float32)
+    dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    radius = np.linspace(30.0, 1.0, n, dtype=np.float32)[:, None]
+    xb = (q0[None, :] + dirs * radius).astype(np.float32)
+    xq = (q0[None, :] + rng.standard_normal((nq, d)).astype(np.float32) * 1e-3).astype(np.float32)
+    ix = _make(m, xb, 1).set_search_params(algo=m.ALGO_TENSOR)
+    D, I = ix.search(xq, k)
+    _check(D, I, *orc.np_search_f64(xb, xq, k, 1), 1)
+    st = ix.stats()
+    assert st["last_algo"] == m.ALGO_TENSOR and st["fallback_queries"] > nq // 2, st
+
+
+def test_centred_scan_copy_certifies_embedding_like_data(m):
+    """Rows that share a large common component (sentence embeddings; the reference's own index has |x| ~ 7.7
+    and relative neighbour gaps of 1e-4): the scan copy is taken around the mean of the first rows, so the bf16
+    pass stays decisive and (nearly) every query is certified without the exact scan -- L2 and IP, and the
+    results stay exact either way."""
+    rng = np.random.default_rng(21)
+    n, d, nq, k = 50000, 384, 256, 10
+    common = rng.standard_normal(d).astype(np.float32) * 0.4
+    xb = (common[None, :] + rng.standard_normal((n, d)).astype(np.float32) * 0.02).astype(np.float32)
+    xq = (common[None, :] + rng.standard_normal((nq, d)).astype(np.float32) * 0.02).astype(np.float32)
+    # inner product: unit vectors with cosines around 0.94 (wider noise than the L2 case: at cosines of 0.997 fp32
+    # inner products of neighbouring rows differ by less than one ulp and even the reference's own fp32 scan would
+    # order them differently from a float64 oracle)
+    xbn = common[None, :] + rng.standard_normal((n, d)).astype(np.float32) * 0.1
+    xqn = common[None, :] + rng.standard_normal((nq, d)).astype(np.float32) * 0.1
+    xbn = (xbn / np.linalg.norm(xbn, axis=1, keepdims=True)).astype(np.float32)
+    xqn = (xqn / np.linalg.norm(xqn, axis=1, keepdims=True)).astype(np.float32)
+    for metric, b, q in ((1, xb, xq), (0, xbn, xqn)):
+        ix = _make(m, b, metric).set_search_params(algo=m.ALGO_TENSOR)
+        D, I = ix.search(q, k)
+        _check(D, I, *orc.np_search_f64(b, q, k, metric), metric)
+        st = ix.stats()
+        assert st["last_algo"] == m.ALGO_TENSOR and st["fallback_queries"] <= nq // 20, (metric, st)
+    # rows added later (another batch, same centre) and a search after reset (new centre) stay exact
+    ix = _make(m, xb[:1000], 1).set_search_params(algo=m.ALGO_TENSOR)
+    ix.add(xb[1000:30000] + 0.5)          # far from the first batch's mean
+    both = np.concatenate([xb[:1000], xb[1000:30000] + 0.5])
+    D, I = ix.search(xq[:64], k)
+    _check(D, I, *orc.np_search_f64(both, xq[:64], k, 1), 1)
+    ix.reset()
+    ix.add(xb[:5000] - 3.0)
+    D, I = ix.search(xq[:64] - 3.0, k)
+    _check(D, I, *orc.np_search_f64(xb[:5000] - 3.0, xq[:64] - 3.0, k, 1), 1)
+
+
 def test_async_device_searches_back_to_back(m):
     """Device-buffer searches return without synchronising (the uncertified-query count never visits the
     host): several searches queued back to back on one stream, then on another stream, must all be right."""
