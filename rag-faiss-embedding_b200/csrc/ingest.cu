@@ -16,6 +16,11 @@ __device__ __forceinline__ float warp_sum(float v) {
     for (int s = 16; s >= 1; s >>= 1) v += __shfl_xor_sync(kFull, v, s);
     return v;
 }
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) v += __shfl_xor_sync(kFull, v, s);
+    return v;
+}
 
 // Writes one element group of a row to every derived store and returns (bf16(x)^2, (x-bf16(x))^2).
 __device__ __forceinline__ void emit_elem(float x, int64_t row, int col, int d, float* rows_f32,
@@ -66,14 +71,15 @@ ingest_kernel(const float* __restrict__ src, int64_t n, int d, float* __restrict
     // two addresses serialised the whole kernel: 2.8 ms for 1M rows, 21% of HBM)
     float max_nn = 0.f, max_ee = 0.f;
     for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < n; row += wpg) {
-        float nn = 0.f, ee = 0.f, mx = 0.f;
+        float nn = 0.f, ee = 0.f;
+        double mx = 0.0;  // mu.x in double: its rounding error would otherwise dominate the IP certification slack
         if ((d & 3) == 0) {
             for (int c = lane * 4; c < d; c += 128) {
                 float4 x = ldg_stream(reinterpret_cast<const float4*>(src + row * d + c));
                 if (rows_f32) *reinterpret_cast<float4*>(rows_f32 + row * d + c) = x;
                 if (mu) {
                     const float4 m4 = __ldg(reinterpret_cast<const float4*>(mu + c));
-                    mx = fmaf(m4.x, x.x, mx); mx = fmaf(m4.y, x.y, mx); mx = fmaf(m4.z, x.z, mx); mx = fmaf(m4.w, x.w, mx);
+                    if (ip_bias) mx += (double)m4.x * x.x + (double)m4.y * x.y + (double)m4.z * x.z + (double)m4.w * x.w;
                     x.x -= m4.x; x.y -= m4.y; x.z -= m4.z; x.w -= m4.w;
                 }
                 const __nv_bfloat162 lo = __floats2bfloat162_rn(x.x, x.y), hi = __floats2bfloat162_rn(x.z, x.w);
@@ -91,7 +97,7 @@ ingest_kernel(const float* __restrict__ src, int64_t n, int d, float* __restrict
         } else {
             for (int c = lane; c < d; c += 32) {
                 const float x = src[row * d + c], m = mu ? mu[c] : 0.f;
-                mx = fmaf(m, x, mx);
+                if (ip_bias) mx += (double)m * x;
                 emit_elem(x, row, c, d, rows_f32, scan, dpad, nn, ee, m);
             }
         }
@@ -100,7 +106,7 @@ ingest_kernel(const float* __restrict__ src, int64_t n, int d, float* __restrict
         nn = warp_sum(nn);
         ee = warp_sum(ee);
         if (ip_bias) mx = warp_sum(mx);
-        if (lane == 0 && norms) norms[row] = ip_bias ? -mx : nn;   // the row's bias in the tensor pass
+        if (lane == 0 && norms) norms[row] = ip_bias ? (float)(-mx) : nn;   // the row's bias in the tensor pass
         max_nn = fmaxf(max_nn, nn);
         max_ee = fmaxf(max_ee, ee);
     }
@@ -312,7 +318,8 @@ prep_queries_kernel(const float* __restrict__ q, int nq, int nq_pad, int d, __nv
     const int lane = threadIdx.x & 31;
     const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (r >= nq_pad) return;
-    float nn = 0.f, ee = 0.f, qc = 0.f;
+    float nn = 0.f, ee = 0.f;
+    double qc = 0.0;
     for (int c = lane; c < dpad; c += 32) {
         const bool in = r < nq && c < d;
         const float m = (mu && in) ? mu[c] : 0.f;
@@ -323,7 +330,7 @@ prep_queries_kernel(const float* __restrict__ q, int nq, int nq_pad, int d, __nv
         qb[(int64_t)r * dpad + c] = b;
         nn = fmaf(xb, xb, nn);
         ee = fmaf(x - xb, x - xb, ee);
-        qc = fmaf(m, x, qc);   // (q - mu).mu = q.mu - mu.mu
+        qc += (double)m * ((double)x0 - (double)m);   // (q - mu).mu = q.mu - mu.mu, in double
     }
     nn = warp_sum(nn);
     ee = warp_sum(ee);
@@ -331,7 +338,7 @@ prep_queries_kernel(const float* __restrict__ q, int nq, int nq_pad, int d, __nv
     if (lane == 0 && r < nq) {
         qnorm[r] = nn;
         qerr[r] = sqrtf(ee);
-        qconst[r] = qc;
+        qconst[r] = (float)qc;
     }
 }
 

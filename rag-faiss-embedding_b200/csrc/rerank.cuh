@@ -171,10 +171,13 @@ __device__ __forceinline__ bool rerank_block(const RerankArgs& a, int q, const f
             } else {
                 // keys are negated (centred inner product + mu.x): <q,x> = -key + qconst + rounding terms, so
                 // non-candidates have <q,x> <= -bound + qconst + slack.  The fp32 sums mu.x and q.mu carry their own
-                // accumulation error (|mu| (|x| + |q|) gamma).
+                // rounding error.
                 const float cq = a.qconst ? a.qconst[q] : 0.f;
+                // mu.x and q.mu are accumulated in double, so they only carry the rounding of their fp32 results and
+                // of the fp32 additions they enter (a few ulp of |mu| (|x| + |q|))
                 const float xmax = a.max_row_norm + a.max_row_err + a.mu_norm;   // >= |x| of any row
-                const float nu = gam * (qn * a.max_row_norm + a.mu_norm * (xmax + qn + eq + a.mu_norm));
+                const float nu = gam * qn * a.max_row_norm +
+                                 2.4e-7f * (a.mu_norm * (xmax + qn + eq + a.mu_norm) + qn * a.max_row_norm);
                 const float U = -bound + cq + nu + (qn + eq) * a.max_row_err + a.max_row_norm * eq;
                 certified = U < -tau;
             }
