@@ -297,10 +297,7 @@ def main():
 
     def step_host():
         if sh is not None:
-            Dl, Il = sh.search(xq_pin.to(dev, non_blocking=True), k)
-            D_pin.copy_(Dl, non_blocking=True)
-            I_pin.copy_(Il, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+            sh.search_host(xq_pin, k, D_pin, I_pin)   # each rank uploads its slice of the replicated batch
         else:
             ix.search_into(xq_pin.numpy(), k, D_pin.numpy(), I_pin.numpy())
 

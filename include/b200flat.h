@@ -169,6 +169,13 @@ B2F_API int b2f_pool_normalize(const float* hidden, const int64_t* mask, int64_t
 B2F_API int b2f_index_add_pooled(b2f_index* idx, const float* hidden, const int64_t* mask, int64_t B, int64_t T,
                          int32_t pool, int32_t normalize, void* stream);
 
+/* Query side of the same hand-off (replaces the encode -> .cpu().numpy() -> np.array -> index.search chain of
+ * vectorization.py:38-47 + faiss_store.py:56-64): pools (+ normalises) the encoder output of a query batch on the
+ * device and searches it, all on `stream`; D: [B, k] fp32, I: [B, k] int64, device buffers.              */
+B2F_API int b2f_index_search_pooled(b2f_index* idx, const float* hidden, const int64_t* mask, int64_t B, int64_t T,
+                            int32_t pool, int32_t normalize, int64_t k, float* D, int64_t* I, void* stream,
+                            const b2f_search_params* params);
+
 /* ---- synthetic rows for benchmarks: same bits as oracle/flat_oracle.c orc_synth_rows ----------- */
 B2F_API int b2f_synth_rows(uint64_t seed, int64_t row0, int64_t nrows, int32_t d, int32_t normalize, float* out,
                    int32_t device, void* stream);

@@ -47,6 +47,8 @@ struct b2f_index {
     b2f_stats st{};
     float host_stats[2] = {0.f, 0.f};
     bool stats_dirty = true;
+    float* qpool = nullptr;           // pooled query batch of search_pooled (grow only)
+    size_t qpool_bytes = 0;
     float* centre = nullptr;          // [d] device: centre of the scan copy (fp32 storage; see ingest_kernel), fixed at the first add
     bool mu_set = false;
     float mu_norm = 0.f;              // |mu| (host copy, refreshed with host_stats)
@@ -473,6 +475,7 @@ int b2f_index_destroy(b2f_index* ix) {
     cudaFree(ix->norms);
     cudaFree(ix->stats);
     cudaFree(ix->centre);
+    cudaFree(ix->qpool);
     cudaFree(ix->ws);
     if (ix->pinned) cudaFreeHost(ix->pinned);
     if (ix->host_flag) cudaFreeHost(ix->host_flag);
@@ -945,6 +948,44 @@ int b2f_index_search(b2f_index* ix, int64_t nq64, const float* q, int64_t k64, f
         harvest_flag(ix);
     }
     return B2F_OK;
+}
+
+int b2f_index_search_pooled(b2f_index* ix, const float* hidden, const int64_t* mask, int64_t B, int64_t T, int32_t pool,
+                            int32_t normalize, int64_t k, float* D, int64_t* I, void* stream, const b2f_search_params* params) {
+    if (!ix || B < 0 || (B > 0 && (!hidden || !D || !I))) {
+        set_error("search_pooled: bad arguments");
+        return B2F_EINVAL;
+    }
+    if (B == 0) return B2F_OK;
+    float* qbuf = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(ix->mu);
+        DeviceGuard g(ix->device);
+        if (!g.ok) {
+            set_error("cudaSetDevice(%d) failed", ix->device);
+            return B2F_ENOGPU;
+        }
+        // pooled queries live in their own grow-only buffer (the search below carves the workspace itself)
+        const size_t need = (size_t)B * ix->d * sizeof(float);
+        if (need > ix->qpool_bytes) {
+            if (ix->search_recorded) B2F_CUDA(cudaEventSynchronize(ix->ev_done));
+            cudaFree(ix->qpool);
+            ix->qpool = nullptr;
+            ix->qpool_bytes = 0;
+            if (cudaMalloc(&ix->qpool, need + (need >> 2)) != cudaSuccess) {
+                cudaGetLastError();
+                set_error("search_pooled: cudaMalloc(%zu) failed", need);
+                return B2F_ENOMEM;
+            }
+            ix->qpool_bytes = need + (need >> 2);
+        }
+        qbuf = ix->qpool;
+        cudaStream_t st = stream ? (cudaStream_t)stream : ix->stream;
+        if (ix->search_recorded && ix->last_stream != st) B2F_CUDA(cudaStreamWaitEvent(st, ix->ev_done, 0));
+        B2F_TRY(launch_pool(hidden, mask, B, T, ix->d, pool, normalize, qbuf, nullptr, 0, nullptr, nullptr, st));
+        ix->st.launches++;
+    }
+    return b2f_index_search(ix, B, qbuf, k, D, I, B2F_MEM_DEVICE, stream, params);
 }
 
 int b2f_index_reconstruct(b2f_index* ix, int64_t i0, int64_t n, float* out, int32_t mem, void* stream) {

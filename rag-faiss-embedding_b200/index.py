@@ -171,6 +171,27 @@ class IndexFlat:
                                                C.POOL_MEAN if pool == "mean" else C.POOL_CLS, int(bool(normalize)),
                                                _torch_stream(hidden)))
 
+    def search_pooled(self, hidden, attention_mask, k: int, pool: str = "cls", normalize: bool = False):
+        """Query side of the encoder hand-off: hidden [B,T,d] CUDA fp32 -> pooled (+ normalised) on the device ->
+        search; returns CUDA tensors (D [B,k] float32, I [B,k] int64) on the current torch stream."""
+        import torch
+
+        _assert(k > 0, "k must be > 0")
+        _assert(_is_torch(hidden) and hidden.is_cuda and hidden.dim() == 3 and hidden.shape[2] == self.d,
+                "search_pooled expects a CUDA tensor [B, T, d]")
+        hidden = hidden.to(torch.float32).contiguous()
+        mptr = None
+        if attention_mask is not None:
+            attention_mask = attention_mask.to(device=hidden.device, dtype=torch.int64).contiguous()
+            mptr = attention_mask.data_ptr()
+        B = hidden.shape[0]
+        D = torch.empty((B, k), dtype=torch.float32, device=hidden.device)
+        I = torch.empty((B, k), dtype=torch.int64, device=hidden.device)
+        C.check(self._lib.b2f_index_search_pooled(self._h, hidden.data_ptr(), mptr, B, hidden.shape[1],
+                                                  C.POOL_MEAN if pool == "mean" else C.POOL_CLS, int(bool(normalize)), k,
+                                                  D.data_ptr(), I.data_ptr(), _torch_stream(hidden), ctypes.byref(self._params)))
+        return D, I
+
     def search(self, x, k: int, *, params: Optional[C.SearchParams] = None):
         """index.search(x, k) -> (D float32 [n,k], I int64 [n,k]): faiss_store.py:64,
         rag_datastore_manager.py:218."""

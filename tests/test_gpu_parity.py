@@ -417,6 +417,11 @@ def test_pool_normalize_and_add_pooled(m):
     assert np.array_equal(rows[B:], h[:, 0].cpu().numpy())
     D, I = ix.search(nrm.cpu().numpy()[:5], 1)
     assert I[:, 0].tolist() == [0, 1, 2, 3, 4] or (D[:, 0] >= 1 - 1e-4).all()
+    # query side of the hand-off: pool + normalise + search in one call == pooling first, then searching
+    Dp, Ip = ix.search_pooled(h, mask, 3, pool="mean", normalize=True)
+    Dr, Ir = ix.search(nrm, 3)
+    torch.cuda.synchronize()
+    assert torch.equal(Ip, Ir) and torch.allclose(Dp, Dr, rtol=1e-6, atol=1e-7)
 
 
 def test_synth_bit_identical(m):
