@@ -218,6 +218,9 @@ struct ListArgs {
     int nl_stride;       // lists per query allocated (the largest per-tile list count)
     int cap;             // entries per list
     float* final_thr;    // [nq_pad * nsplits]  threshold the list was pruned against at the end of the stream
+    int extra;           // virtual splits consulted beyond the gv needed (0..3): the gv-th smallest of gv + extra values
+    int early;           // 1: scheduled threshold refreshes happen before the wait for the tile's accumulator
+    int period_mask;     // refresh every (period_mask + 1) tiles after the first 32 (power of two - 1)
 };
 
 // thread-private max-heap in shared memory, element j of thread t at [j * 128 + t].
@@ -491,7 +494,12 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             const float kInf = __int_as_float(0x7f800000);
             const int vsplit = split * HALVES + half, nvs = my_nsplits * HALVES;
             const int jv = (la.kp + nvs - 1) / nvs;      // rows each virtual split vouches for
-            const int gv = (la.kp + jv - 1) / jv;        // virtual splits consulted: gv * jv >= k'
+            const int gv = (la.kp + jv - 1) / jv;        // virtual splits needed: gv * jv >= k'
+            // Splits consulted: up to la.extra (0..3) more than needed.  Among wv published values the gv-th SMALLEST
+            // is still an upper bound of the k'-th best (gv splits vouch for jv rows each at or below it), and it is
+            // tighter than the maximum of exactly gv values.
+            const int wv = nvs < gv + la.extra ? nvs : gv + la.extra;
+            const int lsel = wv - gv;                    // take the (lsel + 1)-th largest of the wv values
             float best[JSLOTS];  // ascending; the first JSLOTS - j slots are pinned at -inf, so best[JSLOTS-1] = j-th best
 #pragma unroll
             for (int i = 0; i < JSLOTS; i++) best[i] = (i < JSLOTS - jv) ? -kInf : kInf;
@@ -507,26 +515,39 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                     pub = best[JSLOTS - 1];
                     __stcg(gq + (int64_t)vsplit * gstride, pub);
                 }
-                float t = -kInf;
+                float t0 = -kInf, t1 = -kInf, t2 = -kInf, t3 = -kInf;  // the four largest, descending
 #pragma unroll 1
-                for (int i0 = 0; i0 < gv; i0 += 16) {  // 16 independent L2 loads in flight
+                for (int i0 = 0; i0 < wv; i0 += 16) {  // 16 independent L2 loads in flight
                     float v[16];
 #pragma unroll
                     for (int u = 0; u < 16; u++) {
                         int s2 = vsplit + i0 + u;
                         if (s2 >= nvs) s2 -= nvs;
-                        v[u] = (i0 + u < gv) ? __ldcg(gq + (int64_t)s2 * gstride) : -kInf;
+                        v[u] = (i0 + u < wv) ? __ldcg(gq + (int64_t)s2 * gstride) : -kInf;
                     }
+                    if (lsel == 0) {
 #pragma unroll
-                    for (int u = 0; u < 16; u++) t = fmaxf(t, v[u]);
+                        for (int u = 0; u < 16; u++) t0 = fmaxf(t0, v[u]);
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < 16; u++) {
+                            float x = v[u], a;
+                            a = fmaxf(t0, x); x = fminf(t0, x); t0 = a;
+                            a = fmaxf(t1, x); x = fminf(t1, x); t1 = a;
+                            a = fmaxf(t2, x); x = fminf(t2, x); t2 = a;
+                            t3 = fmaxf(t3, x);
+                        }
+                    }
                 }
-                thr = t;
+                thr = lsel == 0 ? t0 : (lsel == 1 ? t1 : (lsel == 2 ? t2 : t3));
             };
             auto process = [&](const uint32_t (&r)[32], int t, int c, const float* tbc, int32_t rowc) {
                 // refresh schedule: thresholds move like 1/rows_seen, so consult the other splits often
                 // at the start and rarely later
+                // (from the third tile on the refresh happens at the top of the tile loop, while the thread would
+                // otherwise wait for the MMAs of the tile -- see below)
                 const bool do_refresh = t == 0 || (t == 1 && (c & 1) == 0) ||
-                                        (c == 0 && (t < 8 || (t < 32 && (t & 3) == 0) || (t & 15) == 0));
+                                        (!la.early && c == 0 && (t < 8 || (t < 32 && (t & 3) == 0) || (t & 15) == 0));
                 if (active && do_refresh) {
                     refresh();
                     if (t == 0 && c == 1) {
@@ -579,6 +600,10 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             for (int t = 0; t < my_tiles; t++) {
                 const int acc = t & 1;
                 const uint32_t acc_phase = (t >> 1) & 1;
+                // Scheduled refresh of the shared threshold BEFORE waiting for the tile's accumulator: the ~1.4 us
+                // of L2 round trips overlap the MMAs the thread would wait for anyway, and no accumulator registers
+                // are live yet (same-box A/B: the refreshes inside the tile cost 3-4% of the kernel).
+                if (la.early && active && t >= 2 && (t < 8 || (t < 32 && (t & 3) == 0) || (t & la.period_mask) == 0)) refresh();
                 mbar_wait(&bias_full[acc], acc_phase);
                 mbar_wait(&tmem_full[acc], acc_phase);
                 tc_fence_after();
@@ -1113,6 +1138,29 @@ int launch_tensor_scan(const __nv_bfloat16* scan, int64_t dpad, const float* nor
         la.nl_stride = plan.nlists;
         la.cap = plan.list_cap;
         la.final_thr = lists.final_thr;
+        {
+            static int extra = -1;
+            if (extra < 0) {
+                const char* e = getenv("B200FLAT_THR_EXTRA");
+                extra = e ? atoi(e) : 0;
+                if (extra < 0) extra = 0;
+                if (extra > 3) extra = 3;
+            }
+            la.extra = extra;
+            static int early = -1;
+            if (early < 0) {
+                const char* e = getenv("B200FLAT_EARLY_REFRESH");
+                early = (e && e[0] == '0') ? 0 : 1;
+            }
+            la.early = early;
+            static int period = -1;
+            if (period < 0) {
+                const char* e = getenv("B200FLAT_REFRESH_PERIOD");
+                period = e ? atoi(e) : 32;   // same-box A/B over 4..128: 32 is the flat optimum (profiles/r01_j_ab_refresh.txt)
+                if (period != 2 && period != 4 && period != 8 && period != 16 && period != 32 && period != 64 && period != 128) period = 32;
+            }
+            la.period_mask = period - 1;
+        }
         // lists.shared_thr was filled with 0x7f7f7f7f (3.39e38, "no information yet") by the query-prep kernel
         if (plan.pair_mode)
             return l2 ? k2::launch_k2<0, true, true, true, true>(mq, mx, norms, n, nq, kblocks, plan, pk, pi, la, st)
