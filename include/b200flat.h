@@ -158,6 +158,23 @@ B2F_API int b2f_merge_topk_strided(int32_t metric, int64_t nq, int64_t k, int32_
                    const int64_t* I_parts, int64_t part_stride_bytes, float* D, int64_t* I, int32_t device,
                    void* stream);
 
+/* ---- multi-GPU over NVLink peer memory: the exchange + merge above as ONE kernel (no NCCL call, no second launch).
+ * One process per GPU.  create() allocates this rank's receive buffers (two generations x world slots of
+ * slot_bytes) and returns a 64-byte IPC handle; the host exchanges the handles of all ranks (any side channel,
+ * e.g. torch.distributed.all_gather_object) and passes them, rank-ordered, to connect().  merge() is collective:
+ * every rank calls it once per search with its own message `msg` = [D (nq*k fp32) | pad | I (nq*k int64) at off_i],
+ * msg_bytes a multiple of 16 and <= slot_bytes.  The kernel pushes the message into every peer's slot with
+ * 16-byte stores, signals with a system-scope release flag, waits for all ranks' flags and merges the world
+ * parts into (D, I) [nq, k] on `stream`.  Device buffers only.                                          */
+typedef struct b2f_exchange b2f_exchange;
+B2F_API int b2f_exchange_create(int32_t device, int32_t rank, int32_t world, int64_t slot_bytes, b2f_exchange** out,
+                        void* handle_out_64_bytes);
+B2F_API int b2f_exchange_connect(b2f_exchange* ex, const void* handles_world_x_64_bytes);
+B2F_API int64_t b2f_exchange_slot_bytes(const b2f_exchange* ex);
+B2F_API int b2f_exchange_merge(b2f_exchange* ex, const void* msg, int64_t msg_bytes, int32_t metric, int64_t nq, int64_t k,
+                       int64_t off_i, float* D, int64_t* I, void* stream);
+B2F_API int b2f_exchange_destroy(b2f_exchange* ex);
+
 /* ---- fused encoder epilogue (replaces vectorization.py:44-47, rag_datastore_manager.py:129-132:
  *      last_hidden_state[:,0].cpu().numpy() -> list -> np.array) ---------------------------------
  * hidden: [B, T, d] fp32 device; mask: [B, T] int64 device (HF attention_mask) or NULL.

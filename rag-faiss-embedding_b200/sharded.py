@@ -111,6 +111,15 @@ class ShardedIndexFlat:
         self.ntotal = 0
         self.is_trained = True
 
+    def __del__(self):
+        ex = getattr(self, "_ex", None)
+        if ex is not None:
+            try:
+                C.load().b2f_exchange_destroy(ex)
+            except Exception:  # interpreter shutdown
+                pass
+            self._ex = None
+
     # -- ingest -----------------------------------------------------------------------------------
     def add(self, x):
         """x: the same [n, d] array on every rank; each rank keeps its contiguous slice."""
@@ -148,6 +157,44 @@ class ShardedIndexFlat:
             return D, self.segments.to_global_numpy(I)
         return D, self.segments.to_global_torch(I)
 
+    def _peer_exchange(self, need_bytes: int):
+        """The NVLink peer-memory exchange (csrc/exchange.cu), created on first use and re-created when a search needs
+        bigger slots.  Collective: every rank takes the same decisions (same need_bytes on every rank).  Returns None
+        when B200FLAT_EXCHANGE=nccl or the IPC set-up fails on any rank (then NCCL carries the exchange)."""
+        import os
+
+        if os.environ.get("B200FLAT_EXCHANGE", "peer").lower() == "nccl" or getattr(self, "_ex_failed", False):
+            return None
+        ex = getattr(self, "_ex", None)
+        lib = C.load()
+        if ex is not None and lib.b2f_exchange_slot_bytes(ex) >= need_bytes:
+            return ex
+        import torch
+
+        torch.cuda.synchronize()
+        if ex is not None:
+            self._dist.barrier(group=self.group)   # nobody may still be reading our old buffers
+            lib.b2f_exchange_destroy(ex)
+            self._ex = None
+        slot = max(1 << 20, 2 * need_bytes)
+        h = ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(64)
+        rc = lib.b2f_exchange_create(self.local.device, self.rank, self.world, slot, ctypes.byref(h), handle)
+        handles = [None] * self.world
+        self._dist.all_gather_object(handles, bytes(handle.raw) if rc == 0 else None, group=self.group)
+        ok = rc == 0 and all(b is not None for b in handles)
+        if ok:
+            ok = lib.b2f_exchange_connect(h, b"".join(handles)) == 0
+        oks = [None] * self.world
+        self._dist.all_gather_object(oks, bool(ok), group=self.group)
+        if not all(oks):
+            if rc == 0:
+                lib.b2f_exchange_destroy(h)
+            self._ex_failed = True
+            return None
+        self._ex = h
+        return h
+
     def _search_packed(self, x, k: int):
         """CUDA path of search(): every rank writes its (D, I) into ONE message buffer, one all-gather ships it
         (12 * nq * k bytes per rank), the CUDA merge kernel reads the gathered messages in place."""
@@ -167,11 +214,17 @@ class ShardedIndexFlat:
             Dl, Il = self.local.search(x, k)
             D.copy_(Dl)
             I.copy_(self.segments.to_global_torch(Il))
-        recv = torch.empty(self.world * part, dtype=torch.uint8, device=x.device)
-        self._dist.all_gather_into_tensor(recv, send, group=self.group)   # the one exchange step of the path
         Dm = torch.empty((nq, k), dtype=torch.float32, device=x.device)
         Im = torch.empty((nq, k), dtype=torch.int64, device=x.device)
         stream = int(torch.cuda.current_stream(x.device).cuda_stream) or 1  # 0x1 = cudaStreamLegacy
+        ex = self._peer_exchange(part)
+        if ex is not None:
+            # the one exchange step of the path, fused with the merge: push over NVLink peer memory, flag, merge
+            C.check(C.load().b2f_exchange_merge(ex, send.data_ptr(), part, int(self.metric_type), nq, k, off_i,
+                                                Dm.data_ptr(), Im.data_ptr(), ctypes.c_void_p(stream)))
+            return Dm, Im
+        recv = torch.empty(self.world * part, dtype=torch.uint8, device=x.device)
+        self._dist.all_gather_into_tensor(recv, send, group=self.group)   # NCCL form of the same exchange
         C.check(C.load().b2f_merge_topk_strided(int(self.metric_type), nq, k, self.world, recv.data_ptr(),
                                                 recv.data_ptr() + off_i, part, Dm.data_ptr(), Im.data_ptr(),
                                                 x.device.index or 0, ctypes.c_void_p(stream)))
