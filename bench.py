@@ -92,20 +92,25 @@ class ClockSampler:
         self._t = None
         self.source = "nvidia-smi"
 
+    def _sample_nvml(self, nv, h, mx, get_reasons):
+        try:
+            self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+            self.mx.append(mx)
+            bits = int(get_reasons(h))
+            for name, bit in self.NVML_BITS.items():
+                if bits & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
     def _run_nvml(self, nv, h):
         mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
         get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
-        while not self._stop.is_set():
-            try:
-                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
-                self.mx.append(mx)
-                bits = int(get_reasons(h))
-                for name, bit in self.NVML_BITS.items():
-                    if bits & bit:
-                        self.reasons.add(name)
-            except Exception:
-                pass
-            self._stop.wait(0.002)
+        while True:   # at least one sample even when the whole run is shorter than the thread's start-up
+            self._sample_nvml(nv, h, mx, get_reasons)
+            if self._stop.wait(0.002):
+                break
+        self._sample_nvml(nv, h, mx, get_reasons)
 
     def _run_smi(self):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
