@@ -145,6 +145,15 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p) {
     return r;
 }
 
+// cudaFuncSetAttribute / occupancy are per device: launchers cache what they configured per device, so one
+// process may drive indexes on several GPUs.
+constexpr int kMaxDevices = 64;
+inline int current_device_slot() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= kMaxDevices) d = 0;
+    return d;
+}
+
 // ---- host-side error plumbing ------------------------------------------------------------------
 void set_error(const char* fmt, ...);
 

@@ -334,10 +334,11 @@ static int launch_one(const RowT* rows, int64_t pitch, const ScanArgs& a, cudaSt
     const int dq = ((a.d + Vec::N - 1) / Vec::N) * Vec::N;
     const size_t smem = (((size_t)NQ * dq + 2 * (size_t)kScanWarps * NQ * a.k + 1) & ~(size_t)1) * 4 + (size_t)kGatherCap * 8;
     auto kern = scan_kernel<NQ, L2, RowT, Vec>;
-    static size_t configured_smem = 0;
-    if (configured_smem == 0 || smem > configured_smem) {
+    static size_t configured_smem[kMaxDevices] = {};
+    const int dev = current_device_slot();
+    if (configured_smem[dev] == 0 || smem > configured_smem[dev]) {
         B2F_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 65536 ? smem : 65536)));
-        configured_smem = smem > 65536 ? smem : 65536;
+        configured_smem[dev] = smem > 65536 ? smem : 65536;
     }
     // occupancy per (kernel, smem) is cached: the query costs microseconds and sits on the search path
     static size_t occ_smem = ~(size_t)0;

@@ -68,3 +68,27 @@ def test_sharded_nccl_matches_oracle(tmp_path):
             assert res1["recall"] == 1.0 and res1["id_mismatch"] == 0, (r, metric, res1)
             total += int(z["nlocal"])
         assert total == n
+
+
+def test_two_devices_in_one_process():
+    """One process driving indexes on two GPUs (kernel attributes are configured per device): both answer exactly,
+    through both search paths, interleaved."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import rag_faiss_embedding_b200 as b2f
+
+    d, n, k = 128, 30000, 10
+    xb = orc.c_synth_rows(1234, 0, n, d)
+    xq = orc.c_synth_rows(5678, 0, 200, d)
+    D_ref, I_ref = orc.np_search_f64(xb, xq, k, 1)
+    idx = [b2f.IndexFlat(d, 1, device=dev) for dev in (0, 1)]
+    for ix in idx:
+        ix.add(xb)
+    for algo in (b2f.ALGO_TENSOR, b2f.ALGO_SCAN, b2f.ALGO_TENSOR):
+        for ix in (idx[1], idx[0]):
+            nq = 200 if algo == b2f.ALGO_TENSOR else 9
+            D, I = ix.set_search_params(algo=algo).search(xq[:nq], k)
+            r = orc.recall_and_errors(D, I, D_ref[:nq], I_ref[:nq], 1)
+            assert r["recall"] == 1.0 and r["id_mismatch"] == 0 and r["max_rel_err"] <= 1e-5, (ix.device, algo, r)
