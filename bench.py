@@ -241,6 +241,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--algo", default="auto", choices=["auto", "scan", "tensor"])
+    ap.add_argument("--slack", type=int, default=0, help="tensor path: extra coarse candidates per query (0 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     args = ap.parse_args()
@@ -283,7 +284,7 @@ def main():
     ix = b2f.IndexFlat(d, wl["metric"], storage=storage, device=local_rank)
     ix.reserve(hi - lo)
     ix.add_synthetic(SEED_DB, lo, hi - lo, wl["normalize"])   # generated on the device, bit-identical to the oracle
-    ix.set_search_params(algo=algo, id_offset=lo, profile=True)
+    ix.set_search_params(algo=algo, id_offset=lo, profile=True, slack=args.slack)
     sh = ShardedIndexFlat(d, wl["metric"], local_index=ix) if world > 1 else None
     if sh is not None:
         sh.segments.append(lo, hi - lo)

@@ -94,7 +94,12 @@ __global__ void __launch_bounds__(256) exchange_merge_kernel(const ExArgs a) {
     // ---- 3. wait for every rank's push of this search ------------------------------------------------------
     if (threadIdx.x < a.world) {
         const uint32_t* f = reinterpret_cast<const uint32_t*>(a.peer[a.rank] + a.flags_off) + par * a.world + threadIdx.x;
-        while (ld_acquire_sys(f) != a.seq) __nanosleep(64);
+        // bounded: a peer that died must surface as a CUDA error at the next synchronisation, not as a hung GPU
+        const long long t0 = clock64();
+        while (ld_acquire_sys(f) != a.seq) {
+            __nanosleep(64);
+            if (clock64() - t0 > 20000000000LL) __trap();   // ~10 s at 2 GHz
+        }
     }
     __syncthreads();
     // ---- 4. merge: one warp per query over the world parts (lane l walks part l) ----------------------------
