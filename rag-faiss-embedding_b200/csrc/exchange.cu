@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(256) exchange_merge_kernel(const ExArgs a) {
         const long long t0 = clock64();
         while (ld_acquire_sys(f) != a.seq) {
             __nanosleep(64);
-            if (clock64() - t0 > 20000000000LL) __trap();   // ~10 s at 2 GHz
+            if (clock64() - t0 > 120000000000LL) __trap();   // ~60 s at 2 GHz
         }
     }
     __syncthreads();
