@@ -201,6 +201,9 @@ class ShardedIndexFlat:
         import torch
 
         nq = int(x.shape[0])
+        if nq == 0:
+            return (torch.empty((0, k), dtype=torch.float32, device=x.device),
+                    torch.empty((0, k), dtype=torch.int64, device=x.device))
         off_i = (nq * k * 4 + 15) // 16 * 16
         part = (off_i + nq * k * 8 + 15) // 16 * 16
         send = torch.empty(part, dtype=torch.uint8, device=x.device)

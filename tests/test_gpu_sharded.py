@@ -38,9 +38,23 @@ def _worker(rank, world, port, out_dir):
             assert ix.ntotal == n
             D, I = ix.search(xq, k)               # replicated queries -> identical merged result on all ranks
             D1, I1 = ix.search(xq[:1], k)         # nq = 1 goes through the streaming scan on every shard
+            # the exchange under stress: back-to-back searches of changing size (double-buffered peer slots), a
+            # message larger than the first slots (the exchange is re-created collectively), the NCCL form of the
+            # same step, host-resident queries (slice upload + all-gather), an empty batch
+            outs = [ix.search(xq[: 10 + 7 * i], k) for i in range(8)]
+            Db, Ib = ix.search(xq.repeat(250, 1), k)              # 37500 queries: a 4.5 MB message
+            os.environ["B200FLAT_EXCHANGE"] = "nccl"
+            Dn, In = ix.search(xq, k)
+            del os.environ["B200FLAT_EXCHANGE"]
+            Dh, Ih = ix.search_host(xq.cpu().pin_memory(), k)
+            De, Ie = ix.search(xq[:0], k)
             torch.cuda.synchronize()
+            same = all(torch.equal(Io, I[: Io.shape[0]]) and torch.equal(Do, D[: Do.shape[0]]) for Do, Io in outs)
+            same = same and torch.equal(Ib[:nq], I) and torch.equal(Ib[-nq:], I) and torch.equal(Db[nq:2 * nq], D)
+            same = same and torch.equal(In, I) and torch.equal(Dn, D)
+            same = same and torch.equal(Ih.cuda(), I) and torch.equal(Dh.cuda(), D) and tuple(Ie.shape) == (0, k)
             np.savez(os.path.join(out_dir, f"r{rank}_m{metric}.npz"), D=D.cpu().numpy(), I=I.cpu().numpy(),
-                     D1=D1.cpu().numpy(), I1=I1.cpu().numpy(), nlocal=ix.local.ntotal)
+                     D1=D1.cpu().numpy(), I1=I1.cpu().numpy(), nlocal=ix.local.ntotal, same=bool(same))
     finally:
         dist.destroy_process_group()
 
@@ -66,6 +80,7 @@ def test_sharded_nccl_matches_oracle(tmp_path):
             assert res["recall"] == 1.0 and res["id_mismatch"] == 0 and res["max_rel_err"] <= 1e-5, (r, metric, res)
             res1 = orc.recall_and_errors(z["D1"], z["I1"], D_ref[:1], I_ref[:1], metric)
             assert res1["recall"] == 1.0 and res1["id_mismatch"] == 0, (r, metric, res1)
+            assert bool(z["same"]), (r, metric, "exchange variants disagree")
             total += int(z["nlocal"])
         assert total == n
 
