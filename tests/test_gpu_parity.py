@@ -316,6 +316,63 @@ def test_centred_scan_copy_certifies_embedding_like_data(m):
     _check(D, I, *orc.np_search_f64(xb[:5000] - 3.0, xq[:64] - 3.0, k, 1), 1)
 
 
+def test_random_operation_sequence(m, tmp_path):
+    """Seeded fuzz over the index life cycle: adds (host arrays and device tensors, growing the storage several
+    times), searches (host / device buffers, both paths, changing batch sizes and k, so the workspace is
+    re-carved and re-allocated while earlier device-buffer searches may still be in flight), reset, reconstruct,
+    write + read.  Every search is checked against the oracle on a host mirror of the rows."""
+    import torch
+
+    rng = np.random.default_rng(77)
+    for metric in (1, 0):
+        d = 96
+        ix = m.IndexFlat(d, metric)
+        mirror = np.zeros((0, d), np.float32)
+        pending = []   # device-buffer results checked later (they are produced asynchronously)
+        for step in range(70):
+            op = rng.choice(["add", "add_dev", "search", "search", "search_dev", "search_dev", "reset", "io", "recon"],
+                            p=[0.14, 0.1, 0.24, 0.0, 0.3, 0.0, 0.04, 0.06, 0.12])
+            if op in ("add", "add_dev") or mirror.shape[0] == 0:
+                n = int(rng.choice([1, 5, 100, 1500, 9000]))
+                x = (rng.standard_normal((n, d)) + 0.3).astype(np.float32)
+                ix.add(torch.from_numpy(x).cuda() if op == "add_dev" else x)
+                mirror = np.concatenate([mirror, x])
+                assert ix.ntotal == mirror.shape[0]
+            elif op in ("search", "search_dev"):
+                nq = int(rng.choice([1, 3, 40, 130, 600]))
+                k = int(rng.choice([1, 10, 50]))
+                algo = int(rng.choice([m.ALGO_AUTO, m.ALGO_SCAN, m.ALGO_TENSOR]))
+                xq = (rng.standard_normal((nq, d)) + 0.3).astype(np.float32)
+                ix.set_search_params(algo=algo)
+                ref = orc.np_search_f64(mirror, xq, k, metric)
+                if op == "search_dev":
+                    pending.append((ix.search(torch.from_numpy(xq).cuda(), k), ref, (step, nq, k, algo)))
+                else:
+                    D, I = ix.search(xq, k)
+                    _check(D, I, *ref, metric)
+            elif op == "reset":
+                torch.cuda.synchronize()
+                for (D, I), ref, tag in pending:
+                    _check(D.cpu().numpy(), I.cpu().numpy(), *ref, metric)
+                pending = []
+                ix.reset()
+                mirror = np.zeros((0, d), np.float32)
+            elif op == "io":
+                path = tmp_path / f"fuzz_{metric}_{step}.bin"
+                m.write_index(ix, path)
+                back = m.read_index(path)
+                assert back.ntotal == ix.ntotal and back.metric_type == metric
+                assert np.array_equal(back.reconstruct_n(), mirror)
+                ix = back
+            else:
+                i = int(rng.integers(0, mirror.shape[0]))
+                assert np.array_equal(ix.reconstruct(i), mirror[i])
+        torch.cuda.synchronize()
+        for (D, I), ref, tag in pending:
+            r = orc.recall_and_errors(D.cpu().numpy(), I.cpu().numpy(), *ref, metric)
+            assert r["recall"] == 1.0 and r["id_mismatch"] == 0 and r["padding_ok"] and r["max_rel_err"] <= REL, (tag, r)
+
+
 def test_async_device_searches_back_to_back(m):
     """Device-buffer searches return without synchronising (the uncertified-query count never visits the
     host): several searches queued back to back on one stream, then on another stream, must all be right."""
