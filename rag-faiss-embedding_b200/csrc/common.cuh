@@ -302,6 +302,7 @@ struct TensorScanLists {  // LIST-mode scratch (device)
     void* cand;           // [nq_pad * nlists][list_cap] x 8 bytes
     int32_t* counts;      // [nq_pad * nlists]
     float* final_thr;     // [nq_pad * nlists]  the threshold each list was pruned against at the end of the stream
+    int32_t* die_ctr;     // [4] ticket counters of the die-aware unit assignment (zero between launches), or null
 };
 int plan_tensor_scan(int nq, int64_t n, int d, int kp, TensorScanPlan* plan);
 int launch_tensor_scan(const __nv_bfloat16* scan, int64_t dpad, const float* norms, int64_t n, int metric,

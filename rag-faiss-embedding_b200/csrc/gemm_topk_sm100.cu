@@ -129,6 +129,19 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 // TMA load issued by either CTA of the pair; the bytes are credited to the LEADER CTA's mbarrier
+// Same load with an L2 cache policy (database blocks that several units read: keep them, evict_last)
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void tma_load_2d_pair_hint(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerBitMask), "r"(x), "r"(y), "l"(policy)
+        : "memory");
+}
 __device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
     asm volatile(
         "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
@@ -221,6 +234,9 @@ struct ListArgs {
     int extra;           // virtual splits consulted beyond the gv needed (0..3): the gv-th smallest of gv + extra values
     int early;           // 1: scheduled threshold refreshes happen before the wait for the tile's accumulator
     int period_mask;     // refresh every (period_mask + 1) tiles after the first 32 (power of two - 1)
+    int l2_keep;         // 1: database blocks are loaded with an evict_last L2 policy (several units read each block)
+    int die_mode;        // > 0: die-aware unit assignment (pair kernel); the value selects the smid -> die guess
+    int32_t* die_ctr;    // [4] ticket counters (zero between launches)
 };
 
 // thread-private max-heap in shared memory, element j of thread t at [j * 128 + t].
@@ -294,8 +310,52 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     // queries [128 r, 128 r + 128) of the pair tile and stages rows [128 r, 128 r + 128) of every
     // 256-row database block; the leader (rank 0) issues tcgen05.mma.cta_group::2 for both.
     const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
-    const int unit = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;       // cluster (PAIR) or CTA index
+    int unit = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;       // cluster (PAIR) or CTA index
     const int units_per_split = PAIR ? (nq_tiles >> 1) : nq_tiles;
+    if constexpr (PAIR && LIST) {
+        // Die-aware work assignment.  The units that share a database split read the same blocks at about the same
+        // time; when they sit on both dies the second reader pulls every block across the die-to-die L2 fabric.
+        // Each pair therefore takes a ticket from its own die's counter (SM ids below 74: die 0) and the
+        // (tile, split) items are dealt so that a split's units all come from one die (even splits: die 0, odd
+        // splits: die 1; a die with more pairs than items takes the other die's last ones).  DRAM traffic is
+        // unchanged by this (the 2x comes from tiles with different split counts walking the database
+        // out of phase); the kernel is ~1% faster.
+        if (la.die_mode > 0) {
+            // (in the spare bytes behind the TMEM base holder: the pair variant has no room for static shared memory)
+            int& s_unit = *reinterpret_cast<int*>(smem + L::tmem_off + 8);
+            const int U = (int)(gridDim.x >> 1), T = units_per_split;
+            if (threadIdx.x == 0 && cta_rank == 0) {
+                uint32_t smid;
+                asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+                const int die = la.die_mode == 1 ? (smid >= (uint32_t)(kNumSMs / 2) ? 1 : 0)
+                              : la.die_mode == 2 ? (int)(smid & 1u) : (int)((smid >> 1) & 1u);
+                auto items_of = [&](int dd) {   // units u in [0, U) whose split u / T has parity dd
+                    int cnt = 0;
+                    for (int sidx = dd; sidx * T < U; sidx += 2) cnt += (U - sidx * T) < T ? (U - sidx * T) : T;
+                    return cnt;
+                };
+                auto item = [&](int dd, int t) { return (2 * (t / T) + dd) * T + (t % T); };
+                const int mine = items_of(die), other = items_of(die ^ 1);
+                const int t = atomicAdd(la.die_ctr + die, 1);
+                int u;
+                if (t < mine) {
+                    u = item(die, t);
+                } else {
+                    const int o = atomicAdd(la.die_ctr + 2, 1);
+                    u = item(die ^ 1, other - 1 - o);
+                }
+                if (atomicAdd(la.die_ctr + 3, 1) == U - 1) {   // every pair has its item: re-arm the counters
+                    la.die_ctr[0] = 0; la.die_ctr[1] = 0; la.die_ctr[2] = 0; la.die_ctr[3] = 0;
+                }
+                s_unit = u;
+                uint32_t remote;
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(&s_unit)), "r"(1));
+                asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(remote), "r"(u) : "memory");
+            }
+            cluster_sync_all();
+            unit = s_unit;
+        }
+    }
     const int qt = PAIR ? (unit % units_per_split) * 2 + (int)cta_rank : unit % units_per_split;
     const int split = unit / units_per_split;
     // Units (CTAs / CTA pairs) are dealt round-robin over the query tiles, so when the unit count is not a
@@ -350,6 +410,7 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            const uint64_t l2_keep_policy = (PAIR && la.l2_keep) ? l2_policy_evict_last() : 0ull;
             if constexpr (PAIR) {
                 // both CTAs load their own 128-query tile; the bytes of both are credited to the leader's barrier
                 if (cta_rank == 0) mbar_expect_tx(q_full, (uint32_t)(2 * kblocks * A_BYTES));
@@ -368,7 +429,8 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                     if constexpr (PAIR) {
                         // this CTA's half of the 256-row block; the leader's full barrier collects both halves
                         if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * kStageBytes);
-                        tma_load_2d_pair(sa, &map_x, kb * BK, row0 + (int)cta_rank * (BN / 2), &full_bar[stage]);
+                        if (la.l2_keep) tma_load_2d_pair_hint(sa, &map_x, kb * BK, row0 + (int)cta_rank * (BN / 2), &full_bar[stage], l2_keep_policy);
+                        else tma_load_2d_pair(sa, &map_x, kb * BK, row0 + (int)cta_rank * (BN / 2), &full_bar[stage]);
                         if (++stage == STAGES) {
                             stage = 0;
                             phase ^= 1;
@@ -1161,6 +1223,20 @@ int launch_tensor_scan(const __nv_bfloat16* scan, int64_t dpad, const float* nor
                 if (period != 2 && period != 4 && period != 8 && period != 16 && period != 32 && period != 64 && period != 128) period = 32;
             }
             la.period_mask = period - 1;
+            static int keep = -1;
+            if (keep < 0) {
+                const char* e = getenv("B200FLAT_L2_KEEP");
+                keep = (e && e[0] == '1') ? 1 : 0;
+            }
+            la.l2_keep = keep;
+            static int die_mode = -1;
+            if (die_mode < 0) {
+                const char* e = getenv("B200FLAT_DIE_MODE");
+                die_mode = e ? atoi(e) : 1;   // same-box A/B at C2: 0.616 -> 0.610 ms
+                if (die_mode < 0 || die_mode > 3) die_mode = 1;
+            }
+            la.die_mode = lists.die_ctr ? die_mode : 0;
+            la.die_ctr = lists.die_ctr;
         }
         // lists.shared_thr was filled with 0x7f7f7f7f (3.39e38, "no information yet") by the query-prep kernel
         if (plan.pair_mode)

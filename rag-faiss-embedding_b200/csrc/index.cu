@@ -872,7 +872,8 @@ int b2f_index_search(b2f_index* ix, int64_t nq64, const float* q, int64_t k64, f
         }
         int32_t* fail_list = bump.take<int32_t>(nq);
         // [0] uncertified queries, [1] of which list overflows, [2..3] u64 list entries, [4] rescued by the extended pass
-        int32_t* counters = bump.take<int32_t>(8);
+        int32_t* counters = bump.take<int32_t>(16);   // [8..11]: ticket counters of K2's die-aware unit assignment
+        lists.die_ctr = counters + 8;
         B2F_TRY(refresh_host_stats(ix, st));
         for (int c0 = 0; c0 < nq; c0 += chunk_nq) {
             const int cn = nq - c0 < chunk_nq ? nq - c0 : chunk_nq;  // queries in this pass (the plan covers chunk_nq)
@@ -880,7 +881,7 @@ int b2f_index_search(b2f_index* ix, int64_t nq64, const float* q, int64_t k64, f
             // one launch: bf16 copy / norms of the queries, reset the shared thresholds, clear the counters (first pass)
             B2F_TRY(launch_prep_queries(qc, cn, nq_pad, ix->d, qb, ix->dpad, qnorm, qerr, qconst, ix->mu_set ? ix->centre : nullptr,
                                         reinterpret_cast<uint32_t*>(counters),
-                                        c0 == 0 ? 8 : 0, reinterpret_cast<uint32_t*>(lists.shared_thr),
+                                        c0 == 0 ? 16 : 0, reinterpret_cast<uint32_t*>(lists.shared_thr),
                                         plan.list_mode ? (int64_t)nq_pad * plan.nlists : 0, st));
             B2F_TRY(main_event(0));
             B2F_TRY(launch_tensor_scan(ix->scan, ix->dpad, ix->norms, ix->ntotal, ix->metric, qb, cn, nq_pad, plan, pk, pi, lists, st));
