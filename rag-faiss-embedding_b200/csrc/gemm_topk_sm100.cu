@@ -235,6 +235,7 @@ struct ListArgs {
     int early;           // 1: scheduled threshold refreshes happen before the wait for the tile's accumulator
     int period_mask;     // refresh every (period_mask + 1) tiles after the first 32 (power of two - 1)
     int l2_keep;         // 1: database blocks are loaded with an evict_last L2 policy (several units read each block)
+    int strided;         // 1: a split walks every nsplits-th database tile (all units sweep the database together)
     int die_mode;        // > 0: die-aware unit assignment (pair kernel); the value selects the smid -> die guess
     int32_t* die_ctr;    // [4] ticket counters (zero between launches)
 };
@@ -365,8 +366,16 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     const int my_nsplits = LIST ? total_units / units_per_split + ((unit % units_per_split) < (total_units % units_per_split) ? 1 : 0)
                                 : nsplits;
     const int64_t ntiles = (n + BN - 1) / BN;
-    const int64_t t_begin = ntiles * split / my_nsplits, t_end = ntiles * (split + 1) / my_nsplits;
-    const int my_tiles = (int)(t_end - t_begin);
+    // Which database tiles a split walks.  Contiguous ranges (HEAP mode), or -- LIST mode -- every my_nsplits-th tile
+    // starting at `split`: then all units sweep the database front to back together, the tiles with one split more
+    // or less than the others included, and a block that several units need is still in L2 when the later ones
+    // arrive (with contiguous ranges a 19-way and an 18-way split of the same rows are walked out of phase and every
+    // block is fetched from DRAM once per group: ncu 1.51 GB for the 768 MB copy at nq = 1024).
+    const bool strided = LIST && la.strided;
+    const int64_t t_begin = strided ? split : ntiles * split / my_nsplits;
+    const int64_t t_step = strided ? my_nsplits : 1;
+    const int my_tiles = strided ? (int)(ntiles > split ? (ntiles - split + my_nsplits - 1) / my_nsplits : 0)
+                                 : (int)(ntiles * (split + 1) / my_nsplits - ntiles * split / my_nsplits);
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_q)) : "memory");
@@ -422,7 +431,7 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 for (int kb = 0; kb < kblocks; kb++) tma_load_2d(smem + L::q_off + (size_t)kb * A_BYTES, &map_q, kb * BK, qt * BM, q_full);
             }
             for (int t = 0; t < my_tiles; t++) {
-                const int row0 = (int)((t_begin + t) * BN);
+                const int row0 = (int)((t_begin + t * t_step) * BN);
                 for (int kb = 0; kb < kblocks; kb++) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + L::stages_off + (size_t)stage * kStageBytes;
@@ -492,7 +501,7 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             const int acc = t & 1;
             const uint32_t acc_phase = (t >> 1) & 1;
             mbar_wait(PAIR ? &bias_empty[acc] : &tmem_empty[acc], acc_phase ^ 1);
-            const int64_t row0 = (t_begin + t) * BN;
+            const int64_t row0 = (t_begin + t * t_step) * BN;
 #pragma unroll
             for (int j = 0; j < BN / 32; j++) {
                 const int64_t row = row0 + j * 32 + lane;
@@ -669,7 +678,7 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 mbar_wait(&bias_full[acc], acc_phase);
                 mbar_wait(&tmem_full[acc], acc_phase);
                 tc_fence_after();
-                const int32_t row0 = (int32_t)((t_begin + t) * BN) + half * COLS;
+                const int32_t row0 = (int32_t)((t_begin + t * t_step) * BN) + half * COLS;
                 const float* tb = bias + acc * BN + half * COLS;
                 const uint32_t tile_taddr = lane_taddr + (uint32_t)(acc * BN + half * COLS);
                 uint32_t ra[32], rb[32];
@@ -728,7 +737,7 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 mbar_wait(&bias_full[acc], acc_phase);
                 mbar_wait(&tmem_full[acc], acc_phase);
                 tc_fence_after();
-                const int32_t row0 = (int32_t)((t_begin + t) * BN);
+                const int32_t row0 = (int32_t)((t_begin + t * t_step) * BN);
                 const float* tb = bias + acc * BN;
                 const uint32_t tile_taddr = lane_taddr + (uint32_t)(acc * BN);
 #pragma unroll 1
@@ -1235,6 +1244,12 @@ int launch_tensor_scan(const __nv_bfloat16* scan, int64_t dpad, const float* nor
                 die_mode = e ? atoi(e) : 1;   // same-box A/B at C2: 0.616 -> 0.610 ms
                 if (die_mode < 0 || die_mode > 3) die_mode = 1;
             }
+            static int strided = -1;
+            if (strided < 0) {
+                const char* e = getenv("B200FLAT_STRIDED_SPLITS");
+                strided = (e && e[0] == '0') ? 0 : 1;   // same-box A/B at C2: DRAM read 1.52 GB -> 0.87 GB, 0.594 -> 0.575 ms
+            }
+            la.strided = strided;
             la.die_mode = lists.die_ctr ? die_mode : 0;
             la.die_ctr = lists.die_ctr;
         }
