@@ -200,6 +200,12 @@ B2F_API int b2f_synth_rows(uint64_t seed, int64_t row0, int64_t nrows, int32_t d
 B2F_API int b2f_index_add_synth(b2f_index* idx, uint64_t seed, int64_t row0, int64_t nrows, int32_t normalize);
 
 /* ---- diagnostics ------------------------------------------------------------------------------ */
+/* How the tensor path would run a search of nq queries, k neighbours, on n rows of dimension d (pure host logic,
+ * no GPU needed): out[0] = k' (0: tensor path unavailable), out[1] = queries per pass, out[2] = passes,
+ * out[3] = 1 LIST / 0 HEAP selection, out[4] = 1 when CTA pairs are used, out[5] = units (CTAs or pairs) per pass,
+ * out[6] = smallest number of database splits of a query tile, out[7] = candidate lists per query,
+ * out[8] = j (rows each list vouches for), out[9] = entries per list, out[10] = query tiles per pass.   */
+B2F_API int b2f_plan_describe(int64_t nq, int64_t n, int32_t d, int64_t k, int32_t slack, int32_t out[11]);
 B2F_API int b2f_index_stats(const b2f_index* idx, b2f_stats* out);
 B2F_API const char* b2f_last_error(void);
 B2F_API int b2f_version(void);

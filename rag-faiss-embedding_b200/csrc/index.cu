@@ -524,6 +524,31 @@ int32_t b2f_index_metric(const b2f_index* ix) { return ix ? ix->metric : -1; }
 int32_t b2f_index_storage(const b2f_index* ix) { return ix ? ix->storage : -1; }
 int32_t b2f_index_device(const b2f_index* ix) { return ix ? ix->device : -1; }
 
+int b2f_plan_describe(int64_t nq, int64_t n, int32_t d, int64_t k, int32_t slack, int32_t out[11]) {
+    if (!out || nq <= 0 || n <= 0 || d <= 0 || k <= 0 || nq > (1 << 24)) {
+        set_error("plan_describe: bad arguments");
+        return B2F_EINVAL;
+    }
+    for (int i = 0; i < 11; i++) out[i] = 0;
+    const int kp = k <= 1024 ? tensor_kprime((int)k, slack) : 0;
+    if (kp <= 0) return B2F_OK;
+    TensorScanPlan plan{};
+    const int chunk = plan_tensor_chunked((int)nq, n, d, kp, &plan);
+    if (chunk <= 0) return B2F_OK;
+    out[0] = kp;
+    out[1] = chunk;
+    out[2] = (int32_t)((nq + chunk - 1) / chunk);
+    out[3] = plan.list_mode;
+    out[4] = plan.pair_mode;
+    out[5] = plan.units;
+    out[6] = plan.nsplits;
+    out[7] = plan.nlists;
+    out[8] = plan.list_j;
+    out[9] = plan.list_cap;
+    out[10] = plan.nq_tiles;
+    return B2F_OK;
+}
+
 int b2f_index_stats(const b2f_index* cix, b2f_stats* out) {
     if (!cix || !out) {
         set_error("NULL argument");

@@ -139,3 +139,39 @@ def test_store_mirror_host_logic(monkeypatch, tmp_path, golden):
     for row in (0, 7, 22):
         d, ids = s3.search(xb[row], k=5)
         assert ids == [golden["mapping"][i] for i in case["ids"][row]]
+
+
+def test_tensor_path_planner():
+    """Host logic of the tensor path (no GPU needed): k', query chunking for feasibility and balance, the
+    LIST / HEAP choice, CTA pairs, list geometry."""
+    from rag_faiss_embedding_b200 import _capi
+
+    lib = _capi.load()
+
+    def plan(nq, n, d, k, slack=0):
+        out = (ctypes.c_int32 * 11)()
+        assert lib.b2f_plan_describe(nq, n, d, k, slack, out) == 0
+        return dict(zip(["kp", "chunk", "passes", "list", "pair", "units", "ns_min", "nlists", "j", "cap", "tiles"], list(out)))
+
+    c2 = plan(1024, 1_000_000, 384, 10)               # BASELINE config 2
+    assert c2["kp"] == 32 and c2["passes"] == 1 and c2["list"] == 1 and c2["pair"] == 1
+    assert c2["units"] == 74 and c2["tiles"] == 8 and c2["ns_min"] == 18 and c2["j"] == 1
+    big = plan(4096, 1_000_000, 384, 10)              # 16 pair tiles over 74 pairs: two balanced passes of 8
+    assert big["passes"] == 2 and big["chunk"] == 2048 and big["ns_min"] == 9 and big["pair"] == 1
+    c3 = plan(4096, 10_000_000, 768, 100)             # k' = 192 caps a pass (j <= 16); d = 768 rules out the Q-resident pair kernel
+    assert c3["kp"] == 192 and c3["passes"] >= 2 and c3["pair"] == 0 and c3["j"] <= 16 and c3["list"] == 1
+    one = plan(1, 1_000_000, 384, 10)                 # one tile: every SM streams its own split
+    assert one["units"] == 148 and one["passes"] == 1 and one["nlists"] == 296 and one["j"] == 1
+    assert plan(64, 1_000_000, 384, 200)["kp"] == 0   # k' > 256: the exact scan serves it
+    assert plan(64, 1_000_000, 384, 100, slack=28)["kp"] == 128
+    tiny = plan(64, 100, 64, 10)                      # a single database tile: HEAP selection
+    assert tiny["kp"] == 32 and tiny["list"] == 0
+    small = plan(64, 300, 64, 10)                     # two database tiles: one LIST split per query tile
+    assert small["list"] == 1 and small["ns_min"] == 1
+    for nq in (2, 127, 129, 300, 1000, 5000, 20000):
+        for n in (5_000, 125_000, 12_500_000):
+            p = plan(nq, n, 384, 10)
+            assert p["kp"] == 32 and p["chunk"] * p["passes"] >= nq
+            if p["list"]:   # one wave, shared thresholds need every unit resident
+                assert p["units"] <= (74 if p["pair"] else 148) and p["j"] <= 16 and p["cap"] >= 128
+                assert p["nlists"] * p["j"] >= 1
