@@ -374,21 +374,34 @@ int plan_tensor_chunked(int nq, int64_t n, int d, int kp, TensorScanPlan* plan) 
     int best_chunk = feasible;
     double best_cost = 1e30;
     const char* nb = getenv("B200FLAT_NO_BALANCE");   // diagnostics: "1" = feasibility chunking only
-    const int max_m = (nb && nb[0] == '1') ? 1 : 8;
-    for (int m = 1; m <= max_m; m++) {
+    const bool balance = !(nb && nb[0] == '1');
+    // candidates: 1..8 equal passes, and the fixed pass sizes that fill one wave of pairs (74 / 37 pair tiles) or
+    // give every tile many splits -- so that very large batches are cut into LIST-mode passes instead of falling
+    // into the multi-wave HEAP selection (the first version of K2, ~6x slower per query)
+    int cands[12];
+    int nc = 0;
+    for (int m = 1; m <= (balance ? 8 : 1); m++) {
         int chunk = (nq + m - 1) / m;
         chunk = (chunk + 255) / 256 * 256;   // whole pair tiles
-        if (chunk > feasible) {
-            if (m == 1) chunk = feasible;
-            else continue;
-        }
-        if (chunk < 256 && m > 1) break;
+        if (chunk > feasible) chunk = m == 1 ? feasible : 0;
+        if (chunk >= 256 || m == 1) cands[nc++] = chunk;
+    }
+    if (balance) {
+        const int fixed[4] = {74 * 256, 37 * 256, 4096, 2048};
+        for (int i = 0; i < 4; i++)
+            if (fixed[i] < nq && fixed[i] <= feasible) cands[nc++] = fixed[i];
+    }
+    for (int i = 0; i < nc; i++) {
+        const int chunk = cands[i];
+        if (chunk <= 0) continue;
         TensorScanPlan p{};
         if (plan_tensor_scan(chunk, n, d, kp, &p) != B2F_OK) continue;
         const int passes = (nq + chunk - 1) / chunk;
-        const double t_mma = (double)n / p.nsplits * 128.0 * dpad * 2.0 / kSmRate;  // slowest unit, per SM
+        const double waves = p.list_mode ? 1.0 : (double)((p.units + kNumSMs - 1) / kNumSMs);
+        double t_mma = (double)n / p.nsplits * 128.0 * dpad * 2.0 / kSmRate * waves;  // slowest unit, per SM
+        if (!p.list_mode) t_mma *= 6.0;   // per-thread heaps instead of shared-threshold lists
         const double cost = passes * ((t_mma > t_hbm ? t_mma : t_hbm) + kPassOverhead);
-        if (cost < best_cost * 0.97) {  // a new pass has to buy at least 3%
+        if (cost < best_cost * 0.97) {  // a new candidate has to buy at least 3%
             best_cost = cost;
             best_chunk = chunk;
         }

@@ -168,6 +168,8 @@ def test_tensor_path_planner():
     assert tiny["kp"] == 32 and tiny["list"] == 0
     small = plan(64, 300, 64, 10)                     # two database tiles: one LIST split per query tile
     assert small["list"] == 1 and small["ns_min"] == 1
+    huge = plan(100_000, 1_000_000, 384, 10)          # far more than one wave of query tiles: LIST-mode passes, not HEAP
+    assert huge["list"] == 1 and huge["pair"] == 1 and huge["passes"] * huge["chunk"] >= 100_000 and huge["chunk"] <= 74 * 256
     for nq in (2, 127, 129, 300, 1000, 5000, 20000):
         for n in (5_000, 125_000, 12_500_000):
             p = plan(nq, n, 384, 10)

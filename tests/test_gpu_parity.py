@@ -316,6 +316,21 @@ def test_centred_scan_copy_certifies_embedding_like_data(m):
     _check(D, I, *orc.np_search_f64(xb[:5000] - 3.0, xq[:64] - 3.0, k, 1), 1)
 
 
+def test_very_large_batch_is_cut_into_list_passes(m):
+    """20000 queries are far more than one wave of query tiles: the planner cuts the batch into LIST-mode passes
+    (not the multi-wave HEAP selection); results must be exact and independent of the cut."""
+    n, d, nq, k = 30000, 64, 20000, 10
+    xb = orc.c_synth_rows(1234, 0, n, d)
+    xq = orc.c_synth_rows(5678, 0, nq, d)
+    ix = _make(m, xb, 1).set_search_params(algo=m.ALGO_TENSOR)
+    D, I = ix.search(xq, k)
+    _check(D, I, *orc.np_search_f64(xb, xq, k, 1), 1)
+    st = ix.stats()
+    assert st["last_algo"] == m.ALGO_TENSOR and st["overflow_queries"] == 0, st
+    D2, I2 = ix.search(xq[7000:7300], k)
+    assert np.array_equal(I2, I[7000:7300]) and np.allclose(D2, D[7000:7300], rtol=1e-6)
+
+
 def test_random_operation_sequence(m, tmp_path):
     """Seeded fuzz over the index life cycle: adds (host arrays and device tensors, growing the storage several
     times), searches (host / device buffers, both paths, changing batch sizes and k, so the workspace is
