@@ -177,3 +177,24 @@ def test_tensor_path_planner():
             if p["list"]:   # one wave, shared thresholds need every unit resident
                 assert p["units"] <= (74 if p["pair"] else 148) and p["j"] <= 16 and p["cap"] >= 128
                 assert p["nlists"] * p["j"] >= 1
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU restatement timed on the host cores) prints ONE JSON line with the keys
+    the driver reads; runs without a GPU."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                          "--workload", "c2_nq1"], capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    assert j["impl"] == "reference" and j["unit"] == "queries/sec" and j["higher_is_better"] is True and j["value"] > 0
+    assert j["steps"] == 1 and j["n_gpus"] == 1 and j["vs_baseline"] is None and j["data"] == "synthetic"
+    assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1 and j["cpu_baseline"]["value"] == j["value"]
+    assert j["e2e"] == {"value": j["value"], "unit": "queries/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in j["config"]
