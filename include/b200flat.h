@@ -77,7 +77,7 @@ typedef struct b2f_search_params {
     int32_t scan_max_nq;   /* AUTO: largest nq served by the streaming scan (0 = default: 1, the reference's nq,
                               for fp32 storage; none for bf16 storage, where the tensor path is always faster) */
     int32_t slack;         /* tensor path: extra coarse candidates per query kept for the exact re-rank
-                              (0 = default: k' = min(max(k + 22, 2k), cap)) */
+                              (0 = default: k' = k + max(22, ceil(0.9 k)), rounded up to 32 / 64 / a multiple of 8, <= 256) */
     int32_t certify;       /* tensor path: 1 (default when 0 is passed via NULL params) = prove from the
                               bf16 rounding bound that no non-candidate can beat the k-th re-ranked
                               result; queries that fail are re-run through the exact scan. -1 = off */
@@ -173,6 +173,12 @@ B2F_API int b2f_exchange_connect(b2f_exchange* ex, const void* handles_world_x_6
 B2F_API int64_t b2f_exchange_slot_bytes(const b2f_exchange* ex);
 B2F_API int b2f_exchange_merge(b2f_exchange* ex, const void* msg, int64_t msg_bytes, int32_t metric, int64_t nq, int64_t k,
                        int64_t off_i, float* D, int64_t* I, void* stream);
+/* The whole sharded step behind ONE call: search this rank's shard (labels + params->id_offset) straight into
+ * the exchange's own message buffer, then the push + flag + merge kernel above, all enqueued on `stream` -- no host
+ * allocation, no second library call.  Collective: every rank calls it once per search with the same nq / k.
+ * q: [nq, d] fp32, D: [nq, k] fp32, I: [nq, k] int64, device buffers.                                     */
+B2F_API int b2f_exchange_search(b2f_exchange* ex, b2f_index* idx, int64_t nq, const float* q, int64_t k, float* D,
+                        int64_t* I, void* stream, const b2f_search_params* params);
 B2F_API int b2f_exchange_destroy(b2f_exchange* ex);
 
 /* ---- fused encoder epilogue (replaces vectorization.py:44-47, rag_datastore_manager.py:129-132:

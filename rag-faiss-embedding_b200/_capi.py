@@ -88,6 +88,7 @@ PROTOTYPES = {
     "b2f_exchange_connect": (ctypes.c_int, [_vp, _vp]),
     "b2f_exchange_slot_bytes": (_i64, [_vp]),
     "b2f_exchange_merge": (ctypes.c_int, [_vp, _vp, _i64, _i32, _i64, _i64, _i64, _vp, _vp, _vp]),
+    "b2f_exchange_search": (ctypes.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, ctypes.POINTER(SearchParams)]),
     "b2f_exchange_destroy": (ctypes.c_int, [_vp]),
     "b2f_pool_normalize": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _i32, _vp]),
     "b2f_index_add_pooled": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp]),

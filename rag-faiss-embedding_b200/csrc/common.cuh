@@ -6,6 +6,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <mutex>
+
 #include "../../include/b200flat.h"
 
 namespace b2f {
@@ -148,6 +150,10 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p) {
 // cudaFuncSetAttribute / occupancy are per device: launchers cache what they configured per device, so one
 // process may drive indexes on several GPUs.
 constexpr int kMaxDevices = 64;
+// Launchers keep small per-device caches (configured shared-memory sizes, occupancy).  The index mutex is per
+// index, so two indexes searched from two threads reach the same launcher concurrently: the caches are guarded by
+// one process-wide mutex (taken only around the cache look-up, never around a launch).
+std::mutex& launch_cache_mutex();
 inline int current_device_slot() {
     int d = 0;
     if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= kMaxDevices) d = 0;

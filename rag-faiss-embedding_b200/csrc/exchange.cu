@@ -6,13 +6,18 @@
 //      peer mappings (cudaIpc; NVLink / NVSwitch),
 //   2. the last CTA to finish pushing publishes this search's sequence number into every peer's flag word
 //      (system-scope release),
-//   3. every CTA waits until the flags of all ranks show the sequence number (acquire), and
-//   4. merges its share of the queries straight out of the receive buffer (one warp per query, faiss
-//      ordering, -1 padding) into the caller's (D, I).
+//   3. every CTA waits until the flags of all PEER ranks show the sequence number (acquire), and
+//   4. merges its share of the queries (one warp per query, faiss ordering, -1 padding) into the caller's
+//      (D, I): the peers' parts straight out of the receive buffer, its own part straight out of its message.
 // Receive buffers and flags are double buffered by the parity of the sequence number: a rank can only start
 // search s + 2 after it merged s + 1, which needed every peer's push of s + 1, which those peers issued after
 // their merge of s -- so no slot is overwritten while a slower peer still reads it.  Nothing here depends on
-// co-residency of the whole grid: pushes never wait, and waiting CTAs only wait for pushes.
+// co-residency of this rank's own grid: pushes never wait, a CTA waits for PEER flags only (its own part is
+// local), so a co-running kernel that keeps some of this grid's CTAs off the SMs cannot stall the ones that run.
+//
+// b2f_exchange_search() is the whole sharded step behind one C call: the local search writes (D, I) straight into
+// the exchange's own message buffer, then the kernel above runs on the same stream -- no allocation, no second
+// library call on the host.
 #include <string.h>
 
 #include <new>
@@ -31,6 +36,7 @@ struct b2f_exchange {
     char** peer_dev = nullptr;         // device copy of the table
     uint32_t seq = 0;
     bool connected = false;
+    char* msg = nullptr;               // [2][slot_bytes] this rank's outgoing messages (b2f_exchange_search), by sequence parity
 };
 
 namespace {
@@ -62,14 +68,14 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 __global__ void __launch_bounds__(256) exchange_merge_kernel(const ExArgs a) {
     const int par = (int)(a.seq & 1u);
     const int64_t buf_off = (int64_t)par * a.world * a.slot_bytes;
-    // ---- 1. push: my message into slot [rank] of every rank's receive buffer (own copy included) -----------
+    // ---- 1. push: my message into slot [rank] of every PEER's receive buffer -------------------------------
     {
         const int64_t nvec = a.msg_bytes >> 4;   // messages are padded to 16 bytes
         const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
         const uint4* s = reinterpret_cast<const uint4*>(a.src);
         for (int64_t i = tid; i < nvec; i += nth) {
             const uint4 v = s[i];
-            for (int r = 0; r < a.world; r++) {
+            for (int r = 1; r < a.world; r++) {              // peers only: this rank merges its own part from `src`
                 const int dst = (a.rank + r) % a.world;   // spread the NVLink traffic: every rank starts at a different peer
                 reinterpret_cast<uint4*>(a.peer[dst] + buf_off + (int64_t)a.rank * a.slot_bytes)[i] = v;
             }
@@ -86,13 +92,13 @@ __global__ void __launch_bounds__(256) exchange_merge_kernel(const ExArgs a) {
         if (s_last) *ctr = 0u;   // self-cleaning for the next call (stream ordered)
     }
     __syncthreads();
-    if (s_last && threadIdx.x < a.world) {
+    if (s_last && threadIdx.x < a.world && (int)threadIdx.x != a.rank) {
         __threadfence_system();
         uint32_t* f = reinterpret_cast<uint32_t*>(a.peer[threadIdx.x] + a.flags_off) + par * a.world + a.rank;
         st_release_sys(f, a.seq);
     }
-    // ---- 3. wait for every rank's push of this search ------------------------------------------------------
-    if (threadIdx.x < a.world) {
+    // ---- 3. wait for every PEER's push of this search (never for this rank's own grid) ------------------------
+    if (threadIdx.x < a.world && (int)threadIdx.x != a.rank) {
         const uint32_t* f = reinterpret_cast<const uint32_t*>(a.peer[a.rank] + a.flags_off) + par * a.world + threadIdx.x;
         // bounded: a peer that died must surface as a CUDA error at the next synchronisation, not as a hung GPU
         const long long t0 = clock64();
@@ -108,8 +114,9 @@ __global__ void __launch_bounds__(256) exchange_merge_kernel(const ExArgs a) {
     const char* base = a.peer[a.rank] + buf_off;
     for (int64_t q = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); q < a.nq; q += (int64_t)gridDim.x * wpb) {
         const bool have = lane < a.world;
-        const float* dl = reinterpret_cast<const float*>(base + (int64_t)(have ? lane : 0) * a.slot_bytes) + q * a.k;
-        const int64_t* il = reinterpret_cast<const int64_t*>(base + (int64_t)(have ? lane : 0) * a.slot_bytes + a.off_i) + q * a.k;
+        const char* part = (have && lane != a.rank) ? base + (int64_t)lane * a.slot_bytes : a.src;   // own part: the message itself
+        const float* dl = reinterpret_cast<const float*>(part) + q * a.k;
+        const int64_t* il = reinterpret_cast<const int64_t*>(part + a.off_i) + q * a.k;
         int pos = 0;
         float hk = FLT_MAX;
         int64_t hi = -1;
@@ -174,6 +181,7 @@ int b2f_exchange_create(int32_t device, int32_t rank, int32_t world, int64_t slo
     cudaError_t e = cudaMalloc(&ex->local, ex->local_bytes);
     if (e == cudaSuccess) e = cudaMemset(ex->local, 0, ex->local_bytes);
     if (e == cudaSuccess) e = cudaMalloc(&ex->peer_dev, sizeof(char*) * world);
+    if (e == cudaSuccess) e = cudaMalloc(&ex->msg, 2 * (size_t)ex->slot_bytes);
     cudaIpcMemHandle_t h;
     if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, ex->local);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
@@ -182,6 +190,7 @@ int b2f_exchange_create(int32_t device, int32_t rank, int32_t world, int64_t slo
         set_error("exchange_create: %s", cudaGetErrorString(e));
         cudaFree(ex->local);
         cudaFree(ex->peer_dev);
+        cudaFree(ex->msg);
         delete ex;
         return B2F_ECUDA;
     }
@@ -252,6 +261,32 @@ int b2f_exchange_merge(b2f_exchange* ex, const void* msg, int64_t msg_bytes, int
     return B2F_OK;
 }
 
+int b2f_exchange_search(b2f_exchange* ex, b2f_index* idx, int64_t nq, const float* q, int64_t k, float* D, int64_t* I,
+                        void* stream, const b2f_search_params* params) {
+    if (!ex || !ex->connected || !idx || nq < 0 || k <= 0 || (nq > 0 && (!q || !D || !I))) {
+        set_error("exchange_search: bad arguments");
+        return B2F_EINVAL;
+    }
+    if (nq == 0) return B2F_OK;
+    const int64_t off_i = (nq * k * 4 + 15) / 16 * 16;
+    const int64_t msg_bytes = (off_i + nq * k * 8 + 15) / 16 * 16;
+    if (msg_bytes > ex->slot_bytes) {
+        set_error("exchange_search: message of %lld bytes exceeds the slot size %lld (re-create the exchange)", (long long)msg_bytes,
+                  (long long)ex->slot_bytes);
+        return B2F_EINVAL;
+    }
+    if (b2f_index_device(idx) != ex->device) {
+        set_error("exchange_search: the index lives on device %d, the exchange on device %d", b2f_index_device(idx), ex->device);
+        return B2F_EINVAL;
+    }
+    // the local search writes its faiss-formatted (D, I) straight into the outgoing message (double buffered by the
+    // parity of the next sequence number, so a caller that alternates streams cannot overwrite a message in flight)
+    char* msg = ex->msg + (size_t)((ex->seq + 1) & 1u) * (size_t)ex->slot_bytes;
+    B2F_TRY(b2f_index_search(idx, nq, q, k, reinterpret_cast<float*>(msg), reinterpret_cast<int64_t*>(msg + off_i), B2F_MEM_DEVICE,
+                             stream, params));
+    return b2f_exchange_merge(ex, msg, msg_bytes, b2f_index_metric(idx), nq, k, off_i, D, I, stream);
+}
+
 int b2f_exchange_destroy(b2f_exchange* ex) {
     if (!ex) return B2F_OK;
     cudaSetDevice(ex->device);
@@ -260,6 +295,7 @@ int b2f_exchange_destroy(b2f_exchange* ex) {
         if (r != ex->rank && ex->peer[r]) cudaIpcCloseMemHandle(ex->peer[r]);
     cudaFree(ex->local);
     cudaFree(ex->peer_dev);
+    cudaFree(ex->msg);
     delete ex;
     return B2F_OK;
 }

@@ -1076,11 +1076,14 @@ static int launch_k2(const CUtensorMap& mq, const CUtensorMap& mx, const float* 
     constexpr size_t smem = Smem < LIST ? 0 : KP, PAIR ? STAGES_PAIR : (QRES ? STAGES_QRES : (LIST ? STAGES_LIST : STAGES_HEAP)),
                      QRES ? QRES_MAX_KB : 0, PAIR > ::alloc;
     static_assert(smem <= 232448, "shared memory budget exceeded");
-    static bool configured[kMaxDevices] = {};
-    const int dev = current_device_slot();
-    if (!configured[dev]) {
-        B2F_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[dev] = true;
+    {
+        static bool configured[kMaxDevices] = {};
+        const int dev = current_device_slot();
+        std::lock_guard<std::mutex> lk(launch_cache_mutex());
+        if (!configured[dev]) {
+            B2F_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured[dev] = true;
+        }
     }
     if constexpr (PAIR) {
         cudaLaunchConfig_t cfg{};
@@ -1290,12 +1293,15 @@ int launch_merge_lists(const TensorScanLists& lists, int nq, const TensorScanPla
     if (cap_entries > k2::MERGE_MAX) cap_entries = k2::MERGE_MAX;
     const int cap_c = cap_entries > k2::RANK_MAX ? cap_entries : k2::RANK_MAX;
     const size_t smem = (size_t)cap_c * 8 + (size_t)k2::KP_MAX * 8 + (size_t)k2::RANK_MAX * 8 + (size_t)cap_entries * 2;
-    static bool configured[kMaxDevices] = {};
-    const int dev = current_device_slot();
-    if (!configured[dev]) {
-        B2F_CUDA(cudaFuncSetAttribute(k2::merge_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)((size_t)k2::MERGE_MAX * 10 + (size_t)k2::KP_MAX * 8 + (size_t)k2::RANK_MAX * 8)));
-        configured[dev] = true;
+    {
+        static bool configured[kMaxDevices] = {};
+        const int dev = current_device_slot();
+        std::lock_guard<std::mutex> lk(launch_cache_mutex());
+        if (!configured[dev]) {
+            B2F_CUDA(cudaFuncSetAttribute(k2::merge_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)((size_t)k2::MERGE_MAX * 10 + (size_t)k2::KP_MAX * 8 + (size_t)k2::RANK_MAX * 8)));
+            configured[dev] = true;
+        }
     }
     k2::merge_lists_kernel<<<nq, k2::MERGE_THREADS, smem, st>>>(reinterpret_cast<const uint2*>(lists.cand), lists.counts, lists.final_thr,
                                                                plan.nlists, plan.pair_mode ? 2 * k2::BM : k2::BM, plan.tile_units, plan.units,

@@ -26,6 +26,11 @@ void set_error(const char* fmt, ...) {
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+std::mutex& launch_cache_mutex() {
+    static std::mutex m;
+    return m;
+}
+
 }  // namespace b2f
 
 using namespace b2f;
@@ -61,6 +66,9 @@ struct b2f_index {
     cudaEvent_t ev_done = nullptr;    // recorded at the end of every search (searches return without synchronising)
     cudaStream_t last_stream = nullptr;
     bool search_recorded = false;
+    cudaEvent_t ev_ingest = nullptr;  // recorded behind every add on the stream it was enqueued on
+    cudaStream_t last_add_stream = nullptr;
+    bool add_recorded = false;
     // profiling: a ring of event sets so that timing never forces a host synchronisation inside a search
     struct ProfSlot {
         cudaEvent_t t0 = nullptr, t1 = nullptr;
@@ -89,8 +97,10 @@ struct DeviceGuard {
 
 int check_device(int device) {
     // cached: cudaGetDeviceProperties costs milliseconds and this runs on per-search entry points
+    static std::mutex cache_mu;   // indexes on several devices may be created from several threads
     static int cached_count = -1;
     static int cached_major[64];
+    std::lock_guard<std::mutex> cache_lk(cache_mu);
     if (cached_count < 0) {
         int n = 0;
         cudaError_t e = cudaGetDeviceCount(&n);
@@ -198,6 +208,9 @@ int ensure_capacity(b2f_index* ix, int64_t need) {
         return B2F_ENOMEM;
     }
     if (ix->ntotal > 0) {
+        // an ingest may still be pending on a caller stream (e.g. behind an encoder forward): its rows must have landed
+        // before they are copied into the new buffers
+        if (ix->add_recorded && ix->last_add_stream != ix->stream) B2F_CUDA(cudaStreamWaitEvent(ix->stream, ix->ev_ingest, 0));
         if (nrows) B2F_CUDA(cudaMemcpyAsync(nrows, ix->rows_f32, (size_t)ix->ntotal * ix->d * sizeof(float), cudaMemcpyDeviceToDevice, ix->stream));
         B2F_CUDA(cudaMemcpyAsync(nscan, ix->scan, (size_t)ix->ntotal * ix->dpad * sizeof(__nv_bfloat16), cudaMemcpyDeviceToDevice, ix->stream));
         B2F_CUDA(cudaMemcpyAsync(nnorm, ix->norms, (size_t)ix->ntotal * sizeof(float), cudaMemcpyDeviceToDevice, ix->stream));
@@ -249,6 +262,22 @@ int order_after(cudaStream_t waiter, cudaStream_t producer, b2f_index* ix) {
     }
     B2F_CUDA(cudaEventRecord(e, producer));
     B2F_CUDA(cudaStreamWaitEvent(waiter, e, 0));
+    return B2F_OK;
+}
+
+// Adds are enqueued on the caller's stream (a device-tensor add / add_pooled runs behind the encoder on torch's
+// stream) and return without synchronising.  Everything that reads rows, norms, stats or the centre on ANOTHER
+// stream -- searches, write, reconstruct, the stats refresh, the growth copies -- first waits for the latest add.
+int wait_ingest(b2f_index* ix, cudaStream_t st) {
+    if (ix->add_recorded && ix->last_add_stream != st) B2F_CUDA(cudaStreamWaitEvent(st, ix->ev_ingest, 0));
+    return B2F_OK;
+}
+int record_ingest(b2f_index* ix, cudaStream_t st) {
+    if (!ix->ev_ingest) B2F_CUDA(cudaEventCreateWithFlags(&ix->ev_ingest, cudaEventDisableTiming));
+    // an add on a new stream is ordered behind the previous add (both write stats / may share the workspace)
+    B2F_CUDA(cudaEventRecord(ix->ev_ingest, st));
+    ix->last_add_stream = st;
+    ix->add_recorded = true;
     return B2F_OK;
 }
 
@@ -495,6 +524,7 @@ int b2f_index_destroy(b2f_index* ix) {
     cudaFree(ix->totals);
     for (cudaEvent_t e : ix->ev) cudaEventDestroy(e);
     if (ix->ev_done) cudaEventDestroy(ix->ev_done);
+    if (ix->ev_ingest) cudaEventDestroy(ix->ev_ingest);
     for (auto& sl : ix->prof) {
         if (sl.t0) cudaEventDestroy(sl.t0);
         if (sl.t1) cudaEventDestroy(sl.t1);
@@ -515,6 +545,7 @@ int b2f_index_reset(b2f_index* ix) {
     ix->ntotal = 0;
     ix->mu_set = false;
     if (ix->search_recorded) B2F_CUDA(cudaEventSynchronize(ix->ev_done));
+    if (ix->add_recorded) B2F_CUDA(cudaEventSynchronize(ix->ev_ingest));
     B2F_CUDA(cudaMemsetAsync(ix->stats, 0, 2 * sizeof(float), ix->stream));
     B2F_CUDA(cudaStreamSynchronize(ix->stream));
     ix->stats_dirty = true;
@@ -633,6 +664,7 @@ int b2f_index_add(b2f_index* ix, int64_t n, const float* x, int32_t mem, void* s
     B2F_TRY(ensure_capacity(ix, ix->ntotal + n));
     cudaStream_t st = stream ? (cudaStream_t)stream : ix->stream;
     if (ix->search_recorded && ix->last_stream != st) B2F_CUDA(cudaStreamWaitEvent(st, ix->ev_done, 0));
+    B2F_TRY(wait_ingest(ix, st));
     if (mem == B2F_MEM_DEVICE) {
         B2F_TRY(add_device_rows(ix, x, n, st));
         ix->ntotal += n;
@@ -654,6 +686,7 @@ int b2f_index_add(b2f_index* ix, int64_t n, const float* x, int32_t mem, void* s
         }
     }
     ix->stats_dirty = true;
+    B2F_TRY(record_ingest(ix, st));
     if (mem == B2F_MEM_HOST) B2F_CUDA(cudaStreamSynchronize(st));
     return B2F_OK;
 }
@@ -669,6 +702,7 @@ int b2f_index_add_synth(b2f_index* ix, uint64_t seed, int64_t row0, int64_t nrow
     B2F_TRY(ensure_capacity(ix, ix->ntotal + nrows));
     cudaStream_t st = ix->stream;
     if (ix->search_recorded && ix->last_stream != st) B2F_CUDA(cudaStreamWaitEvent(st, ix->ev_done, 0));
+    B2F_TRY(wait_ingest(ix, st));
     if (ix->storage == B2F_STORE_F32) {
         float* dst = ix->rows_f32 + ix->ntotal * ix->d;
         B2F_TRY(launch_synth(seed, row0, nrows, ix->d, normalize, dst, st));
@@ -687,6 +721,7 @@ int b2f_index_add_synth(b2f_index* ix, uint64_t seed, int64_t row0, int64_t nrow
         }
     }
     ix->stats_dirty = true;
+    B2F_TRY(record_ingest(ix, st));
     B2F_CUDA(cudaStreamSynchronize(st));
     return B2F_OK;
 }
@@ -703,20 +738,32 @@ int b2f_index_add_pooled(b2f_index* ix, const float* hidden, const int64_t* mask
     B2F_TRY(ensure_capacity(ix, ix->ntotal + B));
     cudaStream_t st = stream ? (cudaStream_t)stream : ix->stream;
     if (ix->search_recorded && ix->last_stream != st) B2F_CUDA(cudaStreamWaitEvent(st, ix->ev_done, 0));
+    B2F_TRY(wait_ingest(ix, st));
+    // The pooled rows go through the SAME ingest kernel every other add uses: it derives the scan copy, the per-row
+    // bias of the tensor pass (L2: |x~'|^2, IP: -mu.x -- NOT a norm) and the stats for either storage mode and metric.
     if (ix->storage == B2F_STORE_F32) {
-        // pooled rows land in their final place; the derived data (centred bf16 copy, norms / biases, stats) comes
-        // from the same ingest kernel every other add uses (it needs the index's centre, fixed at the first add)
+        // pooled rows land in their final place
         float* dst = ix->rows_f32 + ix->ntotal * ix->d;
         B2F_TRY(launch_pool(hidden, mask, B, T, ix->d, pool, normalize, dst, nullptr, 0, nullptr, nullptr, st));
         ix->st.launches++;
         B2F_TRY(add_device_rows(ix, dst, B, st));
+        ix->ntotal += B;
     } else {
-        B2F_TRY(launch_pool(hidden, mask, B, T, ix->d, pool, normalize, nullptr, ix->scan + ix->ntotal * ix->dpad, ix->dpad,
-                            ix->norms + ix->ntotal, ix->stats, st));
-        ix->st.launches++;
+        // bf16 storage: pool fp32 chunks into the workspace, ingest from there
+        const int64_t chunk = (64LL << 20) / ((int64_t)ix->d * 4) > 0 ? (64LL << 20) / ((int64_t)ix->d * 4) : 1;
+        B2F_TRY(ensure_ws(ix, (size_t)(B < chunk ? B : chunk) * ix->d * 4 + 4096));
+        for (int64_t b0 = 0; b0 < B; b0 += chunk) {
+            const int64_t m = B - b0 < chunk ? B - b0 : chunk;
+            float* tmp = reinterpret_cast<float*>(ix->ws);
+            B2F_TRY(launch_pool(hidden + b0 * T * ix->d, mask ? mask + b0 * T : nullptr, m, T, ix->d, pool, normalize, tmp, nullptr, 0,
+                                nullptr, nullptr, st));
+            ix->st.launches++;
+            B2F_TRY(add_device_rows(ix, tmp, m, st));
+            ix->ntotal += m;
+        }
     }
-    ix->ntotal += B;
     ix->stats_dirty = true;
+    B2F_TRY(record_ingest(ix, st));
     return B2F_OK;
 }
 
@@ -764,13 +811,13 @@ int b2f_merge_topk(int32_t metric, int64_t nq, int64_t k, int32_t nparts, const 
     return launch_merge_faiss(metric, nq, k, nparts, D_parts, I_parts, nq * k * 4, nq * k * 8, D, I, (cudaStream_t)stream);
 }
 
+}  // extern "C"
+
 // ---- search ----------------------------------------------------------------------------------------
-int b2f_index_search(b2f_index* ix, int64_t nq64, const float* q, int64_t k64, float* D, int64_t* I, int32_t mem,
-                     void* stream, const b2f_search_params* params) {
-    if (!ix) {
-        set_error("index is NULL");
-        return B2F_EINVAL;
-    }
+// The caller holds ix->mu (search_pooled pools the queries into the index's buffer and searches them under ONE
+// lock, so a second thread cannot overwrite or re-allocate that buffer in between).
+static int search_locked(b2f_index* ix, int64_t nq64, const float* q, int64_t k64, float* D, int64_t* I, int32_t mem,
+                         void* stream, const b2f_search_params* params) {
     if (k64 <= 0) {
         set_error("k must be > 0 (faiss asserts k > 0)");
         return B2F_EINVAL;
@@ -787,7 +834,6 @@ int b2f_index_search(b2f_index* ix, int64_t nq64, const float* q, int64_t k64, f
     const int nq = (int)nq64, k = (int)k64;
     b2f_search_params P{};
     if (params) P = *params;
-    std::lock_guard<std::mutex> lk(ix->mu);
     DeviceGuard g(ix->device);
     if (!g.ok) {
         set_error("cudaSetDevice(%d) failed", ix->device);
@@ -795,6 +841,7 @@ int b2f_index_search(b2f_index* ix, int64_t nq64, const float* q, int64_t k64, f
     }
     cudaStream_t st = stream ? (cudaStream_t)stream : ix->stream;
     B2F_TRY(order_after(st, ix->stream, ix));
+    B2F_TRY(wait_ingest(ix, st));   // the latest add may sit on another stream (torch's, behind an encoder forward)
     // searches return without synchronising: a search on another stream must not reuse the workspace early
     if (ix->search_recorded && ix->last_stream != st) B2F_CUDA(cudaStreamWaitEvent(st, ix->ev_done, 0));
     const bool host = mem == B2F_MEM_HOST;
@@ -989,6 +1036,18 @@ int b2f_index_search(b2f_index* ix, int64_t nq64, const float* q, int64_t k64, f
     return B2F_OK;
 }
 
+extern "C" {
+
+int b2f_index_search(b2f_index* ix, int64_t nq, const float* q, int64_t k, float* D, int64_t* I, int32_t mem, void* stream,
+                     const b2f_search_params* params) {
+    if (!ix) {
+        set_error("index is NULL");
+        return B2F_EINVAL;
+    }
+    std::lock_guard<std::mutex> lk(ix->mu);
+    return search_locked(ix, nq, q, k, D, I, mem, stream, params);
+}
+
 int b2f_index_search_pooled(b2f_index* ix, const float* hidden, const int64_t* mask, int64_t B, int64_t T, int32_t pool,
                             int32_t normalize, int64_t k, float* D, int64_t* I, void* stream, const b2f_search_params* params) {
     if (!ix || B < 0 || (B > 0 && (!hidden || !D || !I))) {
@@ -997,8 +1056,8 @@ int b2f_index_search_pooled(b2f_index* ix, const float* hidden, const int64_t* m
     }
     if (B == 0) return B2F_OK;
     float* qbuf = nullptr;
+    std::lock_guard<std::mutex> lk(ix->mu);   // held across pooling AND the search: the pooled queries live in ix->qpool
     {
-        std::lock_guard<std::mutex> lk(ix->mu);
         DeviceGuard g(ix->device);
         if (!g.ok) {
             set_error("cudaSetDevice(%d) failed", ix->device);
@@ -1024,7 +1083,7 @@ int b2f_index_search_pooled(b2f_index* ix, const float* hidden, const int64_t* m
         B2F_TRY(launch_pool(hidden, mask, B, T, ix->d, pool, normalize, qbuf, nullptr, 0, nullptr, nullptr, st));
         ix->st.launches++;
     }
-    return b2f_index_search(ix, B, qbuf, k, D, I, B2F_MEM_DEVICE, stream, params);
+    return search_locked(ix, B, qbuf, k, D, I, B2F_MEM_DEVICE, stream, params);
 }
 
 int b2f_index_reconstruct(b2f_index* ix, int64_t i0, int64_t n, float* out, int32_t mem, void* stream) {
@@ -1041,6 +1100,8 @@ int b2f_index_reconstruct(b2f_index* ix, int64_t i0, int64_t n, float* out, int3
     DeviceGuard g(ix->device);
     cudaStream_t st = stream ? (cudaStream_t)stream : ix->stream;
     B2F_TRY(order_after(st, ix->stream, ix));
+    B2F_TRY(wait_ingest(ix, st));
+    if (ix->search_recorded && ix->last_stream != st) B2F_CUDA(cudaStreamWaitEvent(st, ix->ev_done, 0));  // shares the workspace
     const size_t bytes = (size_t)n * ix->d * 4;
     if (ix->storage == B2F_STORE_F32) {
         B2F_CUDA(cudaMemcpyAsync(out, ix->rows_f32 + i0 * ix->d, bytes, mem == B2F_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
@@ -1067,6 +1128,8 @@ int b2f_index_write(b2f_index* ix, const char* path) {
     }
     std::lock_guard<std::mutex> lk(ix->mu);
     DeviceGuard g(ix->device);
+    B2F_TRY(wait_ingest(ix, ix->stream));
+    if (ix->search_recorded && ix->last_stream != ix->stream) B2F_CUDA(cudaStreamWaitEvent(ix->stream, ix->ev_done, 0));
     FILE* f = fopen(path, "wb");
     if (!f) {
         set_error("could not open %s for writing", path);

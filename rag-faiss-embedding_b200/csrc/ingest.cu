@@ -239,11 +239,14 @@ int launch_pool(const float* hidden, const int64_t* mask, int64_t B, int64_t T, 
     // srow [d] + the mean path's partial sums [256 / (d/4)][d]
     const int nth = (d % 4 == 0 && d / 4 <= 256) ? 256 / (d / 4) : 0;
     const size_t smem = (size_t)d * 4 * (1 + (pool == B2F_POOL_MEAN ? nth : 0));
-    static size_t configured[kMaxDevices] = {};
-    const int dev = current_device_slot();
-    if (smem > 48 * 1024 && smem > configured[dev]) {
-        B2F_CUDA(cudaFuncSetAttribute(pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        configured[dev] = 160 * 1024;
+    if (smem > 48 * 1024) {
+        static size_t configured[kMaxDevices] = {};
+        const int dev = current_device_slot();
+        std::lock_guard<std::mutex> lk(launch_cache_mutex());
+        if (smem > configured[dev]) {
+            B2F_CUDA(cudaFuncSetAttribute(pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            configured[dev] = 160 * 1024;
+        }
     }
     pool_kernel<<<(unsigned)B, 256, smem, st>>>(hidden, mask, T, d, pool, normalize, out_f32, scan, dpad, norms, stats);
     B2F_CUDA(cudaGetLastError());

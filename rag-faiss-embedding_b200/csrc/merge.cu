@@ -41,11 +41,14 @@ int launch_merge_parts(const float* pk, const int32_t* pi, int nq, int nparts, i
         return B2F_EINVAL;
     }
     const size_t smem = ngroups > 1 ? (size_t)ngroups * kout * 8 : 0;
-    static size_t configured[kMaxDevices] = {};
-    const int dev = current_device_slot();
-    if (smem > 48 * 1024 && smem > configured[dev]) {
-        B2F_CUDA(cudaFuncSetAttribute(merge_parts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured[dev] = 200 * 1024;
+    if (smem > 48 * 1024) {
+        static size_t configured[kMaxDevices] = {};
+        const int dev = current_device_slot();
+        std::lock_guard<std::mutex> lk(launch_cache_mutex());
+        if (smem > configured[dev]) {
+            B2F_CUDA(cudaFuncSetAttribute(merge_parts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            configured[dev] = 200 * 1024;
+        }
     }
     if (smem > 200 * 1024) {
         set_error("merge: %zu bytes of shared memory needed", smem);

@@ -351,18 +351,28 @@ static int launch_one(const RowT* rows, int64_t pitch, const ScanArgs& a, cudaSt
     const int dq = ((a.d + Vec::N - 1) / Vec::N) * Vec::N;
     const size_t smem = (((size_t)NQ * dq + 2 * (size_t)kScanWarps * NQ * a.k + 1) & ~(size_t)1) * 4 + (size_t)kGatherCap * 8;
     auto kern = scan_kernel<NQ, L2, RowT, Vec>;
-    static size_t configured_smem[kMaxDevices] = {};
-    const int dev = current_device_slot();
-    if (configured_smem[dev] == 0 || smem > configured_smem[dev]) {
-        B2F_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 65536 ? smem : 65536)));
-        configured_smem[dev] = smem > 65536 ? smem : 65536;
-    }
-    // occupancy per (kernel, smem) is cached: the query costs microseconds and sits on the search path
-    static size_t occ_smem = ~(size_t)0;
-    static int occ = 1;
-    if (occ_smem != smem) {
-        B2F_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kScanThreads, smem));
-        occ_smem = smem;
+    int occ = 1;
+    {
+        // per template instantiation AND per device; guarded, because the index mutex is per index
+        static size_t configured_smem[kMaxDevices] = {};
+        static size_t occ_smem[kMaxDevices];
+        static int occ_cached[kMaxDevices];
+        static bool occ_valid[kMaxDevices] = {};
+        const int dev = current_device_slot();
+        std::lock_guard<std::mutex> lk(launch_cache_mutex());
+        if (configured_smem[dev] == 0 || smem > configured_smem[dev]) {
+            B2F_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 65536 ? smem : 65536)));
+            configured_smem[dev] = smem > 65536 ? smem : 65536;
+        }
+        // occupancy per (kernel, device, smem) is cached: the query costs microseconds and sits on the search path
+        if (!occ_valid[dev] || occ_smem[dev] != smem) {
+            int o = 1;
+            B2F_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, kScanThreads, smem));
+            occ_cached[dev] = o;
+            occ_smem[dev] = smem;
+            occ_valid[dev] = true;
+        }
+        occ = occ_cached[dev];
     }
     if (occ < 1) {
         set_error("scan kernel does not fit: smem %zu", smem);

@@ -121,6 +121,11 @@ class IndexFlat:
             p.profile = 1 if profile else 0
         return self
 
+    def _check_tensor(self, t, what: str):
+        # a CUDA pointer of another GPU would be dereferenced on the index's device (illegal address, sticky error)
+        _assert(t.is_cuda and t.device.index == self.device,
+                f"{what} must be a CUDA tensor on the index's GPU (cuda:{self.device}), got {t.device}")
+
     def stats(self) -> dict:
         s = C.Stats()
         C.check(self._lib.b2f_index_stats(self._h, ctypes.byref(s)))
@@ -143,7 +148,7 @@ class IndexFlat:
             import torch
 
             _assert(x.dim() == 2 and x.shape[1] == self.d, f"dimension mismatch: got {tuple(x.shape)}, d={self.d}")
-            _assert(x.device.index == self.device, "tensor is on another GPU than the index")
+            self._check_tensor(x, "x")
             x = x.to(torch.float32).contiguous()
             C.check(self._lib.b2f_index_add(self._h, x.shape[0], x.data_ptr(), C.MEM_DEVICE, _torch_stream(x)))
             return
@@ -162,6 +167,7 @@ class IndexFlat:
 
         _assert(_is_torch(hidden) and hidden.is_cuda and hidden.dim() == 3 and hidden.shape[2] == self.d,
                 "add_pooled expects a CUDA tensor [B, T, d]")
+        self._check_tensor(hidden, "hidden")
         hidden = hidden.to(torch.float32).contiguous()
         mptr = None
         if attention_mask is not None:
@@ -179,6 +185,7 @@ class IndexFlat:
         _assert(k > 0, "k must be > 0")
         _assert(_is_torch(hidden) and hidden.is_cuda and hidden.dim() == 3 and hidden.shape[2] == self.d,
                 "search_pooled expects a CUDA tensor [B, T, d]")
+        self._check_tensor(hidden, "hidden")
         hidden = hidden.to(torch.float32).contiguous()
         mptr = None
         if attention_mask is not None:
@@ -201,6 +208,7 @@ class IndexFlat:
             import torch
 
             _assert(x.dim() == 2 and x.shape[1] == self.d, f"dimension mismatch: got {tuple(x.shape)}, d={self.d}")
+            self._check_tensor(x, "x")
             x = x.to(torch.float32).contiguous()
             D = torch.empty((x.shape[0], k), dtype=torch.float32, device=x.device)
             I = torch.empty((x.shape[0], k), dtype=torch.int64, device=x.device)
@@ -227,6 +235,8 @@ class IndexFlat:
         _assert(D.is_cuda and I.is_cuda and D.dtype == torch.float32 and I.dtype == torch.int64
                 and D.is_contiguous() and I.is_contiguous() and tuple(D.shape) == (x.shape[0], k) == tuple(I.shape),
                 "D / I must be contiguous CUDA tensors [n, k] of float32 / int64")
+        for t, what in ((x, "x"), (D, "D"), (I, "I")):
+            self._check_tensor(t, what)
         x = x.to(torch.float32).contiguous()
         p = params if params is not None else self._params
         C.check(self._lib.b2f_index_search(self._h, x.shape[0], x.data_ptr(), k, D.data_ptr(), I.data_ptr(),

@@ -1,9 +1,12 @@
 """Row-sharded exact search across the GPUs of one box (BASELINE config 4).
 
-One process per GPU (torch.distributed, NCCL over NVLink).  Every rank holds a contiguous range of
-the database rows in its own single-GPU IndexFlat; queries are replicated; each rank searches its
-shard (global label = shard offset + local row), the per-rank (distance, label)[nq, k] lists are
-exchanged with ONE all-gather and merged on every rank by the CUDA merge kernel (b2f_merge_topk).
+One process per GPU (torch.distributed for the plumbing: ranks, the one-time exchange of IPC handles, barriers).
+Every rank holds a contiguous range of the database rows in its own single-GPU IndexFlat; queries are
+replicated; each rank searches its shard (global label = shard offset + local row) straight into a message
+buffer, and ONE kernel per rank pushes the message into every peer's receive buffer over NVLink peer memory,
+flags, waits for the peers' flags and merges the world parts (csrc/exchange.cu; the whole step is one C call,
+b2f_exchange_search).  B200FLAT_EXCHANGE=nccl (or a failed IPC set-up) selects the NCCL form of the same step:
+one all_gather_into_tensor of the packed messages + the CUDA merge kernel (b2f_merge_topk_strided).
 Exact top-k over a partition = merge of per-part exact top-k, so results equal the single-GPU index.
 
 The reference has no multi-process code; its file order / .mapping list stay valid because global
@@ -149,8 +152,11 @@ class ShardedIndexFlat:
     # -- search -----------------------------------------------------------------------------------
     def search_local(self, x, k: int):
         off = self.segments.single_offset()
+        if hasattr(self.local, "set_search_params"):
+            # always set: an offset left behind by an earlier single-segment search must not leak into the
+            # multi-segment branch, whose labels are remapped below
+            self.local.set_search_params(id_offset=off if off is not None else 0)
         if off is not None and hasattr(self.local, "set_search_params"):
-            self.local.set_search_params(id_offset=off)
             return self.local.search(x, k)
         D, I = self.local.search(x, k)
         if isinstance(I, np.ndarray):
@@ -195,32 +201,49 @@ class ShardedIndexFlat:
         self._ex = h
         return h
 
-    def _search_packed(self, x, k: int):
-        """CUDA path of search(): every rank writes its (D, I) into ONE message buffer, one all-gather ships it
-        (12 * nq * k bytes per rank), the CUDA merge kernel reads the gathered messages in place."""
+    def _search_packed(self, x, k: int, out=None):
+        """CUDA path of search(): every rank writes its (D, I) into ONE message buffer (12 * nq * k bytes), one kernel
+        pushes it to the peers over NVLink and merges the world parts (or: one NCCL all-gather + the merge kernel).
+        out = (D [nq, k] float32, I [nq, k] int64) CUDA tensors to write into (else allocated here)."""
         import torch
 
         nq = int(x.shape[0])
+        if out is not None:
+            Dm, Im = out
+            if not (Dm.is_cuda and Im.is_cuda and Dm.dtype == torch.float32 and Im.dtype == torch.int64
+                    and Dm.is_contiguous() and Im.is_contiguous() and tuple(Dm.shape) == (nq, k) == tuple(Im.shape)):
+                raise AssertionError("out must be contiguous CUDA tensors (D [nq, k] float32, I [nq, k] int64)")
+        else:
+            Dm = torch.empty((nq, k), dtype=torch.float32, device=x.device)
+            Im = torch.empty((nq, k), dtype=torch.int64, device=x.device)
         if nq == 0:
-            return (torch.empty((0, k), dtype=torch.float32, device=x.device),
-                    torch.empty((0, k), dtype=torch.int64, device=x.device))
+            return Dm, Im
+        if x.device.index != self.local.device:
+            raise AssertionError("queries are on another GPU than this rank's shard")
         off_i = (nq * k * 4 + 15) // 16 * 16
         part = (off_i + nq * k * 8 + 15) // 16 * 16
+        stream = int(torch.cuda.current_stream(x.device).cuda_stream) or 1  # 0x1 = cudaStreamLegacy
+        off = self.segments.single_offset()
+        ex = self._peer_exchange(part)
+        if ex is not None and off is not None:
+            # the whole sharded step behind one C call: local search into the exchange's message buffer, then
+            # push over NVLink peer memory + flag + merge in one kernel -- no allocation, no second library call
+            x = x.to(torch.float32).contiguous()
+            p = C.SearchParams.from_buffer_copy(self.local._params)
+            p.id_offset = off
+            C.check(C.load().b2f_exchange_search(ex, self.local._h, nq, x.data_ptr(), k, Dm.data_ptr(), Im.data_ptr(),
+                                                 ctypes.c_void_p(stream), ctypes.byref(p)))
+            return Dm, Im
         send = torch.empty(part, dtype=torch.uint8, device=x.device)
         D = send[: nq * k * 4].view(torch.float32).view(nq, k)
         I = send[off_i: off_i + nq * k * 8].view(torch.int64).view(nq, k)
-        off = self.segments.single_offset()
+        self.local.set_search_params(id_offset=off if off is not None else 0)
         if off is not None:
-            self.local.set_search_params(id_offset=off)
             self.local.search_tensors_into(x, k, D, I)
         else:
             Dl, Il = self.local.search(x, k)
             D.copy_(Dl)
             I.copy_(self.segments.to_global_torch(Il))
-        Dm = torch.empty((nq, k), dtype=torch.float32, device=x.device)
-        Im = torch.empty((nq, k), dtype=torch.int64, device=x.device)
-        stream = int(torch.cuda.current_stream(x.device).cuda_stream) or 1  # 0x1 = cudaStreamLegacy
-        ex = self._peer_exchange(part)
         if ex is not None:
             # the one exchange step of the path, fused with the merge: push over NVLink peer memory, flag, merge
             C.check(C.load().b2f_exchange_merge(ex, send.data_ptr(), part, int(self.metric_type), nq, k, off_i,
@@ -251,7 +274,7 @@ class ShardedIndexFlat:
         else:
             x.copy_(x_host, non_blocking=True)
         D, I = self.search(x, k)
-        if D_out is None:
+        if D_out is None or I_out is None:
             D_out = torch.empty((nq, k), dtype=torch.float32).pin_memory()
             I_out = torch.empty((nq, k), dtype=torch.int64).pin_memory()
         D_out.copy_(D, non_blocking=True)
@@ -259,11 +282,12 @@ class ShardedIndexFlat:
         torch.cuda.current_stream(dev).synchronize()
         return D_out, I_out
 
-    def search(self, x, k: int):
-        """Replicated queries -> identical merged (D, I) on every rank."""
+    def search(self, x, k: int, out=None):
+        """Replicated queries -> identical merged (D, I) on every rank.  out: optional caller-owned CUDA result
+        tensors (CUDA path only), so that a serving loop allocates nothing per search."""
         if (self.world > 1 and self._merge is merge_topk and hasattr(x, "is_cuda") and x.is_cuda
                 and hasattr(self.local, "search_tensors_into")):
-            return self._search_packed(x, k)
+            return self._search_packed(x, k, out)
         D, I = self.search_local(x, k)
         if self.world == 1:
             return D, I
@@ -286,5 +310,7 @@ class ShardedIndexFlat:
 
     def reset(self):
         self.local.reset()
+        if hasattr(self.local, "set_search_params"):
+            self.local.set_search_params(id_offset=0)
         self.segments = SegmentMap()
         self.ntotal = 0

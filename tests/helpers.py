@@ -38,6 +38,7 @@ class OracleIndex:
 
     def reset(self):
         self.x = np.zeros((0, self.d), np.float32)
+        # (the id offset is NOT cleared here: the sharded wrapper must reset it itself)
 
 
 def np_merge(metric, Dg, Ig):

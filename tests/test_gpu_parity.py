@@ -496,6 +496,76 @@ def test_pool_normalize_and_add_pooled(m):
     assert torch.equal(Ip, Ir) and torch.allclose(Dp, Dr, rtol=1e-6, atol=1e-7)
 
 
+@pytest.mark.parametrize("metric", [0, 1])
+@pytest.mark.parametrize("normalize", [False, True])
+def test_add_pooled_bf16_storage_both_metrics(m, metric, normalize):
+    """add_pooled into a bf16-storage index, inner product included: the per-row bias of the tensor pass must come
+    from the ingest kernel (IP: -mu.x, not |x|^2), so the tensor path -- where AUTO sends every batch on bf16
+    storage -- finds the true neighbours of the rounded rows."""
+    import torch
+
+    from rag_faiss_embedding_b200.encoder import pool_normalize
+
+    torch.manual_seed(3)
+    B, T, d, k = 3000, 5, 128, 10
+    h = torch.randn(B, T, d, device="cuda") + 0.25
+    mask = torch.ones(B, T, dtype=torch.int64, device="cuda")
+    ix = m.IndexFlat(d, metric, storage=m.STORE_BF16)
+    ix.add_pooled(h[:2000], mask[:2000], pool="mean", normalize=normalize)
+    ix.add_pooled(h[2000:], mask[2000:], pool="mean", normalize=normalize)
+    rows = ix.reconstruct_n()   # the authoritative (rounded) rows
+    pooled = pool_normalize(h, mask, "mean", normalize)
+    assert np.allclose(rows, pooled.cpu().numpy(), rtol=1e-2, atol=1e-2)
+    xq = pooled[:64].cpu().numpy() + 0.01
+    for algo in (m.ALGO_AUTO, m.ALGO_TENSOR, m.ALGO_SCAN):
+        D, I = ix.set_search_params(algo=algo).search(xq, k)
+        _check(D, I, *orc.np_search_f64(rows, xq, k, metric), metric)
+        if algo != m.ALGO_SCAN:
+            assert ix.stats()["last_algo"] == m.ALGO_TENSOR
+
+
+def test_add_on_side_stream_is_ordered_before_search(m):
+    """A device-tensor add enqueued on a caller stream behind a long-running kernel, immediately followed by a numpy
+    search (the index's own non-blocking stream), a growth re-allocation and a write: every consumer must wait for
+    the ingest (no torch.cuda.synchronize() anywhere in between)."""
+    import torch
+
+    d, k = 128, 5
+    xb = orc.c_synth_rows(1234, 0, 6000, d)
+    xq = orc.c_synth_rows(5678, 0, 8, d)
+    side = torch.cuda.Stream()
+    ix = m.IndexFlatL2(d)
+    ix.add(xb[:1000])                       # capacity 1024: the next add must grow the storage
+    big = torch.empty(64 << 20, device="cuda")
+    with torch.cuda.stream(side):
+        for _ in range(20):
+            big.normal_()                   # keeps the side stream busy for a while
+        xt = torch.from_numpy(xb[1000:1020]).cuda(non_blocking=False)
+        ix.add(xt)                          # enqueued behind the busy work on `side`
+        for _ in range(20):
+            big.normal_()
+        ix.add(torch.from_numpy(xb[1020:6000]).cuda())   # grows: copies the old rows (incl. the pending 20) first
+    D, I = ix.search(xq, k)                 # numpy search: index stream
+    _check(D, I, *orc.np_search_f64(xb, xq, k, 1), 1)
+    assert np.array_equal(ix.reconstruct_n(990, 40), xb[990:1030])
+    torch.cuda.synchronize()
+
+
+def test_tensor_on_other_device_is_rejected(m):
+    import torch
+
+    ix = m.IndexFlatL2(16)
+    ix.add(np.zeros((4, 16), np.float32))
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    x = torch.zeros(2, 16, device="cuda:1")
+    for fn in (lambda: ix.search(x, 1), lambda: ix.add(x),
+               lambda: ix.search_tensors_into(x, 1, torch.empty(2, 1, device="cuda:1"),
+                                              torch.empty(2, 1, dtype=torch.int64, device="cuda:1"))):
+        with pytest.raises(AssertionError):
+            fn()
+
+
 def test_synth_bit_identical(m):
     from rag_faiss_embedding_b200.encoder import synth_rows
 

@@ -53,6 +53,21 @@ def _worker(rank, world, port, out_dir):
             same = same and torch.equal(Ib[:nq], I) and torch.equal(Ib[-nq:], I) and torch.equal(Db[nq:2 * nq], D)
             same = same and torch.equal(In, I) and torch.equal(Dn, D)
             same = same and torch.equal(Ih.cuda(), I) and torch.equal(Dh.cuda(), D) and tuple(Ie.shape) == (0, k)
+            # caller-owned result tensors (nothing allocated per search)
+            Do, Io = torch.empty_like(D), torch.empty_like(I)
+            ix.search(xq, k, out=(Do, Io))
+            torch.cuda.synchronize()
+            same = same and torch.equal(Io, I) and torch.equal(Do, D)
+            # add, search, add, search: the shard offset of the single-segment search must not leak into the
+            # multi-segment remap (rows arrive in two adds, so every shard holds two label ranges)
+            ix2 = b2f.ShardedIndexFlat(d, metric, device=rank)
+            ix2.add_synthetic(1234, 30000)
+            Da, Ia = ix2.search(xq, k)
+            ix2.add_synthetic(1234, n - 30000)
+            D2, I2 = ix2.search(xq, k)
+            torch.cuda.synchronize()
+            same = same and ix2.ntotal == n and torch.equal(I2, I) and torch.allclose(D2, D, rtol=1e-6)
+            same = same and bool((Ia < 30000).all())
             np.savez(os.path.join(out_dir, f"r{rank}_m{metric}.npz"), D=D.cpu().numpy(), I=I.cpu().numpy(),
                      D1=D1.cpu().numpy(), I1=I1.cpu().numpy(), nlocal=ix.local.ntotal, same=bool(same))
     finally:

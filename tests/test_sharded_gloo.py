@@ -40,11 +40,16 @@ def _worker(rank, world, port, metric, out_dir):
 
         ix = ShardedIndexFlat(d, metric, local_index=OracleIndex(d, metric), merge_fn=merge)
         ix.add(xb1)
+        D0, I0 = ix.search(xq, k)   # single segment: the shard offset is applied by the local index ...
         ix.add(xb2)   # second add: labels continue after the first, shard holds two segments
         assert ix.ntotal == 578
-        D, I = ix.search(xq, k)
+        D, I = ix.search(xq, k)     # ... and must not leak into the multi-segment remap (add, search, add, search)
         Dk, Ik = ix.search(xq, 600)  # k > rows per shard and > ntotal: padding must survive the merge
-        np.savez(os.path.join(out_dir, f"r{rank}.npz"), D=D, I=I, Dk=Dk, Ik=Ik, nlocal=ix.local.ntotal)
+        ix.reset()
+        ix.add(xb2)
+        Dr, Ir = ix.search(xq, k)   # after reset(): labels start at 0 again
+        np.savez(os.path.join(out_dir, f"r{rank}.npz"), D=D, I=I, Dk=Dk, Ik=Ik, D0=D0, I0=I0, Dr=Dr, Ir=Ir,
+                 nlocal=ix.local.ntotal)
     finally:
         dist.destroy_process_group()
 
@@ -59,6 +64,8 @@ def test_sharded_equals_single(tmp_path, world, metric):
     xq = orc.np_synth_rows(12, 0, 9, d)
     D_ref, I_ref = orc.c_search(xb, xq, k, metric)
     Dk_ref, Ik_ref = orc.c_search(xb, xq, 600, metric)
+    D0_ref, I0_ref = orc.c_search(xb[:501], xq, k, metric)
+    Dr_ref, Ir_ref = orc.c_search(xb[501:], xq, k, metric)
     total = 0
     for r in range(world):
         z = np.load(os.path.join(tmp_path, f"r{r}.npz"))
@@ -66,5 +73,7 @@ def test_sharded_equals_single(tmp_path, world, metric):
         assert np.allclose(z["D"], D_ref, rtol=1e-6)
         assert np.array_equal(z["Ik"], Ik_ref)
         assert np.array_equal(z["Dk"], Dk_ref)
+        assert np.array_equal(z["I0"], I0_ref) and np.allclose(z["D0"], D0_ref, rtol=1e-6)
+        assert np.array_equal(z["Ir"], Ir_ref) and np.allclose(z["Dr"], Dr_ref, rtol=1e-6)
         total += int(z["nlocal"])
-    assert total == 578
+    assert total == 77
