@@ -198,3 +198,17 @@ def test_bench_reference_arm_contract():
     assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1 and j["cpu_baseline"]["value"] == j["value"]
     assert j["e2e"] == {"value": j["value"], "unit": "queries/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in j["config"]
+    # both arms print the SAME workload-defining config (one function), so the driver's same_config comparison holds
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert j["config"] == bench.workload_config(bench.WORKLOADS["c2_nq1"], 1)
+    c8 = bench.workload_config(bench.WORKLOADS["c2"], 8)
+    assert c8["nq"] == 8192 and c8["rows_per_gpu"] == 125000 and c8["l2_policy"].startswith("L2 flushed")   # 96 MB < L2
+    assert bench.workload_config(bench.WORKLOADS["c2"], 1)["l2_policy"].startswith("inputs larger than L2")
+    c4 = bench.workload_config(bench.WORKLOADS["c4shard"], 8)
+    assert c4["rows_total"] == 100_000_000 and c4["rows_per_gpu"] == 12_500_000 and c4["nq"] == 4096
+    assert j["cpu_baseline"]["one_thread"]["cores"] == 1
+
