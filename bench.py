@@ -54,6 +54,10 @@ WORKLOADS = {
                       label="synthetic 1Mx384 fp32 flat L2, 4096 queries, k=10 (large-batch series)"),
     "c2_nq32": dict(n=1_000_000, d=384, nq=32, k=10, metric=1, normalize=False, storage="fp32",
                     label="synthetic 1Mx384 fp32 flat L2, 32 queries, k=10 (small-batch series)"),
+    "c2_shard4": dict(n=250_000, d=384, nq=4096, k=10, metric=1, normalize=False, storage="fp32",
+                      label="synthetic 250k x 384 fp32 flat L2, 4096 queries, k=10 (one rank's share of the N = 4 weak-scaling point)"),
+    "c2_shard8": dict(n=125_000, d=384, nq=8192, k=10, metric=1, normalize=False, storage="fp32",
+                      label="synthetic 125k x 384 fp32 flat L2, 8192 queries, k=10 (one rank's share of the N = 8 weak-scaling point)"),
     "c3_nq1": dict(n=10_000_000, d=768, nq=1, k=100, metric=0, normalize=True, storage="fp32",
                    label="synthetic 10Mx768 flat inner-product (normalized), batch 1, k=100 (BASELINE configs[2])"),
     "c3_nq32": dict(n=10_000_000, d=768, nq=32, k=100, metric=0, normalize=True, storage="fp32",

@@ -10,6 +10,11 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libb200flat.so")
+# diagnostics: B200FLAT_LIB=<path> loads another build of the library (same-box A/B runs of two kernel versions);
+# entry points that build lacks are then skipped instead of failing the import
+_LIB_OVERRIDE = os.environ.get("B200FLAT_LIB")
+if _LIB_OVERRIDE:
+    LIB_PATH = os.path.abspath(_LIB_OVERRIDE)
 
 METRIC_INNER_PRODUCT = 0
 METRIC_L2 = 1
@@ -96,6 +101,8 @@ PROTOTYPES = {
     "b2f_synth_rows": (ctypes.c_int, [_u64, _i64, _i64, _i32, _i32, _vp, _i32, _vp]),
     "b2f_index_add_synth": (ctypes.c_int, [_vp, _u64, _i64, _i64, _i32]),
     "b2f_plan_describe": (ctypes.c_int, [_i64, _i64, _i32, _i64, _i32, ctypes.POINTER(_i32)]),
+    "b2f_plan_unit_work": (ctypes.c_int, [_i32, _i32, _i32, _i64, _i32, ctypes.POINTER(_i32), ctypes.POINTER(_i64), _i64,
+                                          ctypes.POINTER(_i32)]),
     "b2f_index_stats": (ctypes.c_int, [_vp, ctypes.POINTER(Stats)]),
     "b2f_last_error": (ctypes.c_char_p, []),
     "b2f_version": (ctypes.c_int, []),
@@ -118,6 +125,8 @@ def load():
     except OSError as e:  # pragma: no cover - loud failure, never a fallback
         raise ImportError(f"the CUDA extension {LIB_PATH} could not be loaded: {e}") from e
     for name, (res, args) in PROTOTYPES.items():
+        if _LIB_OVERRIDE and not hasattr(lib, name):
+            continue
         fn = getattr(lib, name)  # AttributeError = header/library mismatch: fail loudly
         fn.restype = res
         fn.argtypes = args

@@ -292,16 +292,17 @@ int launch_rerank(const RerankArgs& a, cudaStream_t st);
 // K2: tcgen05 / TMEM / TMA contraction with fused top-k (gemm_topk_sm100.cu)
 struct TensorScanPlan {
     int nq_tiles;      // ceil(nq / 128)
-    int nsplits;       // database streams per query tile (LIST mode: the smaller of the two per-tile counts)
+    int nsplits;       // database streams per query tile (LIST mode: whole units per tile; the balanced split gives every unit units/tile_units of a tile)
     int units;         // CTAs (or CTA pairs) launched
-    int tile_units;    // query tiles (pair tiles) the units are dealt over
-    int nlists;        // LIST mode: candidate lists per query = nsplits x column halves (virtual splits)
+    int tile_units;    // query tile units (pair tiles when pair_mode) whose work the units share equally
+    int nlists;        // LIST mode: candidate lists allocated per query = (most segments of any tile) x column halves
     int kp;            // candidates kept per query
     int list_mode;     // 1: shared-threshold candidate lists (K3b merge), 0: per-thread heaps (K3 merge)
     int pair_mode;     // 1: CTA pairs (tcgen05 cta_group::2, M = 256 queries per pair); nq_tiles is then even
     int list_j;        // rows each split vouches for
     int list_g;        // splits consulted for the shared threshold (g * j >= kp)
     int list_cap;      // entries per (query, split) list
+    int round_tiles;   // LIST mode: database tiles per round of the interleaved sweep (k2::SegIter)
 };
 struct TensorScanLists {  // LIST-mode scratch (device)
     float* shared_thr;    // [nlists][nq_pad]
@@ -311,6 +312,7 @@ struct TensorScanLists {  // LIST-mode scratch (device)
     int32_t* die_ctr;     // [4] ticket counters of the die-aware unit assignment (zero between launches), or null
 };
 int plan_tensor_scan(int nq, int64_t n, int d, int kp, TensorScanPlan* plan);
+int plan_unit_work(int T, int U, int R, int64_t ntiles, int unit, int32_t* seg_info, int64_t* tiles, int64_t cap, int32_t* counts);
 int launch_tensor_scan(const __nv_bfloat16* scan, int64_t dpad, const float* norms, int64_t n, int metric,
                        const __nv_bfloat16* qb, int nq, int nq_pad, const TensorScanPlan& plan, float* pk,
                        int32_t* pi, const TensorScanLists& lists, cudaStream_t st);

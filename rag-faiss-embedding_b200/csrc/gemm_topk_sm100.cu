@@ -5,31 +5,34 @@
 // blocks + heap update; the nq >= 20 path behind index.search, faiss_store.py:64,
 // rag_datastore_manager.py:218) with one persistent, warp-specialised sm_100a kernel:
 //
-//   warp 0   TMA producer: cp.async.bulk.tensor.2d of a [128 x 64] bf16 query block and a
-//            [256 x 64] bf16 database block per pipeline stage (SWIZZLE_128B), mbarrier complete_tx
-//   warp 1   MMA issuer: one elected lane issues tcgen05.mma.cta_group::1.kind::f16, M=128 (queries)
-//            x N=256 (database rows) x K=16, fp32 accumulators in TMEM; tcgen05.commit frees the
-//            smem stage / publishes the accumulator
-//   warp 2   TMEM allocator (512 columns = two 128x256 fp32 accumulators, double buffered)
-//   warp 3   bias loader: |x~|^2 of the 256 rows of the tile (+inf for rows past the end) -> smem
-//   warps 4-7  epilogue: tcgen05.ld 32 columns at a time (double buffered); thread t owns query t of
-//            the tile: key = bias[col] - 2*acc (L2) or -acc (IP) is compared with a register threshold
-//            and the rare survivor is kept.  Two selection modes:
-//            LIST (nsplits >= k'/8): survivors are appended to the thread's candidate list in global
-//              memory (fire-and-forget stores).  The threshold is SHARED across the CTAs that stream
-//              different database splits for the same query: every split publishes its j-th best key
-//              so far (j = ceil(k'/g)); T* = max over g splits of those values is an upper bound of
-//              the global k'-th best (g*j >= k' rows are known to be <= T*), and it is far tighter
-//              than any single split's own k'-th best, so ~5x fewer rows survive the filter.
-//            HEAP (few splits, long streams): thread-private max-heap of k' in shared memory
-//              ([slot][thread] layout => conflict free), threshold = heap root.
+//   warp 0   TMA producer: cp.async.bulk.tensor.2d (SWIZZLE_128B) of bf16 database blocks into an mbarrier ring; the
+//            [128 x d] query tile is loaded once per segment and stays resident in shared memory when dpad <= 384
+//            (QRES), otherwise it is streamed per k-block with the database block
+//   warp 1   MMA issuer: one elected lane issues tcgen05.mma.kind::f16, M = queries x N = 256 database rows x K = 16,
+//            fp32 accumulators in TMEM (512 columns = two 128 x 256 accumulators, double buffered); tcgen05.commit
+//            frees the smem stage / publishes the accumulator.  Two forms:
+//              single CTA   cta_group::1, M = 128
+//              CTA pair     cta_group::2, M = 256 over the two SMs of a TPC (batches of >= 2 query tiles): each CTA owns
+//                           128 of the pair's queries and stages its 128-row half of every database block; the leader
+//                           issues the MMAs for both, commits are multicast to both CTAs
+//   warp 2   TMEM allocator
+//   warp 3   bias loader: |x~|^2 (L2) / -mu.x (IP) of the tile's 256 rows (+inf past the end) -> smem
+//   warps 4-11 (LIST) / 4-7 (HEAP)  epilogue: tcgen05.ld 32 columns at a time (double buffered); queries are the M
+//            dimension, so TMEM lane = query and a thread's state is private to (query, column half).  Per value one
+//            FFMA (bias - 2 acc), one compare against a register threshold; the rare survivor is kept.  Two modes:
+//            LIST: survivors are appended to the thread's candidate list in global memory (fire-and-forget stores).
+//              The threshold is SHARED across the units that stream different parts of the database for the same
+//              query: voucher lists publish their j-th best key so far; T* = max over g vouchers (g * j >= k') is
+//              an upper bound of the global k'-th best, far tighter than any single stream's own k'-th best.
+//            HEAP (more than one wave of query tiles, or a database of one tile): thread-private max-heap of k' in
+//              shared memory ([slot][thread] layout => conflict free), threshold = heap root.
 //
-// Work split: grid = nq_tiles x nsplits (<= 148 CTAs, one per SM); CTA (qt, s) streams database tiles
-// [s*NT/nsplits, (s+1)*NT/nsplits) against query tile qt.  CTAs that share a split walk the same
-// database tiles at the same time, so the database is fetched from HBM ~once and re-read from L2.
+// Work split (LIST): the pass's work -- query tile units x database -- is cut into one EQUAL share per unit (CTA or CTA
+// pair, one wave), whatever the two counts are; a unit runs the tail of one query tile and, if its share spills over,
+// the head of the next (struct Seg below).  Every segment sweeps the database front to back in rounds, all segments
+// together, so a block that several query tiles need is fetched from HBM once and re-read from L2.
 //
-// Roofline: nq <= 128 -> HBM-bound, algorithmic bytes n * dpad * 2; large nq -> tensor-bound,
-// 2 * nq * n * d flop.
+// Roofline: nq <= 128 -> HBM-bound, algorithmic bytes n * dpad * 2; large nq -> tensor-bound, 2 * nq * n * d flop.
 #include <cuda.h>
 #include <math.h>
 #include <stdlib.h>
@@ -216,7 +219,7 @@ struct Smem {
     // LIST mode (KP == 0): per-warp staging of one chunk's 32 accumulators per lane, [warp][column][lane]
     static constexpr size_t xpose_off = bias_off + 2 * BN * 4;
     static constexpr size_t bar_off = xpose_off + (KP == 0 ? (size_t)EPI_WARPS_LIST * 32 * 32 * 4 : 0);
-    static constexpr int nbars = 2 * NST + 9;
+    static constexpr int nbars = 2 * NST + 10;
     static constexpr size_t tmem_off = bar_off + nbars * 8;
     static constexpr size_t total = tmem_off + 16;
     static constexpr size_t alloc = total;  // the dynamic smem base is declared __align__(1024)
@@ -231,13 +234,93 @@ struct ListArgs {
     int nl_stride;       // lists per query allocated (the largest per-tile list count)
     int cap;             // entries per list
     float* final_thr;    // [nq_pad * nsplits]  threshold the list was pruned against at the end of the stream
-    int extra;           // virtual splits consulted beyond the gv needed (0..3): the gv-th smallest of gv + extra values
     int early;           // 1: scheduled threshold refreshes happen before the wait for the tile's accumulator
     int period_mask;     // refresh every (period_mask + 1) tiles after the first 32 (power of two - 1)
     int l2_keep;         // 1: database blocks are loaded with an evict_last L2 policy (several units read each block)
-    int strided;         // 1: a split walks every nsplits-th database tile (all units sweep the database together)
-    int die_mode;        // > 0: die-aware unit assignment (pair kernel); the value selects the smid -> die guess
+    int die_mode;        // > 0: die-aware unit assignment; the value selects the smid -> die guess
     int32_t* die_ctr;    // [4] ticket counters (zero between launches)
+    int bal_T;           // balanced work split: query tile units (pair tiles when PAIR) ...
+    int bal_U;           // ... shared evenly by this many units (CTAs / CTA pairs); T <= U
+    int bal_R;           // database tiles per round of the interleaved sweep
+};
+
+// ---- balanced work split (LIST mode) -----------------------------------------------------------------------------
+// The work of a pass is a line of T query tile units x the whole database.  It is cut into U EQUAL intervals, one per
+// unit (CTA or CTA pair), whatever T and U are: unit u owns [u T, (u + 1) T) in units of 1/U of a query tile.  With
+// T <= U an interval touches at most two query tiles, so a unit runs one or two SEGMENTS (query tile, fraction of the
+// database) back to back -- the tail of one tile, then the head of the next.  (Before: units were dealt round-robin
+// over the tiles and a pass lasted as long as the tiles with the fewest units -- 32 pair tiles over 74 pairs ran at
+// the pace of the 2-unit tiles, 2.31 being the fair share: 15% lost; balancing by query chunking cost extra passes.)
+//
+// Which database tiles a segment [p0, p1) of a query tile takes: the database is swept in ROUNDS of R tiles; in round
+// r the segments of a query tile partition the round's R tiles at cut(p) = (p / U * R + phi_r) >> 32 in 32.32 fixed
+// point, phi_r a golden-ratio dither so that every segment's total is proportional to its length (+-2 tiles).  All
+// segments therefore move through the database front to back TOGETHER, a round at a time: a block that several
+// query tiles need is fetched from HBM once and found in L2 by the others (the point of the former strided walk).
+//
+// Lists / shared thresholds: a query tile's segments are its list SLOTS -- the segments that start inside the tile
+// ("first wave": they begin at kernel start) in position order, then the head segment (run by the unit that first
+// finishes the previous tile's tail).  Only first-wave segments of at least half the full length VOUCH (publish
+// their j-th best); they are slots [0, nv).  Every segment prunes against the max of gv vouchers' values.
+struct Seg {
+    int qtile;         // query tile unit
+    int slot;          // list slot within the tile
+    int nv;            // voucher slots of the tile: [0, nv)
+    uint32_t p0, p1;   // in-tile range in units of 1/U tile
+};
+__host__ __device__ __forceinline__ void tile_slots(int t, int T, int U, int& u_lo, int& nfw, int& nv, int& head) {
+    u_lo = (int)(((int64_t)t * U + T - 1) / T);                           // first unit that starts inside tile t
+    const int u_hi = (int)((((int64_t)t + 1) * U + T - 1) / T) - 1;       // last one
+    nfw = u_hi - u_lo + 1;
+    const int tail_len = (int)(((int64_t)t + 1) * U - (int64_t)u_hi * T);  // (0, T]: what the last one covers of tile t
+    nv = nfw - (2 * tail_len < T ? 1 : 0);
+    if (nv < 1) nv = 1;
+    head = ((int64_t)u_lo * T > (int64_t)t * U) ? 1 : 0;                  // unit u_lo - 1 spills into this tile
+}
+__host__ __device__ __forceinline__ int unit_segments(int u, int T, int U, Seg (&seg)[2]) {
+    const int64_t S0 = (int64_t)u * T, S1 = S0 + T;
+    const int a = (int)(S0 / U), b = (int)(S1 / U);
+    const int fa = (int)(S0 - (int64_t)a * U), fb = (int)(S1 - (int64_t)b * U);
+    int u_lo, nfw, nv, head;
+    tile_slots(a, T, U, u_lo, nfw, nv, head);
+    seg[0].qtile = a; seg[0].slot = u - u_lo; seg[0].nv = nv; seg[0].p0 = (uint32_t)fa; seg[0].p1 = (uint32_t)(b > a ? U : fb);
+    if (b > a && fb > 0) {   // the interval spills into the head of the next tile
+        tile_slots(b, T, U, u_lo, nfw, nv, head);
+        seg[1].qtile = b; seg[1].slot = nfw; seg[1].nv = nv; seg[1].p0 = 0u; seg[1].p1 = (uint32_t)fb;
+        return 2;
+    }
+    return 1;
+}
+// The database tiles of one segment, in sweep order.  Contiguous form (HEAP mode): tiles [t0, t1).
+struct SegIter {
+    uint64_t F0, F1;
+    int R, NR, r, j, jend;
+    int64_t ntiles;
+    __host__ __device__ __forceinline__ void init(uint32_t p0, uint32_t p1, int U, int R_, int64_t ntiles_) {
+        F0 = ((uint64_t)p0 << 32) / (uint32_t)U;
+        F1 = ((uint64_t)p1 << 32) / (uint32_t)U;   // p1 == U -> exactly 2^32
+        R = R_;
+        ntiles = ntiles_;
+        NR = (int)((ntiles_ + R_ - 1) / R_);
+        r = -1;
+        j = jend = 0;
+    }
+    __host__ __device__ __forceinline__ void init_contig(int64_t t0, int64_t t1) {
+        F0 = 0; F1 = 0; R = 0; NR = 0; r = 0;   // r * R + j == j
+        ntiles = t1;
+        j = (int)t0; jend = (int)t1;
+    }
+    __host__ __device__ __forceinline__ int64_t next() {   // -1 when exhausted
+        while (true) {
+            if (j < jend) return (int64_t)r * R + j++;
+            if (++r >= NR) return -1;
+            // the last round holds what is left of the database and is shared out the same way
+            const uint64_t Rr = (r == NR - 1) ? (uint64_t)(ntiles - (int64_t)r * R) : (uint64_t)R;
+            const uint64_t phi = (uint32_t)((uint32_t)r * 2654435769u);
+            j = (int)((F0 * Rr + phi) >> 32);
+            jend = (int)((F1 * Rr + phi) >> 32);
+        }
+    }
 };
 
 // thread-private max-heap in shared memory, element j of thread t at [j * 128 + t].
@@ -304,78 +387,86 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     uint64_t* bias_full = bars + 2 * STAGES + 4;   // [2]       bias loader -> epilogue
     uint64_t* q_full = bars + 2 * STAGES + 6;      // [1]       resident query tile landed (QRES)
     uint64_t* bias_empty = bars + 2 * STAGES + 7;  // [2]       epilogue -> bias loader (PAIR: local to each CTA)
+    uint64_t* q_empty = bars + 2 * STAGES + 9;     // [1]       MMA -> TMA: the resident query tile may be replaced (next segment)
     uint32_t* tmem_base_holder = reinterpret_cast<uint32_t*>(smem + L::tmem_off);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // PAIR: a cluster of two CTAs (one TPC) works on 256 queries x one database split; CTA rank r owns
+    // PAIR: a cluster of two CTAs (one TPC) works on 256 queries x one database stream; CTA rank r owns
     // queries [128 r, 128 r + 128) of the pair tile and stages rows [128 r, 128 r + 128) of every
     // 256-row database block; the leader (rank 0) issues tcgen05.mma.cta_group::2 for both.
     const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
     int unit = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;       // cluster (PAIR) or CTA index
-    const int units_per_split = PAIR ? (nq_tiles >> 1) : nq_tiles;
-    if constexpr (PAIR && LIST) {
-        // Die-aware work assignment.  The units that share a database split read the same blocks at about the same
-        // time; when they sit on both dies the second reader pulls every block across the die-to-die L2 fabric.
-        // Each pair therefore takes a ticket from its own die's counter (SM ids below 74: die 0) and the
-        // (tile, split) items are dealt so that a split's units all come from one die (even splits: die 0, odd
-        // splits: die 1; a die with more pairs than items takes the other die's last ones).  DRAM traffic is
-        // unchanged by this (the 2x comes from tiles with different split counts walking the database
-        // out of phase); the kernel is ~1% faster.
+    const int64_t ntiles = (n + BN - 1) / BN;
+    if constexpr (LIST) {
+        // Die-aware work assignment.  Units whose segments sit at the same place inside their query tiles read the
+        // same database tiles of every round at about the same time; when they sit on both dies the second reader
+        // pulls every block across the die-to-die L2 fabric.  Logical units are therefore handed out in the order of
+        // their position inside the tile (frac(u T / U)): the hardware units of die 0 take tickets from the front of
+        // that order, those of die 1 from the back, so each die serves (about) one half of every round's tiles.
         if (la.die_mode > 0) {
             // (in the spare bytes behind the TMEM base holder: the pair variant has no room for static shared memory)
             int& s_unit = *reinterpret_cast<int*>(smem + L::tmem_off + 8);
-            const int U = (int)(gridDim.x >> 1), T = units_per_split;
+            int& s_idx = *reinterpret_cast<int*>(smem + L::tmem_off + 12);
+            const int U = la.bal_U, T = la.bal_T;
             if (threadIdx.x == 0 && cta_rank == 0) {
                 uint32_t smid;
                 asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
                 const int die = la.die_mode == 1 ? (smid >= (uint32_t)(kNumSMs / 2) ? 1 : 0)
                               : la.die_mode == 2 ? (int)(smid & 1u) : (int)((smid >> 1) & 1u);
-                auto items_of = [&](int dd) {   // units u in [0, U) whose split u / T has parity dd
-                    int cnt = 0;
-                    for (int sidx = dd; sidx * T < U; sidx += 2) cnt += (U - sidx * T) < T ? (U - sidx * T) : T;
-                    return cnt;
-                };
-                auto item = [&](int dd, int t) { return (2 * (t / T) + dd) * T + (t % T); };
-                const int mine = items_of(die), other = items_of(die ^ 1);
                 const int t = atomicAdd(la.die_ctr + die, 1);
-                int u;
-                if (t < mine) {
-                    u = item(die, t);
-                } else {
-                    const int o = atomicAdd(la.die_ctr + 2, 1);
-                    u = item(die ^ 1, other - 1 - o);
-                }
-                if (atomicAdd(la.die_ctr + 3, 1) == U - 1) {   // every pair has its item: re-arm the counters
+                s_idx = die == 0 ? t : U - 1 - t;   // front / back of the position order; U tickets in total, no collision
+                if (atomicAdd(la.die_ctr + 3, 1) == U - 1) {   // every unit has its ticket: re-arm the counters
                     la.die_ctr[0] = 0; la.die_ctr[1] = 0; la.die_ctr[2] = 0; la.die_ctr[3] = 0;
                 }
-                s_unit = u;
-                uint32_t remote;
-                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(&s_unit)), "r"(1));
-                asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(remote), "r"(u) : "memory");
             }
-            cluster_sync_all();
+            if constexpr (PAIR) {
+                if (threadIdx.x == 0 && cta_rank == 0) {
+                    uint32_t remote;
+                    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(&s_idx)), "r"(1));
+                    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(remote), "r"(s_idx) : "memory");
+                }
+                cluster_sync_all();
+            } else {
+                __syncthreads();
+            }
+            // the unit whose (position, index) key has rank s_idx: thread v < U counts the keys below its own
+            const int want = s_idx;
+            for (int v = threadIdx.x; v < U; v += blockDim.x) {
+                const int kv = (v * T) % U;   // U, T <= 148
+                int rank = 0, kw = 0;
+                for (int w = 0; w < U; w++) {
+                    rank += (kw < kv || (kw == kv && w < v)) ? 1 : 0;
+                    kw += T;                  // (w T) mod U, incrementally (T <= U)
+                    if (kw >= U) kw -= U;
+                }
+                if (rank == want) s_unit = v;
+            }
+            __syncthreads();
             unit = s_unit;
         }
     }
-    const int qt = PAIR ? (unit % units_per_split) * 2 + (int)cta_rank : unit % units_per_split;
-    const int split = unit / units_per_split;
-    // Units (CTAs / CTA pairs) are dealt round-robin over the query tiles, so when the unit count is not a
-    // multiple of the tile count the first `extra` tiles get one more database split than the others:
-    // every SM stays busy (nq = 4096: 74 pairs over 16 pair tiles = 5,5,...,4 splits instead of 4 x 16).
-    const int total_units = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-    const int my_nsplits = LIST ? total_units / units_per_split + ((unit % units_per_split) < (total_units % units_per_split) ? 1 : 0)
-                                : nsplits;
-    const int64_t ntiles = (n + BN - 1) / BN;
-    // Which database tiles a split walks.  Contiguous ranges (HEAP mode), or -- LIST mode -- every my_nsplits-th tile
-    // starting at `split`: then all units sweep the database front to back together, the tiles with one split more
-    // or less than the others included, and a block that several units need is still in L2 when the later ones
-    // arrive (with contiguous ranges a 19-way and an 18-way split of the same rows are walked out of phase and every
-    // block is fetched from DRAM once per group: ncu 1.51 GB for the 768 MB copy at nq = 1024).
-    const bool strided = LIST && la.strided;
-    const int64_t t_begin = strided ? split : ntiles * split / my_nsplits;
-    const int64_t t_step = strided ? my_nsplits : 1;
-    const int my_tiles = strided ? (int)(ntiles > split ? (ntiles - split + my_nsplits - 1) / my_nsplits : 0)
-                                 : (int)(ntiles * (split + 1) / my_nsplits - ntiles * split / my_nsplits);
+    // ---- this unit's work ---------------------------------------------------------------------------------------
+    // LIST: one or two segments of the balanced split (see Seg above).  HEAP: one contiguous database range of the
+    // (query tile, split) the unit index names.
+    Seg seg[2];
+    int nseg = 1;
+    int64_t heap_t0 = 0, heap_t1 = 0;
+    const int units_per_split = nq_tiles;   // HEAP mode only (never PAIR)
+    const int split = LIST ? 0 : unit / units_per_split;
+    if constexpr (LIST) {
+        nseg = unit_segments(unit, la.bal_T, la.bal_U, seg);
+    } else {
+        seg[0].qtile = unit % units_per_split; seg[0].slot = split; seg[0].nv = 0; seg[0].p0 = 0u; seg[0].p1 = 0u;
+        heap_t0 = ntiles * split / nsplits;
+        heap_t1 = ntiles * (split + 1) / nsplits;
+    }
+    auto seg_iter = [&](int s_) {
+        SegIter it;
+        if constexpr (LIST) it.init(seg[s_].p0, seg[s_].p1, la.bal_U, la.bal_R, ntiles);
+        else it.init_contig(heap_t0, heap_t1);
+        return it;
+    };
+    auto seg_qt = [&](int s_) { return PAIR ? seg[s_].qtile * 2 + (int)cta_rank : seg[s_].qtile; };
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_q)) : "memory");
@@ -393,6 +484,7 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             mbar_init(&bias_empty[a], EPI_WARPS);
         }
         mbar_init(q_full, 1);
+        mbar_init(q_empty, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -420,38 +512,42 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             int stage = 0;
             uint32_t phase = 0;
             const uint64_t l2_keep_policy = (PAIR && la.l2_keep) ? l2_policy_evict_last() : 0ull;
-            if constexpr (PAIR) {
-                // both CTAs load their own 128-query tile; the bytes of both are credited to the leader's barrier
-                if (cta_rank == 0) mbar_expect_tx(q_full, (uint32_t)(2 * kblocks * A_BYTES));
-                for (int kb = 0; kb < kblocks; kb++)
-                    tma_load_2d_pair(smem + L::q_off + (size_t)kb * A_BYTES, &map_q, kb * BK, qt * BM, q_full);
-            } else if constexpr (QRES) {
-                // the whole query tile (all k-blocks) is loaded once and stays in shared memory
-                mbar_expect_tx(q_full, (uint32_t)(kblocks * A_BYTES));
-                for (int kb = 0; kb < kblocks; kb++) tma_load_2d(smem + L::q_off + (size_t)kb * A_BYTES, &map_q, kb * BK, qt * BM, q_full);
-            }
-            for (int t = 0; t < my_tiles; t++) {
-                const int row0 = (int)((t_begin + t * t_step) * BN);
-                for (int kb = 0; kb < kblocks; kb++) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
-                    uint8_t* sa = smem + L::stages_off + (size_t)stage * kStageBytes;
+            for (int sgi = 0; sgi < nseg; sgi++) {
+                const int qt = seg_qt(sgi);
+                if constexpr (QRES) {
+                    // the whole query tile (all k-blocks) is loaded once per segment and stays in shared memory; a second
+                    // segment replaces it once the MMAs of the first have read it for the last time
+                    if (sgi > 0) mbar_wait(q_empty, (uint32_t)((sgi - 1) & 1));
                     if constexpr (PAIR) {
-                        // this CTA's half of the 256-row block; the leader's full barrier collects both halves
-                        if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * kStageBytes);
-                        if (la.l2_keep) tma_load_2d_pair_hint(sa, &map_x, kb * BK, row0 + (int)cta_rank * (BN / 2), &full_bar[stage], l2_keep_policy);
-                        else tma_load_2d_pair(sa, &map_x, kb * BK, row0 + (int)cta_rank * (BN / 2), &full_bar[stage]);
+                        // both CTAs load their own 128-query tile; the bytes of both are credited to the leader's barrier
+                        if (cta_rank == 0) mbar_expect_tx(q_full, (uint32_t)(2 * kblocks * A_BYTES));
+                        for (int kb = 0; kb < kblocks; kb++)
+                            tma_load_2d_pair(smem + L::q_off + (size_t)kb * A_BYTES, &map_q, kb * BK, qt * BM, q_full);
+                    } else {
+                        mbar_expect_tx(q_full, (uint32_t)(kblocks * A_BYTES));
+                        for (int kb = 0; kb < kblocks; kb++) tma_load_2d(smem + L::q_off + (size_t)kb * A_BYTES, &map_q, kb * BK, qt * BM, q_full);
+                    }
+                }
+                SegIter it = seg_iter(sgi);
+                for (int64_t dbt; (dbt = it.next()) >= 0;) {
+                    const int row0 = (int)(dbt * BN);
+                    for (int kb = 0; kb < kblocks; kb++) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        uint8_t* sa = smem + L::stages_off + (size_t)stage * kStageBytes;
+                        if constexpr (PAIR) {
+                            // this CTA's half of the 256-row block; the leader's full barrier collects both halves
+                            if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * kStageBytes);
+                            if (la.l2_keep) tma_load_2d_pair_hint(sa, &map_x, kb * BK, row0 + (int)cta_rank * (BN / 2), &full_bar[stage], l2_keep_policy);
+                            else tma_load_2d_pair(sa, &map_x, kb * BK, row0 + (int)cta_rank * (BN / 2), &full_bar[stage]);
+                        } else {
+                            mbar_expect_tx(&full_bar[stage], kStageBytes);
+                            if constexpr (!QRES) tma_load_2d(sa, &map_q, kb * BK, qt * BM, &full_bar[stage]);
+                            tma_load_2d(sa + (QRES ? 0 : A_BYTES), &map_x, kb * BK, row0, &full_bar[stage]);
+                        }
                         if (++stage == STAGES) {
                             stage = 0;
                             phase ^= 1;
                         }
-                        continue;
-                    }
-                    mbar_expect_tx(&full_bar[stage], kStageBytes);
-                    if constexpr (!QRES) tma_load_2d(sa, &map_q, kb * BK, qt * BM, &full_bar[stage]);
-                    tma_load_2d(sa + (QRES ? 0 : A_BYTES), &map_x, kb * BK, row0, &full_bar[stage]);
-                    if (++stage == STAGES) {
-                        stage = 0;
-                        phase ^= 1;
                     }
                 }
             }
@@ -462,55 +558,69 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         if (lane == 0 && cta_rank == 0) {  // PAIR: only the leader CTA issues MMAs
             int stage = 0;
             uint32_t phase = 0;
-            if constexpr (QRES) mbar_wait(q_full, 0);
-            for (int t = 0; t < my_tiles; t++) {
-                const int acc = t & 1;
-                const uint32_t acc_phase = (t >> 1) & 1;
-                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-                for (int kb = 0; kb < kblocks; kb++) {
-                    mbar_wait(&full_bar[stage], phase);
+            int gt = 0;   // tiles so far: accumulator buffer and barrier phases run on across segments
+            for (int sgi = 0; sgi < nseg; sgi++) {
+                if constexpr (QRES) mbar_wait(q_full, (uint32_t)(sgi & 1));
+                SegIter it = seg_iter(sgi);
+                for (int64_t dbt; (dbt = it.next()) >= 0; gt++) {
+                    const int acc = gt & 1;
+                    const uint32_t acc_phase = (gt >> 1) & 1;
+                    mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + L::stages_off + (size_t)stage * kStageBytes);
-                    const uint64_t adesc = make_smem_desc(QRES ? smem_u32(smem + L::q_off + (size_t)kb * A_BYTES) : sa);
-                    const uint64_t bdesc = make_smem_desc(sa + (QRES ? 0 : A_BYTES));
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                    for (int kb = 0; kb < kblocks; kb++) {
+                        mbar_wait(&full_bar[stage], phase);
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(smem + L::stages_off + (size_t)stage * kStageBytes);
+                        const uint64_t adesc = make_smem_desc(QRES ? smem_u32(smem + L::q_off + (size_t)kb * A_BYTES) : sa);
+                        const uint64_t bdesc = make_smem_desc(sa + (QRES ? 0 : A_BYTES));
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; k++) {
-                        // advance both descriptors by 32 bytes (16 bf16) inside the 128-byte swizzle atom
-                        if constexpr (PAIR)
-                            umma_bf16_pair(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), kIdescPair, (kb | k) != 0 ? 1u : 0u);
-                        else
-                            umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), (kb | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < BK / UMMA_K; k++) {
+                            // advance both descriptors by 32 bytes (16 bf16) inside the 128-byte swizzle atom
+                            if constexpr (PAIR)
+                                umma_bf16_pair(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), kIdescPair, (kb | k) != 0 ? 1u : 0u);
+                            else
+                                umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), (kb | k) != 0 ? 1u : 0u);
+                        }
+                        if constexpr (PAIR) umma_commit_pair(&empty_bar[stage]);
+                        else umma_commit(&empty_bar[stage]);
+                        if (++stage == STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
                     }
-                    if constexpr (PAIR) umma_commit_pair(&empty_bar[stage]);
-                    else umma_commit(&empty_bar[stage]);
-                    if (++stage == STAGES) {
-                        stage = 0;
-                        phase ^= 1;
+                    if constexpr (PAIR) umma_commit_pair(&tmem_full[acc]);
+                    else umma_commit(&tmem_full[acc]);
+                }
+                if constexpr (QRES) {
+                    if (sgi + 1 < nseg) {   // every MMA that reads this segment's query tile has been issued: free it
+                        if constexpr (PAIR) umma_commit_pair(q_empty);
+                        else umma_commit(q_empty);
                     }
                 }
-                if constexpr (PAIR) umma_commit_pair(&tmem_full[acc]);
-                else umma_commit(&tmem_full[acc]);
             }
         }
         __syncwarp();
     } else if (warp == 3) {
         // ===================== bias loader =====================
-        for (int t = 0; t < my_tiles; t++) {
-            const int acc = t & 1;
-            const uint32_t acc_phase = (t >> 1) & 1;
-            mbar_wait(PAIR ? &bias_empty[acc] : &tmem_empty[acc], acc_phase ^ 1);
-            const int64_t row0 = (t_begin + t * t_step) * BN;
+        int gt = 0;
+        for (int sgi = 0; sgi < nseg; sgi++) {
+            SegIter it = seg_iter(sgi);
+            for (int64_t dbt; (dbt = it.next()) >= 0; gt++) {
+                const int acc = gt & 1;
+                const uint32_t acc_phase = (gt >> 1) & 1;
+                mbar_wait(PAIR ? &bias_empty[acc] : &tmem_empty[acc], acc_phase ^ 1);
+                const int64_t row0 = dbt * BN;
 #pragma unroll
-            for (int j = 0; j < BN / 32; j++) {
-                const int64_t row = row0 + j * 32 + lane;
-                float b = __int_as_float(0x7f800000);  // +inf: rows past the end never pass the threshold
-                if (row < n) b = __ldg(norms + row);  // L2: |x~'|^2; IP: -mu.x (0 without centring)
-                bias[acc * BN + j * 32 + lane] = b;
+                for (int j = 0; j < BN / 32; j++) {
+                    const int64_t row = row0 + j * 32 + lane;
+                    float b = __int_as_float(0x7f800000);  // +inf: rows past the end never pass the threshold
+                    if (row < n) b = __ldg(norms + row);  // L2: |x~'|^2; IP: -mu.x (0 without centring)
+                    bias[acc * BN + j * 32 + lane] = b;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bias_full[acc]);
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bias_full[acc]);
         }
     } else if (warp >= 4) {
         // ===================== epilogue: fused distance + top-k' =====================
@@ -518,8 +628,6 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         const int wq = ew & 3;                        // TMEM lane quarter this warp may access (= warp % 4)
         const int half = ew >> 2;                     // which COLS-wide slice of every tile this warp examines
         const int tid = wq * 32 + lane;               // 0..127 == TMEM lane == query row in the tile
-        const int qrow = qt * BM + tid;
-        const bool active = qrow < nq;
         const uint32_t lane_taddr = tmem_base + ((uint32_t)(wq * 32) << 16);
 
         // Hot loop (both modes): 32 accumulator columns per tcgen05.ld; per value one FFMA + one compare +
@@ -559,58 +667,49 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         };
 
         if constexpr (LIST) {
-            // ---- LIST mode: shared cross-split threshold + append-only candidate lists -----------------
-            // Every (database split, column half) pair is a "virtual split" with its own list and its own
-            // published j-th best; nvs = nsplits * HALVES of them cooperate on each query.
+            // ---- LIST mode: shared cross-segment threshold + append-only candidate lists ----------------
+            // Every (segment, column half) pair of a query tile is a "virtual split" with its own list; the
+            // virtual splits of the tile's voucher segments also publish their j-th best so far.
             const float kInf = __int_as_float(0x7f800000);
-            const int vsplit = split * HALVES + half, nvs = my_nsplits * HALVES;
-            const int jv = (la.kp + nvs - 1) / nvs;      // rows each virtual split vouches for
-            const int gv = (la.kp + jv - 1) / jv;        // virtual splits needed: gv * jv >= k'
-            // Splits consulted: up to la.extra (0..3) more than needed.  Among wv published values the gv-th SMALLEST
-            // is still an upper bound of the k'-th best (gv splits vouch for jv rows each at or below it), and it is
-            // tighter than the maximum of exactly gv values.
-            const int wv = nvs < gv + la.extra ? nvs : gv + la.extra;
-            const int lsel = wv - gv;                    // take the (lsel + 1)-th largest of the wv values
+            uint32_t* xpose = reinterpret_cast<uint32_t*>(smem + L::xpose_off) + ew * 1024;  // this warp's staging area
+            const int64_t gstride = (int64_t)nq_tiles * BM;
+            int gt = 0;   // tiles so far (accumulator / barrier phases run on across segments)
+            for (int sgi = 0; sgi < nseg; sgi++) {
+            const int qrow = seg_qt(sgi) * BM + tid;
+            const bool active = qrow < nq;
+            const int vsplit = seg[sgi].slot * HALVES + half;
+            const int nvs = seg[sgi].nv * HALVES;          // voucher virtual splits of this query tile
+            const bool voucher = seg[sgi].slot < seg[sgi].nv;
+            const int jv = (la.kp + nvs - 1) / nvs;      // rows each voucher vouches for
+            const int gv = (la.kp + jv - 1) / jv;        // vouchers consulted: gv * jv >= k'
+            const int vstart = voucher ? vsplit : vsplit % nvs;   // own value first; the others spread over the vouchers
             float best[JSLOTS];  // ascending; the first JSLOTS - j slots are pinned at -inf, so best[JSLOTS-1] = j-th best
 #pragma unroll
             for (int i = 0; i < JSLOTS; i++) best[i] = (i < JSLOTS - jv) ? -kInf : kInf;
             float thr = 3.0e38f, pub = kInf;  // refreshed before the first compare; never +inf (padding rows have key +inf)
             int cnt = 0;
-            uint32_t* xpose = reinterpret_cast<uint32_t*>(smem + L::xpose_off) + ew * 1024;  // this warp's staging area
             uint2* mylist = la.cand + ((int64_t)(active ? qrow : 0) * la.nl_stride + vsplit) * la.cap;
             // shared thresholds are laid out [virtual split][query] so that a warp's loads for one split coalesce
             float* gq = la.shared_thr + (active ? qrow : 0);
-            const int64_t gstride = (int64_t)nq_tiles * BM;
             auto refresh = [&]() {
-                if (best[JSLOTS - 1] < pub) {
+                if (voucher && best[JSLOTS - 1] < pub) {
                     pub = best[JSLOTS - 1];
                     __stcg(gq + (int64_t)vsplit * gstride, pub);
                 }
-                float t0 = -kInf, t1 = -kInf, t2 = -kInf, t3 = -kInf;  // the four largest, descending
+                float t0 = -kInf;
 #pragma unroll 1
-                for (int i0 = 0; i0 < wv; i0 += 16) {  // 16 independent L2 loads in flight
+                for (int i0 = 0; i0 < gv; i0 += 16) {  // 16 independent L2 loads in flight
                     float v[16];
 #pragma unroll
                     for (int u = 0; u < 16; u++) {
-                        int s2 = vsplit + i0 + u;
+                        int s2 = vstart + i0 + u;
                         if (s2 >= nvs) s2 -= nvs;
-                        v[u] = (i0 + u < wv) ? __ldcg(gq + (int64_t)s2 * gstride) : -kInf;
+                        v[u] = (i0 + u < gv) ? __ldcg(gq + (int64_t)s2 * gstride) : -kInf;
                     }
-                    if (lsel == 0) {
 #pragma unroll
-                        for (int u = 0; u < 16; u++) t0 = fmaxf(t0, v[u]);
-                    } else {
-#pragma unroll
-                        for (int u = 0; u < 16; u++) {
-                            float x = v[u], a;
-                            a = fmaxf(t0, x); x = fminf(t0, x); t0 = a;
-                            a = fmaxf(t1, x); x = fminf(t1, x); t1 = a;
-                            a = fmaxf(t2, x); x = fminf(t2, x); t2 = a;
-                            t3 = fmaxf(t3, x);
-                        }
-                    }
+                    for (int u = 0; u < 16; u++) t0 = fmaxf(t0, v[u]);
                 }
-                thr = lsel == 0 ? t0 : (lsel == 1 ? t1 : (lsel == 2 ? t2 : t3));
+                thr = t0;
             };
             auto process = [&](const uint32_t (&r)[32], int t, int c, const float* tbc, int32_t rowc) {
                 // refresh schedule: thresholds move like 1/rows_seen, so consult the other splits often
@@ -622,9 +721,9 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 if (active && do_refresh) {
                     refresh();
                     if (t == 0 && c == 1) {
-                        // Every virtual split has now seen 32 rows and published.  CTAs start a few
+                        // Every first-wave virtual split has now seen 32 rows and published.  CTAs start a few
                         // microseconds apart; wait (bounded -- never a hard dependency) for the slowest of
-                        // the g splits we consult instead of appending blindly into the list meanwhile.
+                        // the vouchers we consult instead of appending blindly into the list meanwhile.
                         for (int spin = 0; spin < 64 && thr > 1.0e38f; spin++) {
                             __nanosleep(256);
                             refresh();
@@ -668,9 +767,11 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                     }
                 }
             };
-            for (int t = 0; t < my_tiles; t++) {
-                const int acc = t & 1;
-                const uint32_t acc_phase = (t >> 1) & 1;
+            SegIter it = seg_iter(sgi);
+            int t = 0;   // tile index within the segment (refresh schedule)
+            for (int64_t dbt; (dbt = it.next()) >= 0; t++, gt++) {
+                const int acc = gt & 1;
+                const uint32_t acc_phase = (gt >> 1) & 1;
                 // Scheduled refresh of the shared threshold BEFORE waiting for the tile's accumulator: the ~1.4 us
                 // of L2 round trips overlap the MMAs the thread would wait for anyway, and no accumulator registers
                 // are live yet (same-box A/B: the refreshes inside the tile cost 3-4% of the kernel).
@@ -678,7 +779,7 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 mbar_wait(&bias_full[acc], acc_phase);
                 mbar_wait(&tmem_full[acc], acc_phase);
                 tc_fence_after();
-                const int32_t row0 = (int32_t)((t_begin + t * t_step) * BN) + half * COLS;
+                const int32_t row0 = (int32_t)(dbt * BN) + half * COLS;
                 const float* tb = bias + acc * BN + half * COLS;
                 const uint32_t tile_taddr = lane_taddr + (uint32_t)(acc * BN + half * COLS);
                 uint32_t ra[32], rb[32];
@@ -704,7 +805,7 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 }
             }
             if (active) {
-                // End-of-stream pruning: the final shared threshold is far tighter than the ones most
+                // End-of-segment pruning: the final shared threshold is far tighter than the ones most
                 // entries were admitted under (the first chunk is admitted blindly), so re-filter the
                 // thread's own list in place.  Shrinks the merge input ~10x (C2: 1460 -> ~100 per query).
                 refresh();
@@ -724,20 +825,25 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 // smallest of these over the query's lists
                 la.final_thr[(int64_t)qrow * la.nl_stride + vsplit] = thr;
             }
+            }  // segments
         } else {
             // ---- HEAP mode: thread-private max-heap of k' in shared memory ------------------------------
+            const int qrow = seg[0].qtile * BM + tid;
+            const bool active = qrow < nq;
             for (int j = 0; j < KP; j++) {
                 heap_k[j * EPI_THREADS + tid] = FLT_MAX;
                 heap_i[j * EPI_THREADS + tid] = -1;
             }
             float thr = FLT_MAX;
-            for (int t = 0; t < my_tiles; t++) {
+            SegIter it = seg_iter(0);
+            int t = 0;
+            for (int64_t dbt; (dbt = it.next()) >= 0; t++) {
                 const int acc = t & 1;
                 const uint32_t acc_phase = (t >> 1) & 1;
                 mbar_wait(&bias_full[acc], acc_phase);
                 mbar_wait(&tmem_full[acc], acc_phase);
                 tc_fence_after();
-                const int32_t row0 = (int32_t)((t_begin + t * t_step) * BN);
+                const int32_t row0 = (int32_t)(dbt * BN);
                 const float* tb = bias + acc * BN;
                 const uint32_t tile_taddr = lane_taddr + (uint32_t)(acc * BN);
 #pragma unroll 1
@@ -841,9 +947,13 @@ merge_lists_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ c
     float* ek = reinterpret_cast<float*>(comp);                    // [RANK_MAX] exact keys   (comp is dead by then)
     int32_t* ei = reinterpret_cast<int32_t*>(ek + RANK_MAX);       // [RANK_MAX]
     const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // lists of this query: (database splits of its tile) x (column halves); see the kernel's my_nsplits
     const int tile = q / tile_queries;
-    const int nsplits = (total_units / ntile_units + (tile < total_units % ntile_units ? 1 : 0)) * halves;
+    int nsplits;   // lists of this query = (segments of its tile: first wave + head, see Seg) x column halves
+    {
+        int u_lo, nfw, nv, head;
+        tile_slots(tile, ntile_units, total_units, u_lo, nfw, nv, head);
+        nsplits = (nfw + head) * halves;
+    }
     // list lengths and final thresholds: one parallel sweep (up to 296 lists), then a warp-level prefix sum
     if (tid == 0) {
         s_tc_enc = 0xffffffffu;
@@ -1115,38 +1225,45 @@ int plan_tensor_scan(int nq, int64_t n, int d, int kp, TensorScanPlan* plan) {
     plan->nq_tiles = (nq + k2::BM - 1) / k2::BM;
     plan->pair_mode = 0;
     plan->list_mode = 0;
+    plan->round_tiles = 0;
     const int halves = k2::EPI_WARPS_LIST / 4;
     const int64_t ntiles = (n + k2::BN - 1) / k2::BN;
     const int kblocks = (d + k2::BK - 1) / k2::BK;
-    // A "unit" is one CTA, or one CTA pair (cta_group::2).  Units are dealt round-robin over the query
-    // tiles; a tile with s units splits the database s ways.  LIST mode lets s differ by one between tiles
-    // (all SMs busy); it needs every unit resident at once (one wave), at least two database tiles per
-    // split, and j = ceil(k' / lists per query) <= JSLOTS.
-    auto try_list = [&](int tiles, int max_units, int* units_out) -> bool {
+    // A "unit" is one CTA, or one CTA pair (cta_group::2).  LIST mode: the pass's work (query tile units x database)
+    // is cut into one EQUAL share per unit (k2::Seg); it needs every unit resident at once (one wave), at least as
+    // many units as query tile units, a few database tiles per unit, and j = ceil(k' / voucher lists of a tile) <=
+    // JSLOTS for every tile.
+    auto try_list = [&](int tiles, int max_units, int* units_out, int* nv_min_out, int* nseg_max_out) -> bool {
+        if (tiles > max_units || ntiles < 2) return false;   // more than one wave; a single database tile
         int units = max_units;
-        if (tiles > units) return false;                      // more than one wave
-        int ns_max = (units + tiles - 1) / tiles;
-        if ((int64_t)ns_max * 2 > ntiles) {                    // short database: uniform, fewer splits
-            const int ns = (int)(ntiles / 2);
-            if (ns < 1) return false;
-            units = tiles * ns;
+        // >= 4 database tiles per unit: a voucher segment (at least half a share) then always has rows to vouch for;
+        // a database of a few tiles gets one unit per query tile unit
+        const int64_t by_db = (int64_t)tiles * ntiles / 4;
+        if (by_db < units) units = (int)(by_db > tiles ? by_db : tiles);
+        int nv_min = 1 << 30, nseg_max = 0;
+        for (int t = 0; t < tiles; t++) {
+            int u_lo, nfw, nv, head;
+            k2::tile_slots(t, tiles, units, u_lo, nfw, nv, head);
+            if (nv < nv_min) nv_min = nv;
+            if (nfw + head > nseg_max) nseg_max = nfw + head;
         }
-        const int ns_min = units / tiles;
-        if ((kp + halves * ns_min - 1) / (halves * ns_min) > k2::JSLOTS) return false;
+        if ((kp + halves * nv_min - 1) / (halves * nv_min) > k2::JSLOTS) return false;
         *units_out = units;
+        *nv_min_out = nv_min;
+        *nseg_max_out = nseg_max;
         return true;
     };
     // (1) CTA pairs halve the L2->SM traffic of the database blocks; worth it once the batch spans several
     //     128-query tiles (an odd tile count wastes half a pair on padding).
     const char* no_pair = getenv("B200FLAT_NO_PAIR");
-    int units = 0;
+    int units = 0, nv_min = 1, nseg_max = 1;
     if (!(no_pair && no_pair[0] == '1') && kblocks <= k2::QRES_MAX_KB && plan->nq_tiles >= 2 &&
-        (plan->nq_tiles % 2 == 0 || plan->nq_tiles >= 7) && try_list((plan->nq_tiles + 1) / 2, kNumSMs / 2, &units)) {
+        (plan->nq_tiles % 2 == 0 || plan->nq_tiles >= 7) && try_list((plan->nq_tiles + 1) / 2, kNumSMs / 2, &units, &nv_min, &nseg_max)) {
         plan->pair_mode = 1;
         plan->list_mode = 1;
         plan->nq_tiles = 2 * ((plan->nq_tiles + 1) / 2);
         plan->tile_units = plan->nq_tiles / 2;
-    } else if (try_list(plan->nq_tiles, kNumSMs, &units)) {
+    } else if (try_list(plan->nq_tiles, kNumSMs, &units, &nv_min, &nseg_max)) {
         plan->list_mode = 1;
         plan->tile_units = plan->nq_tiles;
     } else {
@@ -1159,16 +1276,28 @@ int plan_tensor_scan(int nq, int64_t n, int d, int kp, TensorScanPlan* plan) {
         units = plan->nq_tiles * ns;
     }
     plan->units = units;
-    const int ns_min = units / plan->tile_units, ns_max = (units + plan->tile_units - 1) / plan->tile_units;
-    plan->nsplits = ns_min;  // HEAP mode: exact; LIST mode: the smaller of the two per-tile split counts
-    plan->nlists = plan->list_mode ? ns_max * halves : ns_min;  // lists allocated per query (stride)
-    const int nl_min = plan->list_mode ? ns_min * halves : ns_min;
-    const int j = (kp + nl_min - 1) / nl_min;
+    plan->nsplits = units / plan->tile_units;   // HEAP mode: exact; LIST mode: whole units per query tile (diagnostics)
+    if (!plan->list_mode) {
+        plan->nlists = plan->nsplits;
+        plan->list_j = kp;
+        plan->list_g = 1;
+        plan->list_cap = 0;
+        return B2F_OK;
+    }
+    plan->nlists = nseg_max * halves;           // lists allocated per query (stride)
+    const int j = (kp + nv_min * halves - 1) / (nv_min * halves);
     plan->list_j = j;
     plan->list_g = (kp + j - 1) / j;
+    // database tiles per round of the interleaved sweep: about two per full-length segment
+    {
+        int r = 2 * ((units + plan->tile_units - 1) / plan->tile_units);
+        if (r < 2) r = 2;
+        if (r > 512) r = 512;
+        plan->round_tiles = r;
+    }
     // expected list length ~ 32 (blind first chunk) + (j + spread) * ln(rows per list / 32); 2.5x headroom
     {
-        const double rows_per_list = (double)n / nl_min;
+        const double rows_per_list = (double)n * plan->tile_units / units / halves;
         const double expected = 32.0 + (j + 2.5) * log(rows_per_list > 64.0 ? rows_per_list / 32.0 : 2.0);
         int cap = (int)(2.5 * expected);
         cap = (cap + 63) / 64 * 64;
@@ -1177,6 +1306,27 @@ int plan_tensor_scan(int nq, int64_t n, int d, int kp, TensorScanPlan* plan) {
         plan->list_cap = cap;
     }
     return B2F_OK;
+}
+
+// diagnostics / CPU tests: the work of one unit under the balanced split, computed by the very functions the kernel runs
+int plan_unit_work(int T, int U, int R, int64_t ntiles, int unit, int32_t* seg_info, int64_t* tiles, int64_t cap, int32_t* counts) {
+    if (T < 1 || U < T || R < 1 || ntiles < 0 || unit < 0 || unit >= U || !seg_info || !counts) return -1;
+    k2::Seg seg[2];
+    const int nseg = k2::unit_segments(unit, T, U, seg);
+    for (int s = 0; s < nseg; s++) {
+        seg_info[5 * s + 0] = seg[s].qtile;
+        seg_info[5 * s + 1] = seg[s].slot;
+        seg_info[5 * s + 2] = seg[s].nv;
+        seg_info[5 * s + 3] = (int32_t)seg[s].p0;
+        seg_info[5 * s + 4] = (int32_t)seg[s].p1;
+        k2::SegIter it;
+        it.init(seg[s].p0, seg[s].p1, U, R, ntiles);
+        int32_t c = 0;
+        for (int64_t t; (t = it.next()) >= 0; c++)
+            if (tiles && c < cap) tiles[(int64_t)s * cap + c] = t;
+        counts[s] = c;
+    }
+    return nseg;
 }
 
 int launch_tensor_scan(const __nv_bfloat16* scan, int64_t dpad, const float* norms, int64_t n, int metric,
@@ -1214,14 +1364,6 @@ int launch_tensor_scan(const __nv_bfloat16* scan, int64_t dpad, const float* nor
         la.cap = plan.list_cap;
         la.final_thr = lists.final_thr;
         {
-            static int extra = -1;
-            if (extra < 0) {
-                const char* e = getenv("B200FLAT_THR_EXTRA");
-                extra = e ? atoi(e) : 0;
-                if (extra < 0) extra = 0;
-                if (extra > 3) extra = 3;
-            }
-            la.extra = extra;
             static int early = -1;
             if (early < 0) {
                 const char* e = getenv("B200FLAT_EARLY_REFRESH");
@@ -1244,17 +1386,14 @@ int launch_tensor_scan(const __nv_bfloat16* scan, int64_t dpad, const float* nor
             static int die_mode = -1;
             if (die_mode < 0) {
                 const char* e = getenv("B200FLAT_DIE_MODE");
-                die_mode = e ? atoi(e) : 1;   // same-box A/B at C2: 0.616 -> 0.610 ms
+                die_mode = e ? atoi(e) : 1;
                 if (die_mode < 0 || die_mode > 3) die_mode = 1;
             }
-            static int strided = -1;
-            if (strided < 0) {
-                const char* e = getenv("B200FLAT_STRIDED_SPLITS");
-                strided = (e && e[0] == '0') ? 0 : 1;   // same-box A/B at C2: DRAM read 1.52 GB -> 0.87 GB, 0.594 -> 0.575 ms
-            }
-            la.strided = strided;
-            la.die_mode = lists.die_ctr ? die_mode : 0;
+            la.die_mode = (lists.die_ctr && plan.tile_units > 1) ? die_mode : 0;   // one query tile: every block has one reader
             la.die_ctr = lists.die_ctr;
+            la.bal_T = plan.tile_units;
+            la.bal_U = plan.units;
+            la.bal_R = plan.round_tiles;
         }
         // lists.shared_thr was filled with 0x7f7f7f7f (3.39e38, "no information yet") by the query-prep kernel
         if (plan.pair_mode)

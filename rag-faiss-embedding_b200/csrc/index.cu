@@ -381,15 +381,13 @@ int tensor_kprime(int k, int slack) {
     return kp <= 256 ? kp : 0;
 }
 
-// Query chunking of the tensor path.  Two reasons to process a batch in several passes:
-//  (1) feasibility -- big k' with a big batch leaves too few database splits per query tile for the shared-
-//      threshold lists;
-//  (2) balance -- units (CTAs / CTA pairs, one wave) are dealt over the query tiles, and the pass lasts as long
-//      as the tiles with the FEWEST splits: 4096 queries = 16 pair tiles over 74 pairs gives 4 or 5 splits, so
-//      every unit of a 4-split tile works through 1/4 of the database while the ideal share is 16/74 = 1/4.6.
-//      Two passes of 8 pair tiles (9 or 10 splits) cost 2/9 instead of 1/4: 11% less time for one more launch.
-// The planner evaluates 1..8 equal passes with a small cost model (tensor time of the slowest unit, floored by
-// the HBM time of one database pass, plus a fixed per-pass overhead) and returns the chunk size of the cheapest.
+// Query chunking of the tensor path.  A batch is processed in several passes for feasibility only: more query tile
+// units than units (one wave), or a big k' with so many tiles that a tile is left with too few voucher lists for the
+// shared threshold (j <= 16).  Balance is no longer a reason: a pass's work is shared equally among the units whatever
+// the tile count is (k2::Seg), so 16 pair tiles over 74 pairs cost 16/74 of the database per unit in ONE pass (before:
+// tiles got 4 or 5 whole units, and two passes of 8 tiles were cheaper than one of 16).
+// The planner still evaluates 1..8 equal passes and a few fixed pass sizes with a small cost model (tensor time per
+// unit, floored by the HBM time of one database pass, plus a fixed per-pass overhead) and returns the cheapest.
 int plan_tensor_chunked(int nq, int64_t n, int d, int kp, TensorScanPlan* plan) {
     int feasible = nq;
     while (true) {
@@ -427,7 +425,10 @@ int plan_tensor_chunked(int nq, int64_t n, int d, int kp, TensorScanPlan* plan) 
         if (plan_tensor_scan(chunk, n, d, kp, &p) != B2F_OK) continue;
         const int passes = (nq + chunk - 1) / chunk;
         const double waves = p.list_mode ? 1.0 : (double)((p.units + kNumSMs - 1) / kNumSMs);
-        double t_mma = (double)n / p.nsplits * 128.0 * dpad * 2.0 / kSmRate * waves;  // slowest unit, per SM
+        // rows every unit streams: LIST mode shares the pass equally (tile_units / units of the database per unit,
+        // whatever the two numbers are), HEAP mode splits every tile nsplits ways
+        const double rows_per_unit = p.list_mode ? (double)n * p.tile_units / p.units : (double)n / p.nsplits;
+        double t_mma = rows_per_unit * 128.0 * dpad * 2.0 / kSmRate * waves;  // per SM
         if (!p.list_mode) t_mma *= 6.0;   // per-thread heaps instead of shared-threshold lists
         const double cost = passes * ((t_mma > t_hbm ? t_mma : t_hbm) + kPassOverhead);
         if (cost < best_cost * 0.97) {  // a new candidate has to buy at least 3%
@@ -568,12 +569,12 @@ int32_t b2f_index_metric(const b2f_index* ix) { return ix ? ix->metric : -1; }
 int32_t b2f_index_storage(const b2f_index* ix) { return ix ? ix->storage : -1; }
 int32_t b2f_index_device(const b2f_index* ix) { return ix ? ix->device : -1; }
 
-int b2f_plan_describe(int64_t nq, int64_t n, int32_t d, int64_t k, int32_t slack, int32_t out[11]) {
+int b2f_plan_describe(int64_t nq, int64_t n, int32_t d, int64_t k, int32_t slack, int32_t out[12]) {
     if (!out || nq <= 0 || n <= 0 || d <= 0 || k <= 0 || nq > (1 << 24)) {
         set_error("plan_describe: bad arguments");
         return B2F_EINVAL;
     }
-    for (int i = 0; i < 11; i++) out[i] = 0;
+    for (int i = 0; i < 12; i++) out[i] = 0;
     const int kp = k <= 1024 ? tensor_kprime((int)k, slack) : 0;
     if (kp <= 0) return B2F_OK;
     TensorScanPlan plan{};
@@ -590,7 +591,15 @@ int b2f_plan_describe(int64_t nq, int64_t n, int32_t d, int64_t k, int32_t slack
     out[8] = plan.list_j;
     out[9] = plan.list_cap;
     out[10] = plan.nq_tiles;
+    out[11] = plan.round_tiles;
     return B2F_OK;
+}
+
+int b2f_plan_unit_work(int32_t tile_units, int32_t units, int32_t round_tiles, int64_t db_tiles, int32_t unit, int32_t seg_info[10],
+                       int64_t* tiles, int64_t cap, int32_t counts[2]) {
+    const int rc = plan_unit_work(tile_units, units, round_tiles, db_tiles, unit, seg_info, tiles, cap, counts);
+    if (rc < 0) set_error("plan_unit_work: bad arguments");
+    return rc < 0 ? B2F_EINVAL : rc;
 }
 
 int b2f_index_stats(const b2f_index* cix, b2f_stats* out) {

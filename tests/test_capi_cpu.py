@@ -149,15 +149,17 @@ def test_tensor_path_planner():
     lib = _capi.load()
 
     def plan(nq, n, d, k, slack=0):
-        out = (ctypes.c_int32 * 11)()
+        out = (ctypes.c_int32 * 12)()
         assert lib.b2f_plan_describe(nq, n, d, k, slack, out) == 0
-        return dict(zip(["kp", "chunk", "passes", "list", "pair", "units", "ns_min", "nlists", "j", "cap", "tiles"], list(out)))
+        return dict(zip(["kp", "chunk", "passes", "list", "pair", "units", "ns_min", "nlists", "j", "cap", "tiles", "round"], list(out)))
 
     c2 = plan(1024, 1_000_000, 384, 10)               # BASELINE config 2
     assert c2["kp"] == 32 and c2["passes"] == 1 and c2["list"] == 1 and c2["pair"] == 1
     assert c2["units"] == 74 and c2["tiles"] == 8 and c2["ns_min"] == 18 and c2["j"] == 1
-    big = plan(4096, 1_000_000, 384, 10)              # 16 pair tiles over 74 pairs: two balanced passes of 8
-    assert big["passes"] == 2 and big["chunk"] == 2048 and big["ns_min"] == 9 and big["pair"] == 1
+    big = plan(4096, 1_000_000, 384, 10)              # 16 pair tiles over 74 pairs: ONE pass, every pair gets 16/74 of it
+    assert big["passes"] == 1 and big["chunk"] == 4096 and big["units"] == 74 and big["pair"] == 1 and big["j"] <= 8
+    n8 = plan(8192, 125_000, 384, 10)                 # the weak-scaling shape at N = 8: 32 pair tiles over 74 pairs
+    assert n8["passes"] == 1 and n8["units"] == 74 and n8["tiles"] == 64 and n8["list"] == 1 and n8["j"] <= 16
     c3 = plan(4096, 10_000_000, 768, 100)             # k' = 192 caps a pass (j <= 16); d = 768 rules out the Q-resident pair kernel
     assert c3["kp"] == 192 and c3["passes"] >= 2 and c3["pair"] == 0 and c3["j"] <= 16 and c3["list"] == 1
     one = plan(1, 1_000_000, 384, 10)                 # one tile: every SM streams its own split
@@ -177,6 +179,62 @@ def test_tensor_path_planner():
             if p["list"]:   # one wave, shared thresholds need every unit resident
                 assert p["units"] <= (74 if p["pair"] else 148) and p["j"] <= 16 and p["cap"] >= 128
                 assert p["nlists"] * p["j"] >= 1
+
+
+def test_balanced_work_split_is_an_exact_partition():
+    """The tensor pass's work split, computed by the functions the kernel itself runs (host build of k2::unit_segments /
+    k2::SegIter): for every query tile unit the segments' database tiles are every tile exactly once; every unit gets
+    the same amount of work (+-2 tiles) whatever the tile / unit counts are; list slots are dense per tile and all
+    segments of a tile agree on its voucher slots."""
+    from rag_faiss_embedding_b200 import _capi
+
+    lib = _capi.load()
+
+    def unit_work(T, U, R, ntiles, u, cap=60000):
+        seg, cnt, tiles = (ctypes.c_int32 * 10)(), (ctypes.c_int32 * 2)(), (ctypes.c_int64 * (2 * cap))()
+        n = lib.b2f_plan_unit_work(T, U, R, ntiles, u, seg, tiles, cap, cnt)
+        assert n in (1, 2), (T, U, u, n)
+        return [dict(qtile=seg[5 * s], slot=seg[5 * s + 1], nv=seg[5 * s + 2], p0=seg[5 * s + 3], p1=seg[5 * s + 4],
+                     tiles=list(tiles[s * cap:s * cap + cnt[s]])) for s in range(n)]
+
+    cases = [(4, 74, 38, 3907), (32, 74, 6, 489), (16, 74, 10, 48829), (1, 148, 296, 3907), (1, 74, 148, 3907), (74, 74, 2, 1000),
+             (73, 74, 4, 977), (37, 74, 4, 500), (5, 148, 60, 79), (64, 148, 6, 489), (3, 7, 6, 100), (7, 7, 2, 30),
+             (13, 148, 24, 40000), (8, 74, 20, 3907), (2, 3, 4, 9), (1, 1, 2, 5)]
+    for T, U, R, ntiles in cases:
+        per_tile = {t: [] for t in range(T)}
+        slots = {t: {} for t in range(T)}
+        totals = []
+        for u in range(U):
+            segs = unit_work(T, U, R, ntiles, u)
+            totals.append(sum(len(s["tiles"]) for s in segs))
+            for i, s in enumerate(segs):
+                assert s["tiles"] == sorted(s["tiles"])              # swept front to back
+                per_tile[s["qtile"]] += s["tiles"]
+                assert s["slot"] not in slots[s["qtile"]]
+                slots[s["qtile"]][s["slot"]] = s
+                if i == 1:                                            # the head of the next tile: never a voucher
+                    assert s["p0"] == 0 and s["slot"] >= s["nv"] and s["qtile"] == segs[0]["qtile"] + 1
+        for t in range(T):
+            assert sorted(per_tile[t]) == list(range(ntiles)), (T, U, R, ntiles, t)
+            ns = len(slots[t])
+            assert sorted(slots[t]) == list(range(ns))
+            nv = slots[t][0]["nv"]
+            assert 1 <= nv <= ns and all(s["nv"] == nv for s in slots[t].values())
+        ideal = T * ntiles / U
+        assert max(totals) - min(totals) <= 4 and max(totals) <= ideal + 3, (T, U, R, ntiles, min(totals), max(totals), ideal)
+    # plans the library makes are consistent with the split: the lists allocated per query cover every tile's segments
+    out = (ctypes.c_int32 * 12)()
+    for nq, n in ((1024, 1_000_000), (4096, 1_000_000), (8192, 125_000), (4096, 12_500_000), (300, 50_000), (128, 1_000_000)):
+        assert lib.b2f_plan_describe(nq, n, 384, 10, 0, out) == 0
+        kp, units, nlists, tiles, pair, rnd = out[0], out[5], out[7], out[10], out[4], out[11]
+        T = tiles // 2 if pair else tiles
+        ntiles = (n + 255) // 256
+        most = 0
+        for u in range(units):
+            for s in unit_work(T, units, rnd, ntiles, u, cap=1):
+                most = max(most, s["slot"] + 1)
+                assert kp <= 16 * 2 * s["nv"]
+        assert most * 2 == nlists, (nq, n, most, nlists)
 
 
 def test_bench_reference_arm_contract():
