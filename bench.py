@@ -207,7 +207,10 @@ def workload_config(wl, world, nq_total=None):
     else:
         sharding = ("rows in contiguous ranges over %d GPUs, batch %d = %d x N replicated; per-rank top-k exchanged and merged "
                     "by one kernel per rank over NVLink peer memory (12 nq k bytes per rank)" % (world, nq, wl["nq"]))
-    return {"workload": wl["label"], "rows_total": rows_total, "rows_per_gpu": rows_per_gpu, "d": d, "nq": nq, "k": wl["k"],
+    label = wl["label"]
+    if nq_total is not None and not wl.get("per_gpu") and nq != wl["nq"] * world:   # another batch size on the same rows (series)
+        label = "%s [batch %d]" % (label, nq)
+    return {"workload": label, "rows_total": rows_total, "rows_per_gpu": rows_per_gpu, "d": d, "nq": nq, "k": wl["k"],
             "metric": "L2" if wl["metric"] == 1 else "IP", "normalized": bool(wl["normalize"]), "storage": wl["storage"],
             "l2_policy": l2, "sharding": sharding}
 

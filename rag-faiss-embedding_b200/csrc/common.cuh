@@ -200,11 +200,13 @@ struct ScanFuse {                  // device-side view (kernel argument)
     int32_t nq_batch, certify;     // echoed to the host flag (adaptive slack)
     uint32_t* tub;                 // persistent [2][3][8]: per-query upper bound of the k-th best key (min over CTAs), all-ones when idle
     int32_t parity;                // launch parity: this launch uses tub[parity] and re-arms tub[parity ^ 1]
+    const float* mu;               // bf16 rows: centre added back to every stored row (null: none)
 };
 struct ScanArgs {                  // host-side launch description
     const float* rows_f32;         // fp32 rows, or
     const __nv_bfloat16* rows_bf16;
     int64_t pitch_bf16;
+    const float* mu;               // bf16 rows: the centre added back to every stored row (null: none)
     int64_t n;
     int d, metric, k;
     const float* q;                // [*, d] device fp32
@@ -244,8 +246,9 @@ int launch_merge_faiss(int metric, int64_t nq, int64_t k, int nparts, const floa
 // stats (device, 2 floats): running max |bf16(x)|^2 and max |x - bf16(x)|^2 (certification bound).
 // mu (optional, device [d]): the scan copy / norms / stats are taken of the centred rows x - mu; ip_bias: store
 // -mu.x instead of |x~'|^2 in norms (inner-product indexes: the row's bias in the tensor pass).
+// bf16_auth: bf16 storage -- the authoritative row is fl32(mu + scan row); the IP bias and stats[1] refer to it.
 int launch_ingest(const float* src, int64_t n, int d, float* rows_f32, __nv_bfloat16* scan, int64_t dpad,
-                  float* norms, float* stats, const float* mu, int ip_bias, cudaStream_t st);
+                  float* norms, float* stats, const float* mu, int ip_bias, int bf16_auth, cudaStream_t st);
 // mu[c] = mean of column c over the m rows of src
 int launch_mean_rows(const float* src, int64_t m, int d, float* mu, cudaStream_t st);
 // K7: pooling (+normalise) of encoder output, optionally fused with the ingest writes.
@@ -259,13 +262,14 @@ int launch_synth(uint64_t seed, int64_t row0, int64_t nrows, int d, int normaliz
 int launch_prep_queries(const float* q, int nq, int nq_pad, int d, __nv_bfloat16* qb, int64_t dpad, float* qnorm,
                         float* qerr, float* qconst, const float* mu, uint32_t* zero, int zero_words, uint32_t* fill,
                         int64_t fill_words, cudaStream_t st);
-int launch_bf16_to_f32(const __nv_bfloat16* src, int64_t pitch, int64_t n, int d, float* dst, cudaStream_t st);
+int launch_bf16_to_f32(const __nv_bfloat16* src, int64_t pitch, int64_t n, int d, const float* mu, float* dst, cudaStream_t st);
 
 // K4: exact fp32 re-rank of coarse candidates + certification.
 struct RerankArgs {
     const float* rows_f32;          // authoritative fp32 rows (or null)
-    const __nv_bfloat16* rows_bf16; // authoritative bf16 rows when storage is bf16
+    const __nv_bfloat16* rows_bf16; // bf16 storage: the stored rows x~'; the authoritative row is fl32(centre + x~')
     int64_t pitch_bf16;
+    const float* centre;            // bf16 storage: the index's centre mu [d] (null: mu = 0)
     const float* q;                 // [nq, d] fp32
     const float* qnorm;             // |q|^2
     const float* qerr;              // |q' - bf16(q')|   (q' = q - mu)

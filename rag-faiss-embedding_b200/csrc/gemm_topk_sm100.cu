@@ -512,7 +512,9 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             int stage = 0;
             uint32_t phase = 0;
             const uint64_t l2_keep_policy = (PAIR && la.l2_keep) ? l2_policy_evict_last() : 0ull;
-            for (int sgi = 0; sgi < nseg; sgi++) {
+#pragma unroll 1
+#pragma unroll 1
+        for (int sgi = 0; sgi < nseg; sgi++) {   // (never unrolled: two copies of the loops below thrash the instruction cache)
                 const int qt = seg_qt(sgi);
                 if constexpr (QRES) {
                     // the whole query tile (all k-blocks) is loaded once per segment and stays in shared memory; a second
@@ -559,7 +561,9 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             int stage = 0;
             uint32_t phase = 0;
             int gt = 0;   // tiles so far: accumulator buffer and barrier phases run on across segments
-            for (int sgi = 0; sgi < nseg; sgi++) {
+#pragma unroll 1
+#pragma unroll 1
+        for (int sgi = 0; sgi < nseg; sgi++) {   // (never unrolled: two copies of the loops below thrash the instruction cache)
                 if constexpr (QRES) mbar_wait(q_full, (uint32_t)(sgi & 1));
                 SegIter it = seg_iter(sgi);
                 for (int64_t dbt; (dbt = it.next()) >= 0; gt++) {
@@ -604,7 +608,8 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     } else if (warp == 3) {
         // ===================== bias loader =====================
         int gt = 0;
-        for (int sgi = 0; sgi < nseg; sgi++) {
+#pragma unroll 1
+        for (int sgi = 0; sgi < nseg; sgi++) {   // (never unrolled: two copies of the loops below thrash the instruction cache)
             SegIter it = seg_iter(sgi);
             for (int64_t dbt; (dbt = it.next()) >= 0; gt++) {
                 const int acc = gt & 1;
@@ -674,7 +679,9 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             uint32_t* xpose = reinterpret_cast<uint32_t*>(smem + L::xpose_off) + ew * 1024;  // this warp's staging area
             const int64_t gstride = (int64_t)nq_tiles * BM;
             int gt = 0;   // tiles so far (accumulator / barrier phases run on across segments)
-            for (int sgi = 0; sgi < nseg; sgi++) {
+#pragma unroll 1
+#pragma unroll 1
+        for (int sgi = 0; sgi < nseg; sgi++) {   // (never unrolled: two copies of the loops below thrash the instruction cache)
             const int qrow = seg_qt(sgi) * BM + tid;
             const bool active = qrow < nq;
             const int vsplit = seg[sgi].slot * HALVES + half;

@@ -292,6 +292,7 @@ int enqueue_scan(b2f_index* ix, const float* qd, const int32_t* qsel, const int3
     a.rows_f32 = ix->storage == B2F_STORE_F32 ? ix->rows_f32 : nullptr;
     a.rows_bf16 = ix->scan;
     a.pitch_bf16 = ix->dpad;
+    a.mu = (ix->storage == B2F_STORE_BF16 && ix->mu_set) ? ix->centre : nullptr;
     a.n = ix->ntotal;
     a.d = ix->d;
     a.metric = ix->metric;
@@ -642,18 +643,19 @@ static int add_device_rows(b2f_index* ix, const float* src_dev, int64_t n, cudaS
     if (ix->storage == B2F_STORE_F32) {
         float* dst = ix->rows_f32 + ix->ntotal * ix->d;
         if (src_dev != dst) rows_out = dst;
-        // The scan copy is taken around the mean of the first rows the index sees (at most 65536), fixed from then
-        // on: any centre is correct, a representative one makes the bf16 pass far more decisive on embeddings
-        // that share a large common component.  (bf16 storage keeps mu = 0: there the scan copy IS the data.)
-        if (!ix->mu_set && ix->ntotal == 0 && centring_enabled()) {
-            B2F_TRY(launch_mean_rows(src_dev, n < 65536 ? n : 65536, ix->d, ix->centre, st));
-            ix->mu_set = true;
-            ix->st.launches++;
-        }
+    }
+    // The scan copy is taken around the mean of the first rows the index sees (at most 65536), fixed from then on: any
+    // centre is correct, a representative one makes the bf16 pass far more decisive on embeddings that share a large
+    // common component.  bf16 storage keeps the same centred copy as its ONLY copy: the authoritative row is then
+    // fl32(mu + bf16(x - mu)) -- closer to x than bf16(x) on such data, and the tensor pass certifies as on fp32 storage.
+    if (!ix->mu_set && ix->ntotal == 0 && centring_enabled()) {
+        B2F_TRY(launch_mean_rows(src_dev, n < 65536 ? n : 65536, ix->d, ix->centre, st));
+        ix->mu_set = true;
+        ix->st.launches++;
     }
     B2F_TRY(launch_ingest(src_dev, n, ix->d, rows_out, ix->scan + ix->ntotal * ix->dpad, ix->dpad,
                           ix->norms + ix->ntotal, ix->stats, ix->mu_set ? ix->centre : nullptr,
-                          ix->metric == B2F_METRIC_INNER_PRODUCT ? 1 : 0, st));
+                          ix->metric == B2F_METRIC_INNER_PRODUCT ? 1 : 0, ix->storage == B2F_STORE_BF16 ? 1 : 0, st));
     ix->st.launches++;
     return B2F_OK;
 }
@@ -985,6 +987,7 @@ static int search_locked(b2f_index* ix, int64_t nq64, const float* q, int64_t k6
             ra.rows_f32 = ix->storage == B2F_STORE_F32 ? ix->rows_f32 : nullptr;
             ra.rows_bf16 = ix->scan;
             ra.pitch_bf16 = ix->dpad;
+            ra.centre = (ix->storage == B2F_STORE_BF16 && ix->mu_set) ? ix->centre : nullptr;
             ra.q = qc;
             ra.qnorm = qnorm;
             ra.qerr = qerr;
@@ -999,7 +1002,8 @@ static int search_locked(b2f_index* ix, int64_t nq64, const float* q, int64_t k6
             ra.metric = ix->metric;
             ra.ntotal = ix->ntotal;
             ra.max_row_norm = sqrtf(ix->host_stats[0]);
-            ra.max_row_err = ix->storage == B2F_STORE_F32 ? sqrtf(ix->host_stats[1]) : 0.f;
+            // fp32 storage: the bf16 rounding of the centred row; bf16 storage: what fl32(mu + x~') loses (0 uncentred)
+            ra.max_row_err = sqrtf(ix->host_stats[1]);
             ra.certify = certify;
             ra.D = Dd + (int64_t)c0 * k;  // the re-rank writes faiss-formatted results directly (no finalize launch)
             ra.I = Id + (int64_t)c0 * k;
@@ -1115,11 +1119,11 @@ int b2f_index_reconstruct(b2f_index* ix, int64_t i0, int64_t n, float* out, int3
     if (ix->storage == B2F_STORE_F32) {
         B2F_CUDA(cudaMemcpyAsync(out, ix->rows_f32 + i0 * ix->d, bytes, mem == B2F_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
     } else if (mem == B2F_MEM_DEVICE) {
-        B2F_TRY(launch_bf16_to_f32(ix->scan + i0 * ix->dpad, ix->dpad, n, ix->d, out, st));
+        B2F_TRY(launch_bf16_to_f32(ix->scan + i0 * ix->dpad, ix->dpad, n, ix->d, ix->mu_set ? ix->centre : nullptr, out, st));
         ix->st.launches++;
     } else {
         B2F_TRY(ensure_ws(ix, bytes + 4096));
-        B2F_TRY(launch_bf16_to_f32(ix->scan + i0 * ix->dpad, ix->dpad, n, ix->d, reinterpret_cast<float*>(ix->ws), st));
+        B2F_TRY(launch_bf16_to_f32(ix->scan + i0 * ix->dpad, ix->dpad, n, ix->d, ix->mu_set ? ix->centre : nullptr, reinterpret_cast<float*>(ix->ws), st));
         ix->st.launches++;
         B2F_CUDA(cudaMemcpyAsync(out, ix->ws, bytes, cudaMemcpyDeviceToHost, st));
     }
@@ -1171,7 +1175,7 @@ int b2f_index_write(b2f_index* ix, const char* path) {
                     e = cudaMemcpyAsync(hbuf, ix->rows_f32 + r0 * ix->d, (size_t)m * ix->d * 4, cudaMemcpyDeviceToHost, ix->stream);
                 } else {
                     float* dbuf = reinterpret_cast<float*>(ix->ws + (size_t)slot * cbytes);
-                    rc = launch_bf16_to_f32(ix->scan + r0 * ix->dpad, ix->dpad, m, ix->d, dbuf, ix->stream);
+                    rc = launch_bf16_to_f32(ix->scan + r0 * ix->dpad, ix->dpad, m, ix->d, ix->mu_set ? ix->centre : nullptr, dbuf, ix->stream);
                     ix->st.launches++;
                     e = cudaMemcpyAsync(hbuf, dbuf, (size_t)m * ix->d * 4, cudaMemcpyDeviceToHost, ix->stream);
                 }

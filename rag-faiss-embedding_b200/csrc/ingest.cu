@@ -23,15 +23,23 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // Writes one element group of a row to every derived store and returns (bf16(x)^2, (x-bf16(x))^2).
+// bf16_auth: the index keeps no fp32 rows -- the authoritative row IS r = fl32(m + bf16(x - m)); then the "rounding
+// error" of the scan copy is what the fp32 addition loses, (r - m) - bf16(x - m), and *r_out receives r.
 __device__ __forceinline__ void emit_elem(float x, int64_t row, int col, int d, float* rows_f32,
-                                          __nv_bfloat16* scan, int64_t dpad, float& nn, float& ee, float m = 0.f) {
+                                          __nv_bfloat16* scan, int64_t dpad, float& nn, float& ee, float m = 0.f,
+                                          bool bf16_auth = false, float* r_out = nullptr) {
     if (rows_f32) rows_f32[row * d + col] = x;
     const float xc = x - m;  // the scan copy holds the CENTRED row (see ingest_kernel)
     const __nv_bfloat16 b = __float2bfloat16_rn(xc);
     const float xb = __bfloat162float(b);
     if (scan) scan[row * dpad + col] = b;
     nn = fmaf(xb, xb, nn);
-    const float e = xc - xb;
+    float e = xc - xb;
+    if (bf16_auth) {
+        const float r = m + xb;
+        e = (float)((double)r - ((double)m + (double)xb));
+        if (r_out) *r_out = r;
+    }
     ee = fmaf(e, e, ee);
 }
 
@@ -61,10 +69,12 @@ int launch_mean_rows(const float* src, int64_t m, int d, float* mu, cudaStream_t
 // neighbour gaps of 1e-4; a random-init encoder: all cosines > 0.95), and bf16 rounding error scales with the
 // magnitude of what is rounded: centred, the certification bound is 5-30x tighter on such data.
 // stats[0] = max |x~'|^2, stats[1] = max |x' - x~'|^2 over every row ever ingested
+// bf16_auth (bf16 storage): there are no fp32 rows; the authoritative row is r = fl32(mu + x~'), so the IP bias is
+// -mu.r and stats[1] bounds |(r - mu) - x~'| (what the fp32 addition loses: ~1e-7 |r|), not the bf16 rounding.
 __global__ void __launch_bounds__(256)
 ingest_kernel(const float* __restrict__ src, int64_t n, int d, float* __restrict__ rows_f32,
               __nv_bfloat16* __restrict__ scan, int64_t dpad, float* __restrict__ norms, float* __restrict__ stats,
-              const float* __restrict__ mu, int ip_bias) {
+              const float* __restrict__ mu, int ip_bias, int bf16_auth) {
     const int lane = threadIdx.x & 31;
     const int64_t wpg = (int64_t)gridDim.x * (blockDim.x >> 5);
     // running maxima of the warp's rows: ONE atomic pair per warp at the end (two atomics per row on the same
@@ -77,9 +87,10 @@ ingest_kernel(const float* __restrict__ src, int64_t n, int d, float* __restrict
             for (int c = lane * 4; c < d; c += 128) {
                 float4 x = ldg_stream(reinterpret_cast<const float4*>(src + row * d + c));
                 if (rows_f32) *reinterpret_cast<float4*>(rows_f32 + row * d + c) = x;
+                float4 m4 = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (mu) {
-                    const float4 m4 = __ldg(reinterpret_cast<const float4*>(mu + c));
-                    if (ip_bias) mx += (double)m4.x * x.x + (double)m4.y * x.y + (double)m4.z * x.z + (double)m4.w * x.w;
+                    m4 = __ldg(reinterpret_cast<const float4*>(mu + c));
+                    if (ip_bias && !bf16_auth) mx += (double)m4.x * x.x + (double)m4.y * x.y + (double)m4.z * x.z + (double)m4.w * x.w;
                     x.x -= m4.x; x.y -= m4.y; x.z -= m4.z; x.w -= m4.w;
                 }
                 const __nv_bfloat162 lo = __floats2bfloat162_rn(x.x, x.y), hi = __floats2bfloat162_rn(x.z, x.w);
@@ -91,14 +102,22 @@ ingest_kernel(const float* __restrict__ src, int64_t n, int d, float* __restrict
                 }
                 const float b0 = __low2float(lo), b1 = __high2float(lo), b2 = __low2float(hi), b3 = __high2float(hi);
                 nn = fmaf(b0, b0, nn); nn = fmaf(b1, b1, nn); nn = fmaf(b2, b2, nn); nn = fmaf(b3, b3, nn);
-                const float e0 = x.x - b0, e1 = x.y - b1, e2 = x.z - b2, e3 = x.w - b3;
+                float e0 = x.x - b0, e1 = x.y - b1, e2 = x.z - b2, e3 = x.w - b3;
+                if (bf16_auth) {
+                    // the authoritative row: r = fl32(mu + x~'); what matters is how far r - mu is from x~'
+                    const float r0 = m4.x + b0, r1 = m4.y + b1, r2 = m4.z + b2, r3 = m4.w + b3;
+                    e0 = (float)((double)r0 - ((double)m4.x + (double)b0)); e1 = (float)((double)r1 - ((double)m4.y + (double)b1));
+                    e2 = (float)((double)r2 - ((double)m4.z + (double)b2)); e3 = (float)((double)r3 - ((double)m4.w + (double)b3));
+                    if (ip_bias) mx += (double)m4.x * r0 + (double)m4.y * r1 + (double)m4.z * r2 + (double)m4.w * r3;
+                }
                 ee = fmaf(e0, e0, ee); ee = fmaf(e1, e1, ee); ee = fmaf(e2, e2, ee); ee = fmaf(e3, e3, ee);
             }
         } else {
             for (int c = lane; c < d; c += 32) {
                 const float x = src[row * d + c], m = mu ? mu[c] : 0.f;
-                if (ip_bias) mx += (double)m * x;
-                emit_elem(x, row, c, d, rows_f32, scan, dpad, nn, ee, m);
+                float r = x;
+                emit_elem(x, row, c, d, rows_f32, scan, dpad, nn, ee, m, bf16_auth != 0, &r);
+                if (ip_bias) mx += (double)m * r;   // r = x (fp32 rows) or the authoritative rounded row (bf16 storage)
             }
         }
         if (scan)
@@ -117,12 +136,12 @@ ingest_kernel(const float* __restrict__ src, int64_t n, int d, float* __restrict
 }
 
 int launch_ingest(const float* src, int64_t n, int d, float* rows_f32, __nv_bfloat16* scan, int64_t dpad, float* norms,
-                  float* stats, const float* mu, int ip_bias, cudaStream_t st) {
+                  float* stats, const float* mu, int ip_bias, int bf16_auth, cudaStream_t st) {
     if (n <= 0) return B2F_OK;
     const int wpb = 8;
     int64_t blocks = (n + wpb - 1) / wpb;
     if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-    ingest_kernel<<<(unsigned)blocks, wpb * 32, 0, st>>>(src, n, d, rows_f32, scan, dpad, norms, stats, mu, ip_bias);
+    ingest_kernel<<<(unsigned)blocks, wpb * 32, 0, st>>>(src, n, d, rows_f32, scan, dpad, norms, stats, mu, ip_bias, bf16_auth);
     B2F_CUDA(cudaGetLastError());
     return B2F_OK;
 }
@@ -356,19 +375,21 @@ int launch_prep_queries(const float* q, int nq, int nq_pad, int d, __nv_bfloat16
     return B2F_OK;
 }
 
+// the authoritative rows of a bf16-storage index: r = fl32(mu + x~') (mu null: the rounded rows themselves)
 __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ src, int64_t pitch, int64_t n, int d,
-                                   float* __restrict__ dst) {
+                                   const float* __restrict__ mu, float* __restrict__ dst) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n * d) return;
     const int64_t r = t / d;
     const int c = (int)(t - r * d);
-    dst[t] = __bfloat162float(src[r * pitch + c]);
+    const float v = __bfloat162float(src[r * pitch + c]);
+    dst[t] = mu ? mu[c] + v : v;
 }
 
-int launch_bf16_to_f32(const __nv_bfloat16* src, int64_t pitch, int64_t n, int d, float* dst, cudaStream_t st) {
+int launch_bf16_to_f32(const __nv_bfloat16* src, int64_t pitch, int64_t n, int d, const float* mu, float* dst, cudaStream_t st) {
     const int64_t total = n * d;
     if (total <= 0) return B2F_OK;
-    bf16_to_f32_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, pitch, n, d, dst);
+    bf16_to_f32_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, pitch, n, d, mu, dst);
     B2F_CUDA(cudaGetLastError());
     return B2F_OK;
 }

@@ -55,9 +55,15 @@ __device__ __forceinline__ float exact_key_8lanes(const RerankArgs& a, const flo
                         const float4 qa = __ldg(reinterpret_cast<const float4*>(qv + j));
                         const float4 qb = __ldg(reinterpret_cast<const float4*>(qv + j + 4));
                         const float qq[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+                        float mm[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                        if (a.centre) {   // the authoritative row: fl32(centre + stored bf16 value)
+                            const float4 ma = __ldg(reinterpret_cast<const float4*>(a.centre + j));
+                            const float4 mb = __ldg(reinterpret_cast<const float4*>(a.centre + j + 4));
+                            mm[0] = ma.x; mm[1] = ma.y; mm[2] = ma.z; mm[3] = ma.w; mm[4] = mb.x; mm[5] = mb.y; mm[6] = mb.z; mm[7] = mb.w;
+                        }
 #pragma unroll
                         for (int h = 0; h < 4; h++) {
-                            const float x0 = __uint_as_float(ww[h] << 16), x1 = __uint_as_float(ww[h] & 0xffff0000u);
+                            const float x0 = mm[2 * h] + __uint_as_float(ww[h] << 16), x1 = mm[2 * h + 1] + __uint_as_float(ww[h] & 0xffff0000u);
                             if (l2) {
                                 const float t0 = x0 - qq[2 * h], t1 = x1 - qq[2 * h + 1];
                                 acc = fmaf(t0, t0, acc); acc = fmaf(t1, t1, acc);
@@ -71,7 +77,7 @@ __device__ __forceinline__ float exact_key_8lanes(const RerankArgs& a, const flo
         } else {
             for (int j = sl; j < a.d; j += 8) {
                 const float xv = a.rows_f32 ? a.rows_f32[(int64_t)id * a.d + j]
-                                            : __bfloat162float(a.rows_bf16[(int64_t)id * a.pitch_bf16 + j]);
+                                            : (a.centre ? a.centre[j] : 0.f) + __bfloat162float(a.rows_bf16[(int64_t)id * a.pitch_bf16 + j]);
                 if (l2) {
                     const float t = xv - qv[j];
                     acc = fmaf(t, t, acc);

@@ -83,7 +83,14 @@ scan_kernel(const RowT* __restrict__ rows, int64_t pitch, int64_t n, int d, int 
     int32_t* li = reinterpret_cast<int32_t*>(lk + kScanWarps * NQ * k);  // [warps][NQ][k]
     // [kGatherCap] (key, id) composites of the final selection, 8-byte aligned behind the lists
     unsigned long long* gath = reinterpret_cast<unsigned long long*>(smem + (((size_t)NQ * dq + 2 * (size_t)kScanWarps * NQ * k + 1) & ~(size_t)1));
+    // bf16 storage: the authoritative row is fl32(mu + stored value) -- the centre [dq] sits behind the gather area
+    // (zeros when the index is not centred: x + 0 is exact)
+    constexpr bool kBf16Rows = sizeof(RowT) == 2;
+    float* smu = reinterpret_cast<float*>(gath + kGatherCap);
     __shared__ int s_m;
+    if constexpr (kBf16Rows) {
+        for (int i = threadIdx.x; i < dq; i += kScanThreads) smu[i] = (f.mu && i < d) ? f.mu[i] : 0.f;
+    }
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     cg::grid_group grid = cg::this_grid();
@@ -171,6 +178,19 @@ scan_kernel(const RowT* __restrict__ rows, int64_t pitch, int64_t n, int d, int 
             Vec x[R];
 #pragma unroll
             for (int r = 0; r < R; r++) x[r].unpack(xn[r]);
+            if constexpr (kBf16Rows) {
+                float mv[VN];
+#pragma unroll
+                for (int h = 0; h < VN / 4; h++) {
+                    const float4 t = *reinterpret_cast<const float4*>(smu + c * VN + 4 * h);
+                    mv[4 * h] = t.x; mv[4 * h + 1] = t.y; mv[4 * h + 2] = t.z; mv[4 * h + 3] = t.w;
+                }
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+#pragma unroll
+                    for (int e = 0; e < VN; e++) x[r].v[e] = mv[e] + x[r].v[e];
+                }
+            }
             if (c + kWarp < nchunk) {
 #pragma unroll
                 for (int r = 0; r < R; r++)
@@ -349,7 +369,8 @@ size_t scan_scratch_bytes(int k) {
 template <int NQ, bool L2, typename RowT, typename Vec>
 static int launch_one(const RowT* rows, int64_t pitch, const ScanArgs& a, cudaStream_t st) {
     const int dq = ((a.d + Vec::N - 1) / Vec::N) * Vec::N;
-    const size_t smem = (((size_t)NQ * dq + 2 * (size_t)kScanWarps * NQ * a.k + 1) & ~(size_t)1) * 4 + (size_t)kGatherCap * 8;
+    const size_t smem = (((size_t)NQ * dq + 2 * (size_t)kScanWarps * NQ * a.k + 1) & ~(size_t)1) * 4 + (size_t)kGatherCap * 8 +
+                        (sizeof(RowT) == 2 ? (size_t)dq * 4 : 0);   // + the centre (bf16 rows)
     auto kern = scan_kernel<NQ, L2, RowT, Vec>;
     int occ = 1;
     {
@@ -404,6 +425,7 @@ static int launch_one(const RowT* rows, int64_t pitch, const ScanArgs& a, cudaSt
     f.certify = a.certify;
     f.tub = a.tub;
     f.parity = a.parity;
+    f.mu = a.mu;
     const RowT* rows_ = rows;
     int64_t pitch_ = pitch, n_ = a.n;
     int d_ = a.d, dq_ = dq, k_ = a.k;

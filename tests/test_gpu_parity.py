@@ -316,6 +316,45 @@ def test_centred_scan_copy_certifies_embedding_like_data(m):
     _check(D, I, *orc.np_search_f64(xb[:5000] - 3.0, xq[:64] - 3.0, k, 1), 1)
 
 
+@pytest.mark.parametrize("metric", [1, 0])
+def test_centred_bf16_storage_certifies_embedding_like_data(m, metric, tmp_path):
+    """The bf16-storage twin of the test above (BASELINE configs[3] stores bf16): rows sharing a large common
+    component are stored as bf16(x - mu), so the tensor pass stays decisive and certifies (nearly) every query; the
+    stored rows are also CLOSER to the fp32 input than a plain bf16 cast; results are exact on the authoritative rows,
+    through add in two batches, write_index / read_index and the exact scan."""
+    import torch
+
+    rng = np.random.default_rng(22)
+    n, d, nq, k = 50000, 384, 256, 10
+    common = rng.standard_normal(d).astype(np.float32) * 0.4
+    scale = 0.02 if metric == 1 else 0.1
+    xb = (common[None, :] + rng.standard_normal((n, d)).astype(np.float32) * scale).astype(np.float32)
+    xq = (common[None, :] + rng.standard_normal((nq, d)).astype(np.float32) * scale).astype(np.float32)
+    if metric == 0:
+        xb = (xb / np.linalg.norm(xb, axis=1, keepdims=True)).astype(np.float32)
+        xq = (xq / np.linalg.norm(xq, axis=1, keepdims=True)).astype(np.float32)
+    ix = m.IndexFlat(d, metric, storage=m.STORE_BF16)
+    ix.add(xb[:30000])
+    ix.add(xb[30000:])
+    rows = ix.reconstruct_n()
+    plain = torch.from_numpy(xb).to(torch.bfloat16).to(torch.float32).numpy()
+    assert np.abs(rows - xb).max() < 0.25 * np.abs(plain - xb).max()     # centred rounding is several times finer
+    ix.set_search_params(algo=m.ALGO_TENSOR)
+    D, I = ix.search(xq, k)
+    _check(D, I, *orc.np_search_f64(rows, xq, k, metric), metric)
+    st = ix.stats()
+    assert st["last_algo"] == m.ALGO_TENSOR and st["fallback_queries"] <= nq // 20, (metric, st)
+    Ds, Is = ix.set_search_params(algo=m.ALGO_SCAN).search(xq[:9], k)
+    _check(Ds, Is, *orc.np_search_f64(rows, xq[:9], k, metric), metric)
+    # the file holds the authoritative rows in fp32 (FAISS layout); an fp32-storage index read from it answers alike
+    path = tmp_path / "bf16.bin"
+    m.write_index(ix, path)
+    back = m.read_index(path)
+    assert np.array_equal(back.reconstruct_n(), rows)
+    D2, I2 = back.set_search_params(algo=m.ALGO_TENSOR).search(xq, k)
+    _check(D2, I2, D, I, metric)
+
+
 def test_very_large_batch_is_cut_into_list_passes(m):
     """20000 queries are far more than one wave of query tiles: the planner cuts the batch into LIST-mode passes
     (not the multi-wave HEAP selection); results must be exact and independent of the cut."""
@@ -425,18 +464,22 @@ def test_auto_dispatch(m):
     _check(D, I, *orc.np_search_f64(xb, orc.c_synth_rows(2, 0, 64, 128), 200, 1), 1)
 
 
-# ---- bf16 storage: the oracle runs on the rounded rows -------------------------------------------------
+# ---- bf16 storage: the oracle runs on the authoritative (rounded) rows ----------------------------------
 @pytest.mark.parametrize("algo_name", ["scan", "tensor"])
 def test_bf16_storage(m, algo_name):
-    import torch
-
+    """bf16 storage keeps ONE copy: bf16(x - mu) around the index's centre mu (mean of the first rows); the
+    authoritative row is fl32(mu + bf16(x - mu)), which is what reconstruct / write_index return and what both
+    search paths measure distances to."""
     n, d, nq, k = 20000, 384, 40, 10
     xb = orc.c_synth_rows(1234, 0, n, d)
-    xb_r = torch.from_numpy(xb).to(torch.bfloat16).to(torch.float32).numpy()
     xq = orc.c_synth_rows(5678, 0, nq, d)
     ix = m.IndexFlat(d, 1, storage=m.STORE_BF16)
     ix.add(xb)
-    assert np.array_equal(ix.reconstruct_n(0, 100), xb_r[:100])
+    xb_r = ix.reconstruct_n()
+    mu = xb.mean(0)
+    # within the bf16 rounding of the CENTRED value (2^-9 relative), plus slack for the centre being an fp32 mean
+    assert np.all(np.abs(xb_r - xb) <= 2.0 ** -8 * np.abs(xb - mu) + 1e-3)
+    assert np.array_equal(ix.reconstruct(7), xb_r[7]) and np.array_equal(ix.reconstruct_n(100, 50), xb_r[100:150])
     ix.set_search_params(algo=m.ALGO_SCAN if algo_name == "scan" else m.ALGO_TENSOR)
     D, I = ix.search(xq, k)
     _check(D, I, *orc.np_search_f64(xb_r, xq, k, 1), 1)
@@ -631,15 +674,13 @@ def test_large_bf16_index_properties(m):
     """> 4 GiB of bf16 rows (6M x 384) and long per-split streams: exercises 64-bit addressing, the adaptive
     candidate-list capacity and the overflow path.  Checked through size-independent properties: self
     queries return themselves at distance 0, and the tensor path agrees with the exact scan."""
-    import torch
-
     n, d, k = 6_000_000, 384, 10
     ix = m.IndexFlat(d, 1, storage=m.STORE_BF16)
     ix.reserve(n)
     ix.add_synthetic(1234, 0, n)
     rows = [0, 1, n // 2, n - 1]
-    q_self = np.stack([orc.c_synth_rows(1234, r, 1, d)[0] for r in rows])
-    q_self = torch.from_numpy(q_self).to(torch.bfloat16).to(torch.float32).numpy()   # the stored (rounded) rows
+    q_self = np.stack([ix.reconstruct(r) for r in rows])   # the stored (authoritative, rounded) rows
+    assert np.allclose(q_self, np.stack([orc.c_synth_rows(1234, r, 1, d)[0] for r in rows]), rtol=2.0 ** -7, atol=1e-2)
     xq = np.concatenate([q_self, orc.c_synth_rows(5678, 0, 1020, d)])
     Dt, It = ix.set_search_params(algo=m.ALGO_TENSOR).search(xq, k)
     assert It[:4, 0].tolist() == rows and (Dt[:4, 0] == 0).all()
