@@ -866,6 +866,16 @@ static int search_locked(b2f_index* ix, int64_t nq64, const float* q, int64_t k6
     // of it because of the unpacking), so every batch size goes to the tensor path there.
     const int scan_max = P.scan_max_nq > 0 ? P.scan_max_nq : (ix->storage == B2F_STORE_BF16 ? 0 : 1);
     int kp = tensor_kprime(k, P.slack);
+    {
+        // diagnostics: B200FLAT_KPRIME=<multiple of 8> forces k' (LIST-mode shapes; same-box A/B of the candidate count)
+        static int kp_env = -1;
+        if (kp_env < 0) {
+            const char* e = getenv("B200FLAT_KPRIME");
+            kp_env = e ? atoi(e) : 0;
+            if (kp_env < 0 || kp_env > 256 || (kp_env & 7)) kp_env = 0;
+        }
+        if (kp_env >= k + 2 && kp > 0) kp = kp_env;
+    }
     if (kp > 0 && P.slack <= 0 && ix->slack_boost > 0) {  // adaptive slack learned from earlier searches on this index
         int boosted = ((kp + ix->slack_boost + 7) / 8) * 8;
         if (boosted > 64) kp = boosted <= 256 ? boosted : 256;
