@@ -583,8 +583,12 @@ def main():
     ap.add_argument("--no-c4", action="store_true", help="skip the BASELINE configs[3] record (12.5M bf16 rows per GPU)")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
+    ap.add_argument("--nq", type=int, default=0, help="diagnostics: another batch size on the workload's rows")
     args = ap.parse_args()
-    wl = WORKLOADS[args.workload]
+    wl = dict(WORKLOADS[args.workload])
+    if args.nq > 0:
+        wl["nq"] = args.nq
+        wl["label"] += " [--nq %d]" % args.nq
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

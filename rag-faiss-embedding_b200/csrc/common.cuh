@@ -290,6 +290,7 @@ struct RerankArgs {
     int32_t* fail_list;             // queries that could not be certified (q + q_base), re-run by the closing exact scan
     int32_t* fail_count;            // [0] uncertified queries, [1] of which list overflows, [2..3] u64 list entries
     int32_t q_base;                 // first query of this pass within the whole batch (query chunks)
+    int32_t stage1;                 // LIST merge: candidates tried first on their own (0 = off; see merge_lists_kernel)
 };
 int launch_rerank(const RerankArgs& a, cudaStream_t st);
 

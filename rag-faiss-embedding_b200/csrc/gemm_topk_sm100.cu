@@ -208,6 +208,13 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// Database tiles of every (unit, segment), computed on the host with SegIter and passed by value: the epilogue -- the
+// kernel's critical path, at the register cap -- then runs a counted loop and takes each tile's first row from shared
+// memory (the bias loader publishes it with the biases) instead of stepping an iterator of its own.
+struct SegCounts {
+    int32_t n[2 * kNumSMs];
+};
+
 template <int KP, int NST, int QKB = 0, bool PAIRED = false>
 struct Smem {
     static constexpr size_t q_off = 0;                                   // resident query tile: QKB x 16 KB
@@ -221,7 +228,7 @@ struct Smem {
     static constexpr size_t bar_off = xpose_off + (KP == 0 ? (size_t)EPI_WARPS_LIST * 32 * 32 * 4 : 0);
     static constexpr int nbars = 2 * NST + 10;
     static constexpr size_t tmem_off = bar_off + nbars * 8;
-    static constexpr size_t total = tmem_off + 16;
+    static constexpr size_t total = tmem_off + 32;   // TMEM base holder, die-ticket scratch, row0 of the tile in each bias buffer
     static constexpr size_t alloc = total;  // the dynamic smem base is declared __align__(1024)
 };
 
@@ -292,33 +299,59 @@ __host__ __device__ __forceinline__ int unit_segments(int u, int T, int U, Seg (
     return 1;
 }
 // The database tiles of one segment, in sweep order.  Contiguous form (HEAP mode): tiles [t0, t1).
+// Every role of the kernel steps one of these per tile and the epilogue is the kernel's critical path, so the state
+// is 32-bit and a step is a compare + add; a round change is two mul.hi / mul.lo pairs (the first version carried
+// 64-bit fixed point through every step: +9% executed instructions, -8% kernel throughput, ncu r02e).
 struct SegIter {
-    uint64_t F0, F1;
-    int R, NR, r, j, jend;
-    int64_t ntiles;
+    uint32_t F0, F1;      // in-tile bounds as Q0.32 fractions of the tile; full1: the segment ends at the tile's end (1.0)
+    int R, NR, r, j, jend, base, ntiles;
+    bool full1;
     __host__ __device__ __forceinline__ void init(uint32_t p0, uint32_t p1, int U, int R_, int64_t ntiles_) {
-        F0 = ((uint64_t)p0 << 32) / (uint32_t)U;
-        F1 = ((uint64_t)p1 << 32) / (uint32_t)U;   // p1 == U -> exactly 2^32
+        F0 = (uint32_t)(((uint64_t)p0 << 32) / (uint32_t)U);
+        full1 = p1 >= (uint32_t)U;
+        F1 = full1 ? 0u : (uint32_t)(((uint64_t)p1 << 32) / (uint32_t)U);
         R = R_;
-        ntiles = ntiles_;
+        ntiles = (int)ntiles_;
         NR = (int)((ntiles_ + R_ - 1) / R_);
         r = -1;
         j = jend = 0;
+        base = -R_;
     }
     __host__ __device__ __forceinline__ void init_contig(int64_t t0, int64_t t1) {
-        F0 = 0; F1 = 0; R = 0; NR = 0; r = 0;   // r * R + j == j
-        ntiles = t1;
+        F0 = F1 = 0u; full1 = false; R = 0; NR = 0; r = 0; base = 0;
+        ntiles = (int)t1;
         j = (int)t0; jend = (int)t1;
+    }
+    // (F * Rr + phi) >> 32 for a Q0.32 fraction F
+    static __host__ __device__ __forceinline__ int cut(uint32_t F, uint32_t Rr, uint32_t phi) {
+#ifdef __CUDA_ARCH__
+        const uint32_t hi = __umulhi(F, Rr);
+#else
+        const uint32_t hi = (uint32_t)(((uint64_t)F * Rr) >> 32);
+#endif
+        const uint32_t lo = F * Rr;
+        return (int)(hi + ((lo + phi) < lo ? 1u : 0u));
+    }
+    __host__ __device__ __forceinline__ int count() {   // tiles of the whole segment (consumes the iterator)
+        int c = jend - j;
+        while (++r < NR) {
+            base += R;
+            const uint32_t Rr = (r == NR - 1) ? (uint32_t)(ntiles - base) : (uint32_t)R;
+            const uint32_t phi = (uint32_t)r * 2654435769u;
+            c += (full1 ? (int)Rr : cut(F1, Rr, phi)) - cut(F0, Rr, phi);
+        }
+        return c;
     }
     __host__ __device__ __forceinline__ int64_t next() {   // -1 when exhausted
         while (true) {
-            if (j < jend) return (int64_t)r * R + j++;
+            if (j < jend) return (int64_t)(base + j++);
             if (++r >= NR) return -1;
+            base += R;
             // the last round holds what is left of the database and is shared out the same way
-            const uint64_t Rr = (r == NR - 1) ? (uint64_t)(ntiles - (int64_t)r * R) : (uint64_t)R;
-            const uint64_t phi = (uint32_t)((uint32_t)r * 2654435769u);
-            j = (int)((F0 * Rr + phi) >> 32);
-            jend = (int)((F1 * Rr + phi) >> 32);
+            const uint32_t Rr = (r == NR - 1) ? (uint32_t)(ntiles - base) : (uint32_t)R;
+            const uint32_t phi = (uint32_t)r * 2654435769u;
+            j = cut(F0, Rr, phi);
+            jend = full1 ? (int)Rr : cut(F1, Rr, phi);
         }
     }
 };
@@ -365,7 +398,7 @@ template <int KP, bool L2, bool LIST, bool QRES, bool PAIR>
 __global__ void __launch_bounds__(k2_threads(LIST), 1)
 tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
                    const float* __restrict__ norms, int64_t n, int nq, int kblocks, int nq_tiles, int nsplits,
-                   float* __restrict__ pk, int32_t* __restrict__ pi, ListArgs la) {
+                   float* __restrict__ pk, int32_t* __restrict__ pi, ListArgs la, const __grid_constant__ SegCounts seg_counts) {
     static_assert(!QRES || LIST, "the Q-resident variant exists for LIST mode only");
     static_assert(!PAIR || QRES, "the CTA-pair variant builds on the Q-resident one");
     constexpr int STAGES = PAIR ? STAGES_PAIR : (QRES ? STAGES_QRES : (LIST ? STAGES_LIST : STAGES_HEAP));
@@ -389,6 +422,7 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     uint64_t* bias_empty = bars + 2 * STAGES + 7;  // [2]       epilogue -> bias loader (PAIR: local to each CTA)
     uint64_t* q_empty = bars + 2 * STAGES + 9;     // [1]       MMA -> TMA: the resident query tile may be replaced (next segment)
     uint32_t* tmem_base_holder = reinterpret_cast<uint32_t*>(smem + L::tmem_off);
+    volatile int32_t* tile_row0 = reinterpret_cast<volatile int32_t*>(smem + L::tmem_off + 16);   // [2], written with bias[acc]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // PAIR: a cluster of two CTAs (one TPC) works on 256 queries x one database stream; CTA rank r owns
@@ -455,18 +489,39 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     const int split = LIST ? 0 : unit / units_per_split;
     if constexpr (LIST) {
         nseg = unit_segments(unit, la.bal_T, la.bal_U, seg);
+        if (nseg == 1) seg[1] = seg[0];
     } else {
         seg[0].qtile = unit % units_per_split; seg[0].slot = split; seg[0].nv = 0; seg[0].p0 = 0u; seg[0].p1 = 0u;
         heap_t0 = ntiles * split / nsplits;
         heap_t1 = ntiles * (split + 1) / nsplits;
     }
+    // (fields are selected with ?: instead of indexing seg[] with the loop variable: a dynamically indexed local array
+    // lives in local memory, and values loaded from there are not warp-uniform for the compiler)
+    auto seg_of = [&](int s_) {
+        Seg r;
+        r.qtile = s_ == 0 ? seg[0].qtile : seg[1].qtile;
+        r.slot = s_ == 0 ? seg[0].slot : seg[1].slot;
+        r.nv = s_ == 0 ? seg[0].nv : seg[1].nv;
+        r.p0 = s_ == 0 ? seg[0].p0 : seg[1].p0;
+        r.p1 = s_ == 0 ? seg[0].p1 : seg[1].p1;
+        return r;
+    };
     auto seg_iter = [&](int s_) {
         SegIter it;
-        if constexpr (LIST) it.init(seg[s_].p0, seg[s_].p1, la.bal_U, la.bal_R, ntiles);
-        else it.init_contig(heap_t0, heap_t1);
+        if constexpr (LIST) {
+            const Seg g = seg_of(s_);
+            it.init(g.p0, g.p1, la.bal_U, la.bal_R, ntiles);
+        } else {
+            it.init_contig(heap_t0, heap_t1);
+        }
         return it;
     };
-    auto seg_qt = [&](int s_) { return PAIR ? seg[s_].qtile * 2 + (int)cta_rank : seg[s_].qtile; };
+    auto seg_qt = [&](int s_) {
+        const int qtile = s_ == 0 ? seg[0].qtile : seg[1].qtile;
+        return PAIR ? qtile * 2 + (int)cta_rank : qtile;
+    };
+    // tiles of segment s_ (host-computed with SegIter, passed by value): the loop count of the roles that need no tile index
+    auto seg_tiles_of = [&](int s_) { return LIST ? seg_counts.n[2 * unit + s_] : (int)(heap_t1 - heap_t0); };
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_q)) : "memory");
@@ -508,7 +563,12 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        // The WHOLE warp runs the loops (warp-uniform control flow and values, so descriptors and addresses live in the
+        // uniform datapath); lane 0 alone issues.  With the loops inside `if (lane == 0)` the compiler loses uniformity
+        // as soon as the trip counts come from an iterator: every tcgen05.mma then cost 17 instructions (five
+        // R2UR.BROADCAST among them) instead of 10 and the single issuing thread became the kernel's bottleneck
+        // (ncu r02e: the epilogue's wait for tmem_full went from 6.6% to 11% of the stall samples, -6% throughput).
+        {
             int stage = 0;
             uint32_t phase = 0;
             const uint64_t l2_keep_policy = (PAIR && la.l2_keep) ? l2_policy_evict_last() : 0ull;
@@ -520,32 +580,39 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                     // the whole query tile (all k-blocks) is loaded once per segment and stays in shared memory; a second
                     // segment replaces it once the MMAs of the first have read it for the last time
                     if (sgi > 0) mbar_wait(q_empty, (uint32_t)((sgi - 1) & 1));
-                    if constexpr (PAIR) {
-                        // both CTAs load their own 128-query tile; the bytes of both are credited to the leader's barrier
-                        if (cta_rank == 0) mbar_expect_tx(q_full, (uint32_t)(2 * kblocks * A_BYTES));
-                        for (int kb = 0; kb < kblocks; kb++)
-                            tma_load_2d_pair(smem + L::q_off + (size_t)kb * A_BYTES, &map_q, kb * BK, qt * BM, q_full);
-                    } else {
-                        mbar_expect_tx(q_full, (uint32_t)(kblocks * A_BYTES));
-                        for (int kb = 0; kb < kblocks; kb++) tma_load_2d(smem + L::q_off + (size_t)kb * A_BYTES, &map_q, kb * BK, qt * BM, q_full);
+                    if (lane == 0) {
+                        if constexpr (PAIR) {
+                            // both CTAs load their own 128-query tile; the bytes of both are credited to the leader's barrier
+                            if (cta_rank == 0) mbar_expect_tx(q_full, (uint32_t)(2 * kblocks * A_BYTES));
+                            for (int kb = 0; kb < kblocks; kb++)
+                                tma_load_2d_pair(smem + L::q_off + (size_t)kb * A_BYTES, &map_q, kb * BK, qt * BM, q_full);
+                        } else {
+                            mbar_expect_tx(q_full, (uint32_t)(kblocks * A_BYTES));
+                            for (int kb = 0; kb < kblocks; kb++) tma_load_2d(smem + L::q_off + (size_t)kb * A_BYTES, &map_q, kb * BK, qt * BM, q_full);
+                        }
                     }
+                    __syncwarp();
                 }
                 SegIter it = seg_iter(sgi);
                 for (int64_t dbt; (dbt = it.next()) >= 0;) {
-                    const int row0 = (int)(dbt * BN);
+                    const int row0 = __shfl_sync(kFull, (int)(dbt * BN), 0);   // (warp-uniform for the compiler, as in the MMA issuer)
                     for (int kb = 0; kb < kblocks; kb++) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
-                        uint8_t* sa = smem + L::stages_off + (size_t)stage * kStageBytes;
-                        if constexpr (PAIR) {
-                            // this CTA's half of the 256-row block; the leader's full barrier collects both halves
-                            if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * kStageBytes);
-                            if (la.l2_keep) tma_load_2d_pair_hint(sa, &map_x, kb * BK, row0 + (int)cta_rank * (BN / 2), &full_bar[stage], l2_keep_policy);
-                            else tma_load_2d_pair(sa, &map_x, kb * BK, row0 + (int)cta_rank * (BN / 2), &full_bar[stage]);
-                        } else {
-                            mbar_expect_tx(&full_bar[stage], kStageBytes);
-                            if constexpr (!QRES) tma_load_2d(sa, &map_q, kb * BK, qt * BM, &full_bar[stage]);
-                            tma_load_2d(sa + (QRES ? 0 : A_BYTES), &map_x, kb * BK, row0, &full_bar[stage]);
+                        const int ustage = __shfl_sync(kFull, stage, 0);
+                        uint8_t* sa = smem + L::stages_off + (size_t)ustage * kStageBytes;
+                        if (lane == 0) {
+                            if constexpr (PAIR) {
+                                // this CTA's half of the 256-row block; the leader's full barrier collects both halves
+                                if (cta_rank == 0) mbar_expect_tx(&full_bar[ustage], 2 * kStageBytes);
+                                if (la.l2_keep) tma_load_2d_pair_hint(sa, &map_x, kb * BK, row0 + (int)cta_rank * (BN / 2), &full_bar[ustage], l2_keep_policy);
+                                else tma_load_2d_pair(sa, &map_x, kb * BK, row0 + (int)cta_rank * (BN / 2), &full_bar[ustage]);
+                            } else {
+                                mbar_expect_tx(&full_bar[ustage], kStageBytes);
+                                if constexpr (!QRES) tma_load_2d(sa, &map_q, kb * BK, qt * BM, &full_bar[ustage]);
+                                tma_load_2d(sa + (QRES ? 0 : A_BYTES), &map_x, kb * BK, row0, &full_bar[ustage]);
+                            }
                         }
+                        __syncwarp();
                         if (++stage == STAGES) {
                             stage = 0;
                             phase ^= 1;
@@ -557,7 +624,8 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         __syncwarp();
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0 && cta_rank == 0) {  // PAIR: only the leader CTA issues MMAs
+        // (whole warp, uniform control flow; lane 0 issues -- see the producer)
+        if (cta_rank == 0) {  // PAIR: only the leader CTA issues MMAs
             int stage = 0;
             uint32_t phase = 0;
             int gt = 0;   // tiles so far: accumulator buffer and barrier phases run on across segments
@@ -565,42 +633,53 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 #pragma unroll 1
         for (int sgi = 0; sgi < nseg; sgi++) {   // (never unrolled: two copies of the loops below thrash the instruction cache)
                 if constexpr (QRES) mbar_wait(q_full, (uint32_t)(sgi & 1));
-                SegIter it = seg_iter(sgi);
-                for (int64_t dbt; (dbt = it.next()) >= 0; gt++) {
+                const int seg_tiles = seg_tiles_of(sgi);
+#pragma unroll 1
+                for (int t = 0; t < seg_tiles; t++, gt++) {
                     const int acc = gt & 1;
                     const uint32_t acc_phase = (gt >> 1) & 1;
                     mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                    // (broadcast from lane 0: tells the compiler the operands are warp-uniform, so the descriptor arithmetic
+                    // runs in the uniform datapath instead of per-MMA R2UR.BROADCAST sequences)
+                    const uint32_t d_tmem = __shfl_sync(kFull, tmem_base + (uint32_t)(acc * BN), 0);
                     for (int kb = 0; kb < kblocks; kb++) {
                         mbar_wait(&full_bar[stage], phase);
                         tc_fence_after();
-                        const uint32_t sa = smem_u32(smem + L::stages_off + (size_t)stage * kStageBytes);
-                        const uint64_t adesc = make_smem_desc(QRES ? smem_u32(smem + L::q_off + (size_t)kb * A_BYTES) : sa);
+                        const uint32_t sa = __shfl_sync(kFull, smem_u32(smem + L::stages_off + (size_t)stage * kStageBytes), 0);
+                        const uint32_t qa = __shfl_sync(kFull, smem_u32(smem + L::q_off + (size_t)kb * A_BYTES), 0);
+                        const uint64_t adesc = make_smem_desc(QRES ? qa : sa);
                         const uint64_t bdesc = make_smem_desc(sa + (QRES ? 0 : A_BYTES));
+                        if (lane == 0) {
 #pragma unroll
-                        for (int k = 0; k < BK / UMMA_K; k++) {
-                            // advance both descriptors by 32 bytes (16 bf16) inside the 128-byte swizzle atom
-                            if constexpr (PAIR)
-                                umma_bf16_pair(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), kIdescPair, (kb | k) != 0 ? 1u : 0u);
-                            else
-                                umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), (kb | k) != 0 ? 1u : 0u);
+                            for (int k = 0; k < BK / UMMA_K; k++) {
+                                // advance both descriptors by 32 bytes (16 bf16) inside the 128-byte swizzle atom
+                                if constexpr (PAIR)
+                                    umma_bf16_pair(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), kIdescPair, (kb | k) != 0 ? 1u : 0u);
+                                else
+                                    umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), (kb | k) != 0 ? 1u : 0u);
+                            }
+                            if constexpr (PAIR) umma_commit_pair(&empty_bar[stage]);
+                            else umma_commit(&empty_bar[stage]);
                         }
-                        if constexpr (PAIR) umma_commit_pair(&empty_bar[stage]);
-                        else umma_commit(&empty_bar[stage]);
+                        __syncwarp();
                         if (++stage == STAGES) {
                             stage = 0;
                             phase ^= 1;
                         }
                     }
-                    if constexpr (PAIR) umma_commit_pair(&tmem_full[acc]);
-                    else umma_commit(&tmem_full[acc]);
+                    if (lane == 0) {
+                        if constexpr (PAIR) umma_commit_pair(&tmem_full[acc]);
+                        else umma_commit(&tmem_full[acc]);
+                    }
+                    __syncwarp();
                 }
                 if constexpr (QRES) {
-                    if (sgi + 1 < nseg) {   // every MMA that reads this segment's query tile has been issued: free it
+                    if (sgi + 1 < nseg && lane == 0) {   // every MMA that reads this segment's query tile has been issued: free it
                         if constexpr (PAIR) umma_commit_pair(q_empty);
                         else umma_commit(q_empty);
                     }
+                    __syncwarp();
                 }
             }
         }
@@ -623,6 +702,7 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                     if (row < n) b = __ldg(norms + row);  // L2: |x~'|^2; IP: -mu.x (0 without centring)
                     bias[acc * BN + j * 32 + lane] = b;
                 }
+                if (lane == 0) tile_row0[acc] = (int32_t)row0;   // the epilogue takes the tile's first row from here
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bias_full[acc]);
             }
@@ -682,11 +762,12 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 #pragma unroll 1
 #pragma unroll 1
         for (int sgi = 0; sgi < nseg; sgi++) {   // (never unrolled: two copies of the loops below thrash the instruction cache)
+            const Seg sg = seg_of(sgi);
             const int qrow = seg_qt(sgi) * BM + tid;
             const bool active = qrow < nq;
-            const int vsplit = seg[sgi].slot * HALVES + half;
-            const int nvs = seg[sgi].nv * HALVES;          // voucher virtual splits of this query tile
-            const bool voucher = seg[sgi].slot < seg[sgi].nv;
+            const int vsplit = sg.slot * HALVES + half;
+            const int nvs = sg.nv * HALVES;          // voucher virtual splits of this query tile
+            const bool voucher = sg.slot < sg.nv;
             const int jv = (la.kp + nvs - 1) / nvs;      // rows each voucher vouches for
             const int gv = (la.kp + jv - 1) / jv;        // vouchers consulted: gv * jv >= k'
             const int vstart = voucher ? vsplit : vsplit % nvs;   // own value first; the others spread over the vouchers
@@ -718,16 +799,13 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 }
                 thr = t0;
             };
-            auto process = [&](const uint32_t (&r)[32], int t, int c, const float* tbc, int32_t rowc) {
-                // refresh schedule: thresholds move like 1/rows_seen, so consult the other splits often
-                // at the start and rarely later
-                // (from the third tile on the refresh happens at the top of the tile loop, while the thread would
-                // otherwise wait for the MMAs of the tile -- see below)
-                const bool do_refresh = t == 0 || (t == 1 && (c & 1) == 0) ||
-                                        (!la.early && c == 0 && (t < 8 || (t < 32 && (t & 3) == 0) || (t & 15) == 0));
+            auto process = [&](const uint32_t (&r)[32], bool do_refresh, bool first_wait, const float* tbc, int32_t rowc) {
+                // refresh schedule (the caller's rmask): thresholds move like 1/rows_seen, so consult the other splits
+                // often at the start and rarely later (from the third tile on the refresh happens at the top of the tile
+                // loop, while the thread would otherwise wait for the MMAs of the tile -- see below)
                 if (active && do_refresh) {
                     refresh();
-                    if (t == 0 && c == 1) {
+                    if (first_wait) {   // second chunk of the segment's first tile
                         // Every first-wave virtual split has now seen 32 rows and published.  CTAs start a few
                         // microseconds apart; wait (bounded -- never a hard dependency) for the slowest of
                         // the vouchers we consult instead of appending blindly into the list meanwhile.
@@ -774,19 +852,23 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                     }
                 }
             };
-            SegIter it = seg_iter(sgi);
-            int t = 0;   // tile index within the segment (refresh schedule)
-            for (int64_t dbt; (dbt = it.next()) >= 0; t++, gt++) {
+            const int seg_tiles = seg_tiles_of(sgi);   // (host-computed with SegIter: no iterator in this role)
+#pragma unroll 1
+            for (int t = 0; t < seg_tiles; t++, gt++) {   // t: tile index within the segment (refresh schedule)
                 const int acc = gt & 1;
                 const uint32_t acc_phase = (gt >> 1) & 1;
                 // Scheduled refresh of the shared threshold BEFORE waiting for the tile's accumulator: the ~1.4 us
                 // of L2 round trips overlap the MMAs the thread would wait for anyway, and no accumulator registers
                 // are live yet (same-box A/B: the refreshes inside the tile cost 3-4% of the kernel).
                 if (la.early && active && t >= 2 && (t < 8 || (t < 32 && (t & 3) == 0) || (t & la.period_mask) == 0)) refresh();
+                // which chunks of this tile start with a refresh: all of tile 0, every other one of tile 1, then (only
+                // without the early refresh above) the first chunk of scheduled tiles
+                const uint32_t rmask = t == 0 ? 0xffffffffu : (t == 1 ? 0x55555555u
+                                     : ((!la.early && (t < 8 || (t < 32 && (t & 3) == 0) || (t & 15) == 0)) ? 1u : 0u));
                 mbar_wait(&bias_full[acc], acc_phase);
                 mbar_wait(&tmem_full[acc], acc_phase);
                 tc_fence_after();
-                const int32_t row0 = (int32_t)(dbt * BN) + half * COLS;
+                const int32_t row0 = tile_row0[acc] + half * COLS;
                 const float* tb = bias + acc * BN + half * COLS;
                 const uint32_t tile_taddr = lane_taddr + (uint32_t)(acc * BN + half * COLS);
                 uint32_t ra[32], rb[32];
@@ -795,10 +877,10 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 for (int c = 0; c < COLS / 32; c += 2) {
                     tmem_ld_wait();
                     tmem_ld32(tile_taddr + (uint32_t)((c + 1) * 32), rb);
-                    process(ra, t, c, tb + c * 32, row0 + c * 32);
+                    process(ra, ((rmask >> c) & 1u) != 0u, false, tb + c * 32, row0 + c * 32);
                     tmem_ld_wait();
                     if (c + 2 < COLS / 32) tmem_ld32(tile_taddr + (uint32_t)((c + 2) * 32), ra);
-                    process(rb, t, c + 1, tb + (c + 1) * 32, row0 + (c + 1) * 32);
+                    process(rb, ((rmask >> (c + 1)) & 1u) != 0u, t == 0 && c == 0, tb + (c + 1) * 32, row0 + (c + 1) * 32);
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -842,15 +924,14 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 heap_i[j * EPI_THREADS + tid] = -1;
             }
             float thr = FLT_MAX;
-            SegIter it = seg_iter(0);
-            int t = 0;
-            for (int64_t dbt; (dbt = it.next()) >= 0; t++) {
+            const int heap_tiles = seg_tiles_of(0);
+            for (int t = 0; t < heap_tiles; t++) {
                 const int acc = t & 1;
                 const uint32_t acc_phase = (t >> 1) & 1;
                 mbar_wait(&bias_full[acc], acc_phase);
                 mbar_wait(&tmem_full[acc], acc_phase);
                 tc_fence_after();
-                const int32_t row0 = (int32_t)(dbt * BN);
+                const int32_t row0 = tile_row0[acc];
                 const float* tb = bias + acc * BN;
                 const uint32_t tile_taddr = lane_taddr + (uint32_t)(acc * BN);
 #pragma unroll 1
@@ -1140,7 +1221,14 @@ merge_lists_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ c
     const float tc = dec_key(s_tc_enc);
     const int nc1 = M < kp ? M : kp;
     const float bound1 = (M > kp) ? fminf(sk[kp - 1], tc) : tc;
-    bool cert = rerank_block(ra, q, sk, si, nc1, bound1, M < kp, ek, ei);
+    // Big batches are bound by the random row reads of the re-rank (8192 queries x 32 candidates x 1.5 KB = 400 MB), so
+    // they first try the best `stage1` coarse candidates alone: every other row has a coarse key >= sk[stage1], and on
+    // data the bf16 pass separates well that already certifies ~95% of the queries with half the rows read.  (Small
+    // batches are latency-bound: a failed first stage would cost them a dependent round trip, so they skip it.)
+    bool cert = false;
+    if (ra.certify && ra.stage1 >= ra.k && ra.stage1 < nc1)
+        cert = rerank_block(ra, q, sk, si, ra.stage1, fminf(sk[ra.stage1], tc), false, ek, ei);
+    if (!cert) cert = rerank_block(ra, q, sk, si, nc1, bound1, M < kp, ek, ei);
     if (!cert && ra.certify && M > kp && M <= RANK_MAX) {
         // every list entry: rows outside the lists have coarse keys above T_c
         cert = rerank_block(ra, q, sk, si, M, tc, false, ek, ei);
@@ -1186,10 +1274,37 @@ static int make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t
     return B2F_OK;
 }
 
+// Database tiles of every (unit, segment) of a LIST plan -- the epilogue's loop counts.  Cached per thread: a serving
+// loop repeats the same (tile units, units, round, database) shape, and one evaluation walks units x rounds steps.
+static const SegCounts& segment_counts(const TensorScanPlan& plan, int64_t ntiles) {
+    struct Key {
+        int T, U, R;
+        int64_t ntiles;
+    };
+    static thread_local Key key{-1, -1, -1, -1};
+    static thread_local SegCounts sc;
+    if (key.T != plan.tile_units || key.U != plan.units || key.R != plan.round_tiles || key.ntiles != ntiles) {
+        for (int i = 0; i < 2 * kNumSMs; i++) sc.n[i] = 0;
+        for (int u = 0; u < plan.units && u < kNumSMs; u++) {
+            Seg seg[2];
+            const int nseg = unit_segments(u, plan.tile_units, plan.units, seg);
+            for (int sg = 0; sg < nseg; sg++) {
+                SegIter it;
+                it.init(seg[sg].p0, seg[sg].p1, plan.units, plan.round_tiles, ntiles);
+                sc.n[2 * u + sg] = it.count();
+            }
+        }
+        key = Key{plan.tile_units, plan.units, plan.round_tiles, ntiles};
+    }
+    return sc;
+}
+
 template <int KP, bool L2, bool LIST, bool QRES, bool PAIR = false>
 static int launch_k2(const CUtensorMap& mq, const CUtensorMap& mx, const float* norms, int64_t n, int nq, int kblocks,
                      const TensorScanPlan& plan, float* pk, int32_t* pi, const ListArgs& la, cudaStream_t st) {
     auto kern = tensor_scan_kernel<KP, L2, LIST, QRES, PAIR>;
+    static const SegCounts no_counts{};
+    const SegCounts& sc = LIST ? segment_counts(plan, (n + BN - 1) / BN) : no_counts;
     constexpr size_t smem = Smem < LIST ? 0 : KP, PAIR ? STAGES_PAIR : (QRES ? STAGES_QRES : (LIST ? STAGES_LIST : STAGES_HEAP)),
                      QRES ? QRES_MAX_KB : 0, PAIR > ::alloc;
     static_assert(smem <= 232448, "shared memory budget exceeded");
@@ -1215,10 +1330,10 @@ static int launch_k2(const CUtensorMap& mq, const CUtensorMap& mx, const float* 
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        B2F_CUDA(cudaLaunchKernelEx(&cfg, kern, mq, mx, norms, n, nq, kblocks, plan.nq_tiles, plan.nsplits, pk, pi, la));
+        B2F_CUDA(cudaLaunchKernelEx(&cfg, kern, mq, mx, norms, n, nq, kblocks, plan.nq_tiles, plan.nsplits, pk, pi, la, sc));
     } else {
         kern<<<plan.units, k2_threads(LIST), smem, st>>>(mq, mx, norms, n, nq, kblocks, plan.nq_tiles, plan.nsplits,
-                                                                  pk, pi, la);
+                                                                  pk, pi, la, sc);
     }
     B2F_CUDA(cudaGetLastError());
     return B2F_OK;
@@ -1300,6 +1415,8 @@ int plan_tensor_scan(int nq, int64_t n, int d, int kp, TensorScanPlan* plan) {
         int r = 2 * ((units + plan->tile_units - 1) / plan->tile_units);
         if (r < 2) r = 2;
         if (r > 512) r = 512;
+        const char* e = getenv("B200FLAT_ROUND_TILES");   // diagnostics: database tiles per round of the sweep
+        if (e && atoi(e) >= 1 && atoi(e) <= 4096) r = atoi(e);
         plan->round_tiles = r;
     }
     // expected list length ~ 32 (blind first chunk) + (j + spread) * ln(rows per list / 32); 2.5x headroom

@@ -1021,6 +1021,16 @@ static int search_locked(b2f_index* ix, int64_t nq64, const float* q, int64_t k6
             ra.fail_list = fail_list;
             ra.fail_count = counters;
             ra.q_base = c0;
+            {   // first-stage re-rank of big (throughput-bound) batches: k + max(6, k / 4) candidates, a multiple of 8
+                static int s1_env = -2;
+                if (s1_env == -2) {
+                    const char* e = getenv("B200FLAT_STAGE1");   // diagnostics: -1 = off, 0 = default, n = forced
+                    s1_env = e ? atoi(e) : 0;
+                }
+                int n0 = ((k + (k / 4 > 6 ? k / 4 : 6)) + 7) / 8 * 8;
+                if (n0 < 16) n0 = 16;
+                ra.stage1 = s1_env > 0 ? s1_env : ((s1_env == 0 && nq >= 2048 && n0 < kp) ? n0 : 0);
+            }
             if (plan.list_mode) {
                 // K3b + K4 + finalize fused: per query, merge the lists, re-rank exactly, certify, write (D, I)
                 B2F_TRY(launch_merge_lists(lists, cn, plan, reinterpret_cast<unsigned long long*>(counters + 2), ra, st));
