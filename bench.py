@@ -208,7 +208,7 @@ def workload_config(wl, world, nq_total=None):
         sharding = ("rows in contiguous ranges over %d GPUs, batch %d = %d x N replicated; per-rank top-k exchanged and merged "
                     "by one kernel per rank over NVLink peer memory (12 nq k bytes per rank)" % (world, nq, wl["nq"]))
     label = wl["label"]
-    if nq_total is not None and not wl.get("per_gpu") and nq != wl["nq"] * world:   # another batch size on the same rows (series)
+    if nq_total is not None and nq != (wl["nq"] if wl.get("per_gpu") else wl["nq"] * world):   # another batch size on the same rows (series)
         label = "%s [batch %d]" % (label, nq)
     return {"workload": label, "rows_total": rows_total, "rows_per_gpu": rows_per_gpu, "d": d, "nq": nq, "k": wl["k"],
             "metric": "L2" if wl["metric"] == 1 else "IP", "normalized": bool(wl["normalize"]), "storage": wl["storage"],
@@ -659,6 +659,14 @@ def main():
             r["clocks"] = ck
             c4 = brief(r)
             c4["config"] = r["config"]
+        # the north star's small-batch target on this configuration: batch 1 and 32 against the HBM roofline
+        small = []
+        for nq_s in (1, 32):
+            rs = measure(c4ctx, nq_s, 10, sw, do_e2e=False, parity="off")
+            if rs:
+                small.append(brief(rs))
+        if c4 is not None and small:
+            c4["small_batches"] = small
         c4ctx.close()
 
     if rank == 0:

@@ -267,8 +267,9 @@ struct ListArgs {
 //
 // Lists / shared thresholds: a query tile's segments are its list SLOTS -- the segments that start inside the tile
 // ("first wave": they begin at kernel start) in position order, then the head segment (run by the unit that first
-// finishes the previous tile's tail).  Only first-wave segments of at least half the full length VOUCH (publish
-// their j-th best); they are slots [0, nv).  Every segment prunes against the max of gv vouchers' values.
+// finishes the previous tile's tail).  Only first-wave segments of (nearly) full length VOUCH (publish their j-th best:
+// a short segment's j-th best of few rows would loosen the shared bound for everyone who consults it); they are slots
+// [0, nv).  Every segment prunes against the max of g vouchers' values (voucher_rule below).
 struct Seg {
     int qtile;         // query tile unit
     int slot;          // list slot within the tile
@@ -280,9 +281,19 @@ __host__ __device__ __forceinline__ void tile_slots(int t, int T, int U, int& u_
     const int u_hi = (int)((((int64_t)t + 1) * U + T - 1) / T) - 1;       // last one
     nfw = u_hi - u_lo + 1;
     const int tail_len = (int)(((int64_t)t + 1) * U - (int64_t)u_hi * T);  // (0, T]: what the last one covers of tile t
-    nv = nfw - (2 * tail_len < T ? 1 : 0);
+    nv = nfw - (4 * tail_len < 3 * T ? 1 : 0);   // the tail vouches only when it is at least 3/4 of a full share
     if (nv < 1) nv = 1;
     head = ((int64_t)u_lo * T > (int64_t)t * U) ? 1 : 0;                  // unit u_lo - 1 spills into this tile
+}
+// How a thread turns the vouchers' published values into its threshold.  nvs voucher lists (voucher segments x column
+// halves) each publish their j-th best key, j = ceil(k' / nvs); a thread reads g = ceil(k' / j) of them (its own first)
+// and takes the MAXIMUM: g lists vouch for j rows each at or below it, g * j >= k', so it is an upper bound of the k'-th
+// best.  (Reading two spare values and taking the third largest -- which would let short tails vouch too -- cut the
+// survivors by a third and still made the kernel 4-13% SLOWER, same-box A/B r02j: the refresh sits on the epilogue's
+// critical path ~24 times per stream and every extra instruction in it counts.  Round 1 saw the same with its "extra".)
+__host__ __device__ __forceinline__ void voucher_rule(int kp, int nvs, int& j, int& g) {
+    j = (kp + nvs - 1) / nvs;
+    g = (kp + j - 1) / j;
 }
 __host__ __device__ __forceinline__ int unit_segments(int u, int T, int U, Seg (&seg)[2]) {
     const int64_t S0 = (int64_t)u * T, S1 = S0 + T;
@@ -768,8 +779,8 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             const int vsplit = sg.slot * HALVES + half;
             const int nvs = sg.nv * HALVES;          // voucher virtual splits of this query tile
             const bool voucher = sg.slot < sg.nv;
-            const int jv = (la.kp + nvs - 1) / nvs;      // rows each voucher vouches for
-            const int gv = (la.kp + jv - 1) / jv;        // vouchers consulted: gv * jv >= k'
+            int jv, gv;   // rows each voucher vouches for; vouchers consulted (gv * jv >= k')
+            voucher_rule(la.kp, nvs, jv, gv);
             const int vstart = voucher ? vsplit : vsplit % nvs;   // own value first; the others spread over the vouchers
             float best[JSLOTS];  // ascending; the first JSLOTS - j slots are pinned at -inf, so best[JSLOTS-1] = j-th best
 #pragma unroll
@@ -1369,7 +1380,7 @@ int plan_tensor_scan(int nq, int64_t n, int d, int kp, TensorScanPlan* plan) {
             if (nv < nv_min) nv_min = nv;
             if (nfw + head > nseg_max) nseg_max = nfw + head;
         }
-        if ((kp + halves * nv_min - 1) / (halves * nv_min) > k2::JSLOTS) return false;
+        if ((kp + halves * nv_min - 1) / (halves * nv_min) > k2::JSLOTS) return false;   // j <= JSLOTS with every voucher consulted
         *units_out = units;
         *nv_min_out = nv_min;
         *nseg_max_out = nseg_max;
@@ -1407,9 +1418,10 @@ int plan_tensor_scan(int nq, int64_t n, int d, int kp, TensorScanPlan* plan) {
         return B2F_OK;
     }
     plan->nlists = nseg_max * halves;           // lists allocated per query (stride)
-    const int j = (kp + nv_min * halves - 1) / (nv_min * halves);
+    int j, g;
+    k2::voucher_rule(kp, nv_min * halves, j, g);   // of the tile with the fewest vouchers (the largest j)
     plan->list_j = j;
-    plan->list_g = (kp + j - 1) / j;
+    plan->list_g = g;
     // database tiles per round of the interleaved sweep: about two per full-length segment
     {
         int r = 2 * ((units + plan->tile_units - 1) / plan->tile_units);
