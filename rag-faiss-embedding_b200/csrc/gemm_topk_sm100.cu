@@ -790,23 +790,41 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             uint2* mylist = la.cand + ((int64_t)(active ? qrow : 0) * la.nl_stride + vsplit) * la.cap;
             // shared thresholds are laid out [virtual split][query] so that a warp's loads for one split coalesce
             float* gq = la.shared_thr + (active ? qrow : 0);
-            auto refresh = [&]() {
+            // The refresh sits on the epilogue's critical path (~24 times per stream; the epilogue is what the tile period
+            // waits for), and its cost is L2 round trips: `wide` keeps 32 loads in flight -- one round trip for g <= 32 --
+            // where no accumulators are live (top of the tile loop, end of the segment); inside a tile 16.
+            auto refresh = [&](bool wide) {
                 if (voucher && best[JSLOTS - 1] < pub) {
                     pub = best[JSLOTS - 1];
                     __stcg(gq + (int64_t)vsplit * gstride, pub);
                 }
                 float t0 = -kInf;
+                if (wide) {
 #pragma unroll 1
-                for (int i0 = 0; i0 < gv; i0 += 16) {  // 16 independent L2 loads in flight
-                    float v[16];
+                    for (int i0 = 0; i0 < gv; i0 += 32) {
+                        float v[32];
 #pragma unroll
-                    for (int u = 0; u < 16; u++) {
-                        int s2 = vstart + i0 + u;
-                        if (s2 >= nvs) s2 -= nvs;
-                        v[u] = (i0 + u < gv) ? __ldcg(gq + (int64_t)s2 * gstride) : -kInf;
+                        for (int u = 0; u < 32; u++) {
+                            int s2 = vstart + i0 + u;
+                            if (s2 >= nvs) s2 -= nvs;
+                            v[u] = (i0 + u < gv) ? __ldcg(gq + (int64_t)s2 * gstride) : -kInf;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 32; u++) t0 = fmaxf(t0, v[u]);
                     }
+                } else {
+#pragma unroll 1
+                    for (int i0 = 0; i0 < gv; i0 += 16) {  // 16 independent L2 loads in flight
+                        float v[16];
 #pragma unroll
-                    for (int u = 0; u < 16; u++) t0 = fmaxf(t0, v[u]);
+                        for (int u = 0; u < 16; u++) {
+                            int s2 = vstart + i0 + u;
+                            if (s2 >= nvs) s2 -= nvs;
+                            v[u] = (i0 + u < gv) ? __ldcg(gq + (int64_t)s2 * gstride) : -kInf;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 16; u++) t0 = fmaxf(t0, v[u]);
+                    }
                 }
                 thr = t0;
             };
@@ -815,14 +833,14 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 // often at the start and rarely later (from the third tile on the refresh happens at the top of the tile
                 // loop, while the thread would otherwise wait for the MMAs of the tile -- see below)
                 if (active && do_refresh) {
-                    refresh();
+                    refresh(false);
                     if (first_wait) {   // second chunk of the segment's first tile
                         // Every first-wave virtual split has now seen 32 rows and published.  CTAs start a few
                         // microseconds apart; wait (bounded -- never a hard dependency) for the slowest of
                         // the vouchers we consult instead of appending blindly into the list meanwhile.
                         for (int spin = 0; spin < 64 && thr > 1.0e38f; spin++) {
                             __nanosleep(256);
-                            refresh();
+                            refresh(false);
                         }
                     }
                 }
@@ -871,7 +889,7 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 // Scheduled refresh of the shared threshold BEFORE waiting for the tile's accumulator: the ~1.4 us
                 // of L2 round trips overlap the MMAs the thread would wait for anyway, and no accumulator registers
                 // are live yet (same-box A/B: the refreshes inside the tile cost 3-4% of the kernel).
-                if (la.early && active && t >= 2 && (t < 8 || (t < 32 && (t & 3) == 0) || (t & la.period_mask) == 0)) refresh();
+                if (la.early && active && t >= 2 && (t < 8 || (t < 32 && (t & 3) == 0) || (t & la.period_mask) == 0)) refresh(true);
                 // which chunks of this tile start with a refresh: all of tile 0, every other one of tile 1, then (only
                 // without the early refresh above) the first chunk of scheduled tiles
                 const uint32_t rmask = t == 0 ? 0xffffffffu : (t == 1 ? 0x55555555u
@@ -908,7 +926,7 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 // End-of-segment pruning: the final shared threshold is far tighter than the ones most
                 // entries were admitted under (the first chunk is admitted blindly), so re-filter the
                 // thread's own list in place.  Shrinks the merge input ~10x (C2: 1460 -> ~100 per query).
-                refresh();
+                refresh(true);
                 const int have = cnt <= la.cap ? cnt : 0;  // an overflowed list is left as is (the query falls back)
                 int w = 0;
 #pragma unroll 1
@@ -1367,12 +1385,24 @@ int plan_tensor_scan(int nq, int64_t n, int d, int kp, TensorScanPlan* plan) {
     // many units as query tile units, a few database tiles per unit, and j = ceil(k' / voucher lists of a tile) <=
     // JSLOTS for every tile.
     auto try_list = [&](int tiles, int max_units, int* units_out, int* nv_min_out, int* nseg_max_out) -> bool {
+        {
+            const char* e = getenv("B200FLAT_MAX_UNITS");   // diagnostics: cap the units of a pass
+            if (e && atoi(e) >= 1 && atoi(e) < max_units) max_units = atoi(e);
+        }
         if (tiles > max_units || ntiles < 2) return false;   // more than one wave; a single database tile
         int units = max_units;
         // >= 4 database tiles per unit: a voucher segment (at least half a share) then always has rows to vouch for;
         // a database of a few tiles gets one unit per query tile unit
         const int64_t by_db = (int64_t)tiles * ntiles / 4;
         if (by_db < units) units = (int)(by_db > tiles ? by_db : tiles);
+        // A unit count that is a multiple of the tile count gives every tile the same number of whole units: no unit
+        // runs two segments (no query tile reload), every list vouches, thresholds are tighter.  Same-box A/B: C3
+        // (16 tiles) 144 units 25.7 ms vs 148 balanced 28.8 ms; C2 (4 pair tiles) 72 vs 74: equal.  So up to 6% of the
+        // units are left idle for it; beyond that (16 or 32 pair tiles over 74 pairs: 64 of 74) the balanced split wins.
+        {
+            const int even = units / tiles * tiles;
+            if (even >= tiles && (int64_t)units * 100 <= (int64_t)even * 106) units = even;
+        }
         int nv_min = 1 << 30, nseg_max = 0;
         for (int t = 0; t < tiles; t++) {
             int u_lo, nfw, nv, head;

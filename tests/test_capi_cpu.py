@@ -155,13 +155,14 @@ def test_tensor_path_planner():
 
     c2 = plan(1024, 1_000_000, 384, 10)               # BASELINE config 2
     assert c2["kp"] == 32 and c2["passes"] == 1 and c2["list"] == 1 and c2["pair"] == 1
-    assert c2["units"] == 74 and c2["tiles"] == 8 and c2["ns_min"] == 18 and c2["j"] == 1
+    assert c2["units"] == 72 and c2["tiles"] == 8 and c2["ns_min"] == 18 and c2["j"] == 1   # 18 whole pairs per pair tile (2 of 74 idle)
     big = plan(4096, 1_000_000, 384, 10)              # 16 pair tiles over 74 pairs: ONE pass, every pair gets 16/74 of it
     assert big["passes"] == 1 and big["chunk"] == 4096 and big["units"] == 74 and big["pair"] == 1 and big["j"] <= 8
     n8 = plan(8192, 125_000, 384, 10)                 # the weak-scaling shape at N = 8: 32 pair tiles over 74 pairs
     assert n8["passes"] == 1 and n8["units"] == 74 and n8["tiles"] == 64 and n8["list"] == 1 and n8["j"] <= 16
     c3 = plan(4096, 10_000_000, 768, 100)             # k' = 192 caps a pass (j <= 16); d = 768 rules out the Q-resident pair kernel
     assert c3["kp"] == 192 and c3["passes"] >= 2 and c3["pair"] == 0 and c3["j"] <= 16 and c3["list"] == 1
+    assert c3["units"] == 144 and c3["ns_min"] == 9   # 16 tiles per pass: 9 whole CTAs each beat 148 balanced (A/B r02l)
     one = plan(1, 1_000_000, 384, 10)                 # one tile: every SM streams its own split
     assert one["units"] == 148 and one["passes"] == 1 and one["nlists"] == 296 and one["j"] == 1
     assert plan(64, 1_000_000, 384, 200)["kp"] == 0   # k' > 256: the exact scan serves it
