@@ -13,5 +13,5 @@ for m in UTCHMMA UTCHMMA.2CTA UTMALDG UTMALDG.2D.2CTA LDTM UTCBAR UTCBAR.2CTA.MU
 done
 echo
 echo "per tensor_scan_kernel instantiation (KP, L2, LIST, QRES, PAIR):"
-awk '/Function : /{name=$3} /UTCHMMA/{u[name]++} /UTMALDG/{t[name]++} /LDTM/{l[name]++} /UTCBAR/{b[name]++} END{for(n in u) printf "  %s  UTCHMMA=%d UTMALDG=%d LDTM=%d UTCBAR=%d\n", n, u[n], t[n], l[n], b[n]}' "$TMP" | sort | c++filt | sed 's/CUtensorMap_st, CUtensorMap_st.*//'
+awk '/Function : /{name=$3} /UTCHMMA/{u[name]++} /UTMALDG/{t[name]++} /LDTM/{l[name]++} /UTCBAR/{b[name]++} END{for(n in u) printf "  UTCHMMA=%-3d UTMALDG=%-3d LDTM=%-3d UTCBAR=%-3d %s\n", u[n], t[n], l[n], b[n], n}' "$TMP" | c++filt | sed 's/(CUtensorMap_st, CUtensorMap_st.*//' | sort -k5
 rm -f "$TMP"
