@@ -602,6 +602,9 @@ def main():
 
     import rag_faiss_embedding_b200 as b2f
 
+    # before any torch CPU op: torchrun exports OMP_NUM_THREADS=1 and the intra-op pool keeps the size it was first used
+    # with, which would cripple rank 0's cpu_baseline leg (N = 2, first run: 149 q/s on 24 cores instead of ~1400)
+    torch.set_num_threads(host_threads())
     if args.warmup < 3:
         args.warmup = 3
     torch.cuda.set_device(local_rank)

@@ -315,6 +315,7 @@ struct TensorScanLists {  // LIST-mode scratch (device)
     int32_t* counts;      // [nq_pad * nlists]
     float* final_thr;     // [nq_pad * nlists]  the threshold each list was pruned against at the end of the stream
     int32_t* die_ctr;     // [4] ticket counters of the die-aware unit assignment (zero between launches), or null
+    uint8_t* big_flag;    // [nq_pad] big batches: queries the warp-per-query merge passes on to the block kernel
 };
 int plan_tensor_scan(int nq, int64_t n, int d, int kp, TensorScanPlan* plan);
 int plan_unit_work(int T, int U, int R, int64_t ntiles, int unit, int32_t* seg_info, int64_t* tiles, int64_t cap, int32_t* counts);

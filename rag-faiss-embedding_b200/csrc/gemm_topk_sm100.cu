@@ -1048,8 +1048,10 @@ __device__ __forceinline__ int block_count_le(const unsigned long long* comp, in
 __global__ void __launch_bounds__(MERGE_THREADS)
 merge_lists_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ counts, const float* __restrict__ final_thr,
                    int nl_stride, int tile_queries, int ntile_units, int total_units, int halves, int kp, int list_cap,
-                   int cap_entries, unsigned long long* __restrict__ total_entries, const RerankArgs ra) {
+                   int cap_entries, unsigned long long* __restrict__ total_entries, const uint8_t* __restrict__ only_flagged,
+                   const RerankArgs ra) {
     extern __shared__ __align__(16) unsigned long long comp[];  // [max(cap_entries, RANK_MAX)], later the re-rank scratch
+    if (only_flagged && !only_flagged[blockIdx.x]) return;   // big batches: the warp-per-query kernel answered this query
     __shared__ int s_off[2 * kNumSMs + 2];
     __shared__ int s_cnt[3];
     __shared__ int s_nsurv, s_nrest;
@@ -1264,6 +1266,149 @@ merge_lists_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ c
         if (tid == 0 && cert) atomicAdd(ra.fail_count + 4, 1);  // diagnostics: queries rescued by the extended pass
     }
     if (tid == 0 && ra.certify && !cert) rerank_record_failure(ra, q, false);
+}
+
+// ---- K3b + K4 for big batches: one WARP per query ---------------------------------------------------------
+// The block kernel above is a chain of dependent steps per query (~10 us) with five CTAs resident per SM: fine for a
+// thousand queries (one wave), but 8192 queries (the N = 8 weak-scaling shape) are eleven waves of it.  After the
+// end-of-stream pruning a query of a big batch has ~80 list entries, so one warp can do everything a CTA does: 64
+// queries in flight per SM instead of five.  Queries it cannot hold (more than WM_MAX entries, an overflowed list)
+// are flagged and answered by the block kernel launched right behind (it skips unflagged queries).
+constexpr int WM_WARPS = 8;      // queries per CTA
+constexpr int WM_MAX = 128;      // list entries per query
+constexpr int WM_LISTS = 64;     // lists per query
+
+// Exact re-rank of the first nc candidates (sk / si: coarse keys ascending) by one warp; writes the best k in faiss
+// conventions, returns whether the result is certified (warp-uniform).  ek / ei: nc floats / ints of scratch.
+__device__ __forceinline__ bool warp_rerank(const RerankArgs& a, int q, const float* sk, const int32_t* si, int nc, float bound,
+                                            bool all_rows, float* ek, int32_t* ei, int lane) {
+    const float* qv = a.q + (int64_t)q * a.d;
+    const bool l2 = a.metric == B2F_METRIC_L2;
+    const int sl = lane & 7;
+    for (int c0 = 0; c0 < nc; c0 += 4) {   // 8 lanes per candidate, 4 candidates per pass
+        const int c = c0 + (lane >> 3);
+        int32_t id = c < nc ? si[c] : -1;
+        if ((int64_t)id >= a.ntotal) id = -1;
+        const float key = exact_key_8lanes(a, qv, id, sl, l2);
+        if (sl == 0 && c < nc) {
+            const bool ok = id >= 0 && !(key != key);
+            ek[c] = ok ? key : FLT_MAX;
+            ei[c] = ok ? id : -1;
+        }
+    }
+    __syncwarp();
+    float tau = FLT_MAX;
+    for (int t = lane; t < nc; t += 32) {
+        const float mk = ek[t];
+        const int32_t mi = ei[t];
+        int rank = 0;
+        for (int j = 0; j < nc; j++) {
+            const float ok_ = ek[j];
+            const int32_t oi_ = ei[j];
+            rank += (cand_less(ok_, oi_, mk, mi) || (ok_ == mk && oi_ == mi && j < t)) ? 1 : 0;
+        }
+        if (rank < a.k) {
+            const int64_t o = (int64_t)q * a.k + rank;
+            a.D[o] = mi < 0 ? (l2 ? FLT_MAX : -FLT_MAX) : (l2 ? mk : -mk);
+            a.I[o] = mi < 0 ? -1 : (int64_t)mi + a.id_offset;
+        }
+        if (rank == a.k - 1) tau = mk;
+    }
+    for (int t = nc + lane; t < a.k; t += 32) {   // fewer candidates than k: pad
+        a.D[(int64_t)q * a.k + t] = l2 ? FLT_MAX : -FLT_MAX;
+        a.I[(int64_t)q * a.k + t] = -1;
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) tau = fminf(tau, __shfl_xor_sync(kFull, tau, d));   // exactly one lane holds the k-th key
+    __syncwarp();
+    return all_rows || rerank_certified(a, q, tau, bound);
+}
+
+__global__ void __launch_bounds__(WM_WARPS * 32)
+merge_lists_warp_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ counts, const float* __restrict__ final_thr,
+                        int nl_stride, int tile_queries, int ntile_units, int total_units, int halves, int kp, int list_cap,
+                        unsigned long long* __restrict__ total_entries, uint8_t* __restrict__ big_flag, int nq, const RerankArgs ra) {
+    __shared__ __align__(16) unsigned long long s_comp[WM_WARPS][WM_MAX];
+    __shared__ float s_sk[WM_WARPS][WM_MAX], s_ek[WM_WARPS][WM_MAX];
+    __shared__ int32_t s_si[WM_WARPS][WM_MAX], s_ei[WM_WARPS][WM_MAX];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = blockIdx.x * WM_WARPS + warp;
+    if (q >= nq) return;
+    unsigned long long* comp = s_comp[warp];
+    float* sk = s_sk[warp];
+    int32_t* si = s_si[warp];
+    int nlists;
+    {
+        int u_lo, nfw, nv, head;
+        tile_slots(q / tile_queries, ntile_units, total_units, u_lo, nfw, nv, head);
+        nlists = (nfw + head) * halves;   // <= WM_LISTS (host-checked)
+    }
+    // list lengths, final thresholds, offsets: lane l owns lists l and l + 32
+    int c0 = 0, c1 = 0;
+    float tc = 3.0e38f;
+    bool ovf = false;
+    if (lane < nlists) {
+        c0 = counts[(int64_t)q * nl_stride + lane];
+        tc = fminf(tc, final_thr[(int64_t)q * nl_stride + lane]);
+    }
+    if (lane + 32 < nlists) {
+        c1 = counts[(int64_t)q * nl_stride + lane + 32];
+        tc = fminf(tc, final_thr[(int64_t)q * nl_stride + lane + 32]);
+    }
+    ovf = c0 > list_cap || c1 > list_cap;
+    int i0 = c0, i1 = c1;   // inclusive scans
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int u0 = __shfl_up_sync(kFull, i0, d), u1 = __shfl_up_sync(kFull, i1, d);
+        if (lane >= d) { i0 += u0; i1 += u1; }
+    }
+    const int tot0 = __shfl_sync(kFull, i0, 31), M = tot0 + __shfl_sync(kFull, i1, 31);
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) tc = fminf(tc, __shfl_xor_sync(kFull, tc, d));
+    ovf = __any_sync(kFull, ovf);
+    if (lane == 0 && total_entries) atomicAdd(total_entries, (unsigned long long)(ovf ? 0 : M));
+    if (ovf || M > WM_MAX) {   // the block kernel answers this one
+        if (lane == 0) big_flag[q] = 1;
+        return;
+    }
+    if (lane == 0) big_flag[q] = 0;
+    // gather: every lane copies its own (short) lists
+    {
+        const uint2* l0 = cand + ((int64_t)q * nl_stride + lane) * list_cap;
+        const int o0 = i0 - c0;
+        for (int i = 0; i < c0; i++) {
+            const uint2 e = l0[i];
+            comp[o0 + i] = ((unsigned long long)enc_key(__uint_as_float(e.x)) << 32) | (unsigned long long)e.y;
+        }
+        const uint2* l1 = cand + ((int64_t)q * nl_stride + lane + 32) * list_cap;
+        const int o1 = tot0 + i1 - c1;
+        for (int i = 0; i < c1; i++) {
+            const uint2 e = l1[i];
+            comp[o1 + i] = ((unsigned long long)enc_key(__uint_as_float(e.x)) << 32) | (unsigned long long)e.y;
+        }
+    }
+    __syncwarp();
+    // full sort by rank counting (composites are distinct: row ids)
+    for (int t = lane; t < M; t += 32) {
+        const unsigned long long mine = comp[t];
+        int rank = 0;
+        for (int j = 0; j < M; j++) rank += comp[j] < mine ? 1 : 0;
+        sk[rank] = dec_key((uint32_t)(mine >> 32));
+        si[rank] = (int32_t)(uint32_t)(mine & 0xffffffffu);
+    }
+    __syncwarp();
+    // exact re-rank + certification: first stage, the k' best, every list entry (see merge_lists_kernel)
+    const int nc1 = M < kp ? M : kp;
+    const float bound1 = (M > kp) ? fminf(sk[kp - 1], tc) : tc;
+    bool cert = false;
+    if (ra.certify && ra.stage1 >= ra.k && ra.stage1 < nc1)
+        cert = warp_rerank(ra, q, sk, si, ra.stage1, fminf(sk[ra.stage1], tc), false, s_ek[warp], s_ei[warp], lane);
+    if (!cert) cert = warp_rerank(ra, q, sk, si, nc1, bound1, M < kp, s_ek[warp], s_ei[warp], lane);
+    if (!cert && ra.certify && M > kp) {
+        cert = warp_rerank(ra, q, sk, si, M, tc, false, s_ek[warp], s_ei[warp], lane);
+        if (lane == 0 && cert) atomicAdd(ra.fail_count + 4, 1);
+    }
+    if (lane == 0 && ra.certify && !cert) rerank_record_failure(ra, q, false);
 }
 
 // ---- host side --------------------------------------------------------------------------------------
@@ -1608,9 +1753,25 @@ int launch_merge_lists(const TensorScanLists& lists, int nq, const TensorScanPla
             configured[dev] = true;
         }
     }
+    // big batches: one warp per query first; what it cannot hold is flagged for the block kernel behind it
+    const uint8_t* only_flagged = nullptr;
+    static int warp_env = -1;
+    if (warp_env < 0) {
+        const char* e = getenv("B200FLAT_WARP_MERGE");   // diagnostics: 0 = off, n > 1 = batch size from which it is used
+        warp_env = e ? atoi(e) : 2048;
+    }
+    if (warp_env > 0 && nq >= warp_env && lists.big_flag && plan.nlists <= k2::WM_LISTS && plan.kp <= k2::WM_MAX / 2 && ra.D) {
+        k2::merge_lists_warp_kernel<<<(nq + k2::WM_WARPS - 1) / k2::WM_WARPS, k2::WM_WARPS * 32, 0, st>>>(
+            reinterpret_cast<const uint2*>(lists.cand), lists.counts, lists.final_thr, plan.nlists, plan.pair_mode ? 2 * k2::BM : k2::BM,
+            plan.tile_units, plan.units, k2::EPI_WARPS_LIST / 4, plan.kp, plan.list_cap, total_entries, lists.big_flag, nq, ra);
+        B2F_CUDA(cudaGetLastError());
+        only_flagged = lists.big_flag;
+        total_entries = nullptr;   // counted by the warp kernel (queries it passes on are counted by neither: diagnostics only)
+    }
     k2::merge_lists_kernel<<<nq, k2::MERGE_THREADS, smem, st>>>(reinterpret_cast<const uint2*>(lists.cand), lists.counts, lists.final_thr,
                                                                plan.nlists, plan.pair_mode ? 2 * k2::BM : k2::BM, plan.tile_units, plan.units,
-                                                               k2::EPI_WARPS_LIST / 4, plan.kp, plan.list_cap, cap_entries, total_entries, ra);
+                                                               k2::EPI_WARPS_LIST / 4, plan.kp, plan.list_cap, cap_entries, total_entries,
+                                                               only_flagged, ra);
     B2F_CUDA(cudaGetLastError());
     return B2F_OK;
 }

@@ -899,6 +899,7 @@ static int search_locked(b2f_index* ix, int64_t nq64, const float* q, int64_t k6
         if (plan.list_mode) {
             need += align_up(nq_pad * plan.nlists * 4, 256) * 3;                       // shared thresholds + counts + final thresholds
             need += align_up(nq_pad * plan.nlists * (size_t)plan.list_cap * 8, 256);   // candidate lists
+            need += align_up(nq_pad, 256);                                              // warp-merge pass-on flags
         } else {
             need += 2 * align_up(nq_pad * plan.nsplits * kp * 4, 256);  // partial lists
             need += 2 * align_up((size_t)chunk_nq * kp * 4, 256);       // merged coarse
@@ -970,6 +971,7 @@ static int search_locked(b2f_index* ix, int64_t nq64, const float* q, int64_t k6
             lists.counts = bump.take<int32_t>((size_t)nq_pad * plan.nlists);
             lists.final_thr = bump.take<float>((size_t)nq_pad * plan.nlists);
             lists.cand = bump.take<uint2>((size_t)nq_pad * plan.nlists * plan.list_cap);
+            lists.big_flag = bump.take<uint8_t>((size_t)nq_pad);
         } else {
             pk = bump.take<float>((size_t)nq_pad * plan.nsplits * kp);
             pi = bump.take<int32_t>((size_t)nq_pad * plan.nsplits * kp);

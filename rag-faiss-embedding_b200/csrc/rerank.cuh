@@ -93,6 +93,36 @@ __device__ __forceinline__ float exact_key_8lanes(const RerankArgs& a, const flo
     return l2 ? acc : -acc;
 }
 
+// The certification test.  tau: exact k-th best key among the re-ranked candidates (FLT_MAX when fewer than k are
+// valid); bound: a coarse key that every row OUTSIDE the candidates is known to reach or exceed.  True when the bf16 /
+// fp32 rounding bounds prove that no such row can beat tau.
+__device__ __forceinline__ bool rerank_certified(const RerankArgs& a, int q, float tau, float bound) {
+    const bool l2 = a.metric == B2F_METRIC_L2;
+    const float qn2 = a.qnorm[q];
+    const float qn = sqrtf(qn2);
+    const float eq = a.qerr[q];
+    // fp32 accumulation slack: gamma_n * sum|q_i x_i| <= n u |q||x| per inner product (n = d + 16 guards
+    // the tensor core's chunked accumulation order, u = 2^-24), doubled for non-IEEE accumulator rounding
+    const float gam = 4.f * (float)(a.d + 16) * 5.9604645e-8f;
+    if (l2) {
+        // c = |q~|^2 + |x~|^2 - 2<q~,x~>: the two norms are fp32 sums as well
+        const float nu = gam * (2.f * qn * a.max_row_norm + qn2 + a.max_row_norm * a.max_row_norm);
+        const float c = bound + qn2 - nu;
+        const float L = sqrtf(fmaxf(c, 0.f)) - eq - a.max_row_err;
+        return L > 0.f && L * L * (1.f - 4e-7f) > tau;
+    }
+    // keys are negated (centred inner product + mu.x): <q,x> = -key + qconst + rounding terms, so
+    // non-candidates have <q,x> <= -bound + qconst + slack.  The fp32 sums mu.x and q.mu carry their own
+    // rounding error.
+    const float cq = a.qconst ? a.qconst[q] : 0.f;
+    // mu.x and q.mu are accumulated in double, so they only carry the rounding of their fp32 results and
+    // of the fp32 additions they enter (a few ulp of |mu| (|x| + |q|))
+    const float xmax = a.max_row_norm + a.max_row_err + a.mu_norm;   // >= |x| of any row
+    const float nu = gam * qn * a.max_row_norm + 2.4e-7f * (a.mu_norm * (xmax + qn + eq + a.mu_norm) + qn * a.max_row_norm);
+    const float U = -bound + cq + nu + (qn + eq) * a.max_row_err + a.max_row_norm * eq;
+    return U < -tau;
+}
+
 // ck/ci: the query's candidates (shared or global memory); nc of them are re-ranked.
 // bound: a coarse key that every row OUTSIDE the nc candidates is known to reach or exceed.
 // all_rows: the candidates are every row of the index (nothing to certify against).
@@ -157,37 +187,7 @@ __device__ __forceinline__ bool rerank_block(const RerankArgs& a, int q, const f
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        bool certified;
-        if (all_rows) {
-            certified = true;  // every row of the index is already a candidate
-        } else {
-            const float tau = s_tau;  // exact k-th best key (FLT_MAX when fewer than k valid candidates)
-            const float qn2 = a.qnorm[q];
-            const float qn = sqrtf(qn2);
-            const float eq = a.qerr[q];
-            // fp32 accumulation slack: gamma_n * sum|q_i x_i| <= n u |q||x| per inner product (n = d + 16 guards
-            // the tensor core's chunked accumulation order, u = 2^-24), doubled for non-IEEE accumulator rounding
-            const float gam = 4.f * (float)(a.d + 16) * 5.9604645e-8f;
-            if (l2) {
-                // c = |q~|^2 + |x~|^2 - 2<q~,x~>: the two norms are fp32 sums as well
-                const float nu = gam * (2.f * qn * a.max_row_norm + qn2 + a.max_row_norm * a.max_row_norm);
-                const float c = bound + qn2 - nu;
-                const float L = sqrtf(fmaxf(c, 0.f)) - eq - a.max_row_err;
-                certified = L > 0.f && L * L * (1.f - 4e-7f) > tau;
-            } else {
-                // keys are negated (centred inner product + mu.x): <q,x> = -key + qconst + rounding terms, so
-                // non-candidates have <q,x> <= -bound + qconst + slack.  The fp32 sums mu.x and q.mu carry their own
-                // rounding error.
-                const float cq = a.qconst ? a.qconst[q] : 0.f;
-                // mu.x and q.mu are accumulated in double, so they only carry the rounding of their fp32 results and
-                // of the fp32 additions they enter (a few ulp of |mu| (|x| + |q|))
-                const float xmax = a.max_row_norm + a.max_row_err + a.mu_norm;   // >= |x| of any row
-                const float nu = gam * qn * a.max_row_norm +
-                                 2.4e-7f * (a.mu_norm * (xmax + qn + eq + a.mu_norm) + qn * a.max_row_norm);
-                const float U = -bound + cq + nu + (qn + eq) * a.max_row_err + a.max_row_norm * eq;
-                certified = U < -tau;
-            }
-        }
+        const bool certified = all_rows || rerank_certified(a, q, s_tau, bound);  // all_rows: every row of the index is already a candidate
         s_cert = certified ? 1 : 0;
     }
     __syncthreads();

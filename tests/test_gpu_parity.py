@@ -361,6 +361,33 @@ def test_centred_bf16_storage_certifies_embedding_like_data(m, metric, tmp_path)
     _check(D2, I2, D, I, metric, min_recall=tie_ok)
 
 
+@pytest.mark.parametrize("metric", [1, 0])
+def test_big_batch_warp_merge_and_first_stage(m, metric):
+    """Batches of >= 2048 queries take the warp-per-query list merge with the first-stage re-rank (best 16 candidates
+    first); queries it cannot hold are passed on to the block kernel.  Exact on benign data, and on data where the first
+    stage cannot certify (near-duplicate rows: dozens of rows within the bf16 band of the k-th neighbour)."""
+    n, d, nq, k = 60000, 128, 4096, 10
+    xb = orc.c_synth_rows(1234, 0, n, d, metric == 0)
+    xq = orc.c_synth_rows(5678, 0, nq, d, metric == 0)
+    ix = _make(m, xb, metric).set_search_params(algo=m.ALGO_TENSOR)
+    D, I = ix.search(xq, k)
+    _check(D, I, *orc.np_search_f64(xb, xq, k, metric), metric)
+    st = ix.stats()
+    assert st["last_algo"] == m.ALGO_TENSOR and st["fallback_queries"] == 0, st
+    # clusters of 40 near-duplicates around 600 centres: the neighbours of a query near a centre are separated by far less
+    # than the bf16 rounding band, so the first stage (and often the k' stage) fails and the later stages must answer
+    rng = np.random.default_rng(5)
+    centres = rng.standard_normal((600, d)).astype(np.float32)
+    xb2 = (np.repeat(centres, 40, axis=0) + rng.standard_normal((24000, d)).astype(np.float32) * 2e-3).astype(np.float32)
+    xq2 = (centres[rng.integers(0, 600, nq)] + rng.standard_normal((nq, d)).astype(np.float32) * 2e-3).astype(np.float32)
+    if metric == 0:
+        xb2 /= np.linalg.norm(xb2, axis=1, keepdims=True)
+        xq2 /= np.linalg.norm(xq2, axis=1, keepdims=True)
+    ix2 = _make(m, xb2, metric).set_search_params(algo=m.ALGO_TENSOR)
+    D2, I2 = ix2.search(xq2, k)
+    _check(D2, I2, *orc.np_search_f64(xb2, xq2, k, metric), metric, min_recall=0.999)
+
+
 def test_very_large_batch_is_cut_into_list_passes(m):
     """20000 queries are far more than one wave of query tiles: the planner cuts the batch into LIST-mode passes
     (not the multi-wave HEAP selection); results must be exact and independent of the cut."""
