@@ -1023,15 +1023,15 @@ static int search_locked(b2f_index* ix, int64_t nq64, const float* q, int64_t k6
             ra.fail_list = fail_list;
             ra.fail_count = counters;
             ra.q_base = c0;
-            {   // first-stage re-rank of big (throughput-bound) batches: k + max(6, k / 4) candidates, a multiple of 8
+            {   // First-stage re-rank (the best n candidates alone before the k' best): OFF.  Same-box A/B (r02n): no gain at
+                // 4096 / 8192 queries with k = 10 (the merge is not bound by the candidate row reads after all), and a loss
+                // at k = 100, k' = 192 (0.69 -> 0.93 ms per C3 search).  B200FLAT_STAGE1=<n> enables it for experiments.
                 static int s1_env = -2;
                 if (s1_env == -2) {
-                    const char* e = getenv("B200FLAT_STAGE1");   // diagnostics: -1 = off, 0 = default, n = forced
+                    const char* e = getenv("B200FLAT_STAGE1");
                     s1_env = e ? atoi(e) : 0;
                 }
-                int n0 = ((k + (k / 4 > 6 ? k / 4 : 6)) + 7) / 8 * 8;
-                if (n0 < 16) n0 = 16;
-                ra.stage1 = s1_env > 0 ? s1_env : ((s1_env == 0 && nq >= 2048 && n0 < kp) ? n0 : 0);
+                ra.stage1 = (s1_env >= k && s1_env < kp) ? s1_env : 0;
             }
             if (plan.list_mode) {
                 // K3b + K4 + finalize fused: per query, merge the lists, re-rank exactly, certify, write (D, I)

@@ -363,10 +363,10 @@ def test_centred_bf16_storage_certifies_embedding_like_data(m, metric, tmp_path)
 
 @pytest.mark.parametrize("metric", [1, 0])
 def test_big_batch_warp_merge_and_first_stage(m, metric):
-    """Batches of >= 2048 queries take the warp-per-query list merge with the first-stage re-rank (best 16 candidates
-    first); queries it cannot hold are passed on to the block kernel.  Exact on benign data, and on data where the first
-    stage cannot certify (near-duplicate rows: dozens of rows within the bf16 band of the k-th neighbour)."""
-    n, d, nq, k = 60000, 128, 4096, 10
+    """Batches of >= 8192 queries take the warp-per-query list merge; queries it cannot hold are passed on to the block
+    kernel.  Exact on benign data, and on data where the k' best cannot certify (near-duplicate rows: dozens of rows
+    within the bf16 band of the k-th neighbour), so that the extended stage and the exact scan must answer."""
+    n, d, nq, k = 60000, 128, 8192, 10
     xb = orc.c_synth_rows(1234, 0, n, d, metric == 0)
     xq = orc.c_synth_rows(5678, 0, nq, d, metric == 0)
     ix = _make(m, xb, metric).set_search_params(algo=m.ALGO_TENSOR)
@@ -385,7 +385,9 @@ def test_big_batch_warp_merge_and_first_stage(m, metric):
         xq2 /= np.linalg.norm(xq2, axis=1, keepdims=True)
     ix2 = _make(m, xb2, metric).set_search_params(algo=m.ALGO_TENSOR)
     D2, I2 = ix2.search(xq2, k)
-    _check(D2, I2, *orc.np_search_f64(xb2, xq2, k, metric), metric, min_recall=0.999)
+    # (normalised near-duplicates: most of the 40 inner products of a cluster are EQUAL in fp32, so which ids fill the
+    # k slots is a tie -- every position must still agree in id or in distance)
+    _check(D2, I2, *orc.np_search_f64(xb2, xq2, k, metric), metric, min_recall=0.999 if metric == 1 else 0.0)
 
 
 def test_very_large_batch_is_cut_into_list_passes(m):
