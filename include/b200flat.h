@@ -214,11 +214,12 @@ B2F_API int b2f_index_add_synth(b2f_index* idx, uint64_t seed, int64_t row0, int
  * per list, out[10] = 128-query tiles per pass, out[11] = database tiles per round of the interleaved sweep.   */
 B2F_API int b2f_plan_describe(int64_t nq, int64_t n, int32_t d, int64_t k, int32_t slack, int32_t out[12]);
 /* The work of unit `unit` (of `units`) under the balanced split of `tile_units` query tile units x `db_tiles` database
- * tiles, as the kernel computes it: returns the number of segments (1 or 2); seg_info[5 s ..] = query tile unit, list
- * slot, voucher slots of that tile, in-tile range [p0, p1) in 1/units; counts[s] = database tiles of segment s, the
+ * tiles with k' = kprime, as the kernel computes it: returns the number of segments (1 or 2), in the order the unit runs
+ * them; seg_info[7 s ..] = query tile unit, list slot, voucher slots of that tile, in-tile range [p0, p1) in 1/units,
+ * rows each list of the piece vouches for, voucher lists a thread consults; counts[s] = database tiles of segment s, the
  * first `cap` of which are written to tiles[s * cap ..] (tiles may be NULL).  Host logic only (tests).          */
-B2F_API int b2f_plan_unit_work(int32_t tile_units, int32_t units, int32_t round_tiles, int64_t db_tiles, int32_t unit,
-                       int32_t seg_info[10], int64_t* tiles, int64_t cap, int32_t counts[2]);
+B2F_API int b2f_plan_unit_work(int32_t tile_units, int32_t units, int32_t round_tiles, int64_t db_tiles, int32_t kprime,
+                       int32_t unit, int32_t seg_info[14], int64_t* tiles, int64_t cap, int32_t counts[2]);
 B2F_API int b2f_index_stats(const b2f_index* idx, b2f_stats* out);
 B2F_API const char* b2f_last_error(void);
 B2F_API int b2f_version(void);

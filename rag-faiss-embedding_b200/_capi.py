@@ -101,7 +101,7 @@ PROTOTYPES = {
     "b2f_synth_rows": (ctypes.c_int, [_u64, _i64, _i64, _i32, _i32, _vp, _i32, _vp]),
     "b2f_index_add_synth": (ctypes.c_int, [_vp, _u64, _i64, _i64, _i32]),
     "b2f_plan_describe": (ctypes.c_int, [_i64, _i64, _i32, _i64, _i32, ctypes.POINTER(_i32)]),
-    "b2f_plan_unit_work": (ctypes.c_int, [_i32, _i32, _i32, _i64, _i32, ctypes.POINTER(_i32), ctypes.POINTER(_i64), _i64,
+    "b2f_plan_unit_work": (ctypes.c_int, [_i32, _i32, _i32, _i64, _i32, _i32, ctypes.POINTER(_i32), ctypes.POINTER(_i64), _i64,
                                           ctypes.POINTER(_i32)]),
     "b2f_index_stats": (ctypes.c_int, [_vp, ctypes.POINTER(Stats)]),
     "b2f_last_error": (ctypes.c_char_p, []),

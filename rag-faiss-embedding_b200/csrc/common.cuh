@@ -318,7 +318,7 @@ struct TensorScanLists {  // LIST-mode scratch (device)
     uint8_t* big_flag;    // [nq_pad] big batches: queries the warp-per-query merge passes on to the block kernel
 };
 int plan_tensor_scan(int nq, int64_t n, int d, int kp, TensorScanPlan* plan);
-int plan_unit_work(int T, int U, int R, int64_t ntiles, int unit, int32_t* seg_info, int64_t* tiles, int64_t cap, int32_t* counts);
+int plan_unit_work(int T, int U, int R, int64_t ntiles, int kp, int unit, int32_t* seg_info, int64_t* tiles, int64_t cap, int32_t* counts);
 int launch_tensor_scan(const __nv_bfloat16* scan, int64_t dpad, const float* norms, int64_t n, int metric,
                        const __nv_bfloat16* qb, int nq, int nq_pad, const TensorScanPlan& plan, float* pk,
                        int32_t* pi, const TensorScanLists& lists, cudaStream_t st);

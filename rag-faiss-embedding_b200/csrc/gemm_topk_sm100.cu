@@ -265,49 +265,88 @@ struct ListArgs {
 // segments therefore move through the database front to back TOGETHER, a round at a time: a block that several
 // query tiles need is fetched from HBM once and found in L2 by the others (the point of the former strided walk).
 //
-// Lists / shared thresholds: a query tile's segments are its list SLOTS -- the segments that start inside the tile
-// ("first wave": they begin at kernel start) in position order, then the head segment (run by the unit that first
-// finishes the previous tile's tail).  Only first-wave segments of (nearly) full length VOUCH (publish their j-th best:
-// a short segment's j-th best of few rows would loosen the shared bound for everyone who consults it); they are slots
-// [0, nv).  Every segment prunes against the max of g vouchers' values (voucher_rule below).
+// Order of a unit's two segments: the LONGER piece first.  A piece that runs first starts at kernel start ("first
+// wave"); the shorter piece follows when the first is done.
+//
+// Lists / shared thresholds: a query tile's pieces are its list SLOTS -- first-wave pieces in position order (whole
+// units, plus the head / tail piece when it is the longer part of its unit: at least half a share), then the second-
+// wave pieces.  The first-wave pieces VOUCH: every one of their lists publishes its j-th best key, j proportional to
+// the piece's length (a j-th best of few rows is loose, so a shorter piece vouches for fewer rows), scaled so that the
+// tile's voucher lists together vouch for >= k' rows.  Every list of the tile, voucher or not, prunes against the
+// maximum of the consulted values: with pieces of unequal length all voucher lists are consulted, with whole units
+// only (equal j) any g = ceil(k' / j) of them.  The vouchers cover all but the shorter halves of the boundary units
+// (~90 % of the rows at 2.3 units per tile), so the shared bound sits close to the k'-th best of everything seen.
 struct Seg {
     int qtile;         // query tile unit
     int slot;          // list slot within the tile
     int nv;            // voucher slots of the tile: [0, nv)
     uint32_t p0, p1;   // in-tile range in units of 1/U tile
+    int j;             // rows each of this piece's lists vouches for (vouchers; 1 otherwise)
+    int g;             // voucher lists a thread of this tile consults
 };
-__host__ __device__ __forceinline__ void tile_slots(int t, int T, int U, int& u_lo, int& nfw, int& nv, int& head) {
-    u_lo = (int)(((int64_t)t * U + T - 1) / T);                           // first unit that starts inside tile t
-    const int u_hi = (int)((((int64_t)t + 1) * U + T - 1) / T) - 1;       // last one
-    nfw = u_hi - u_lo + 1;
-    const int tail_len = (int)(((int64_t)t + 1) * U - (int64_t)u_hi * T);  // (0, T]: what the last one covers of tile t
-    nv = nfw - (4 * tail_len < 3 * T ? 1 : 0);   // the tail vouches only when it is at least 3/4 of a full share
-    if (nv < 1) nv = 1;
-    head = ((int64_t)u_lo * T > (int64_t)t * U) ? 1 : 0;                  // unit u_lo - 1 spills into this tile
+struct TileInfo {
+    int u_lo, u_hi;               // units that start inside the tile
+    int head_len, tail_len;       // head piece (unit u_lo - 1 spilling in) / what a crossing unit u_hi covers; 0 = none
+    bool head_first, tail_first;  // the piece is the longer part of its unit, i.e. first wave
+    int nfull, nfw, nsw;          // whole units; first-wave pieces = voucher slots [0, nfw); second-wave pieces behind them
+    int lv;                       // total voucher length in units of 1/U tile
+    int jfull;                    // rows a list of a whole unit vouches for
+    int g;                        // voucher lists a thread consults
+};
+__host__ __device__ __forceinline__ TileInfo tile_info(int t, int T, int U, int kp, int halves) {
+    TileInfo ti;
+    ti.u_lo = (int)(((int64_t)t * U + T - 1) / T);
+    ti.u_hi = (int)((((int64_t)t + 1) * U + T - 1) / T) - 1;
+    ti.head_len = (int)((int64_t)ti.u_lo * T - (int64_t)t * U);                    // [0, T)
+    const int last_len = (int)(((int64_t)t + 1) * U - (int64_t)ti.u_hi * T);       // (0, T]
+    ti.tail_len = last_len < T ? last_len : 0;
+    ti.head_first = ti.head_len > 0 && 2 * ti.head_len > T;
+    ti.tail_first = ti.tail_len > 0 && 2 * ti.tail_len >= T;
+    ti.nfull = ti.u_hi - ti.u_lo + 1 - (ti.tail_len > 0 ? 1 : 0);
+    ti.nfw = ti.nfull + (ti.head_first ? 1 : 0) + (ti.tail_first ? 1 : 0);
+    ti.nsw = ((ti.head_len > 0 && !ti.head_first) ? 1 : 0) + ((ti.tail_len > 0 && !ti.tail_first) ? 1 : 0);
+    ti.lv = ti.nfull * T + (ti.head_first ? ti.head_len : 0) + (ti.tail_first ? ti.tail_len : 0);
+    if (kp > 0) {
+        ti.jfull = (int)(((int64_t)kp * T + (int64_t)halves * ti.lv - 1) / ((int64_t)halves * ti.lv));
+        const bool uniform = !ti.head_first && !ti.tail_first;   // whole units only: every voucher list vouches jfull rows
+        const int nvs = ti.nfw * halves;
+        ti.g = uniform ? (kp + ti.jfull - 1) / ti.jfull : nvs;
+        if (ti.g > nvs) ti.g = nvs;
+    } else {
+        ti.jfull = 1;
+        ti.g = 1;
+    }
+    return ti;
 }
-// How a thread turns the vouchers' published values into its threshold.  nvs voucher lists (voucher segments x column
-// halves) each publish their j-th best key, j = ceil(k' / nvs); a thread reads g = ceil(k' / j) of them (its own first)
-// and takes the MAXIMUM: g lists vouch for j rows each at or below it, g * j >= k', so it is an upper bound of the k'-th
-// best.  (Reading two spare values and taking the third largest -- which would let short tails vouch too -- cut the
-// survivors by a third and still made the kernel 4-13% SLOWER, same-box A/B r02j: the refresh sits on the epilogue's
-// critical path ~24 times per stream and every extra instruction in it counts.  Round 1 saw the same with its "extra".)
-__host__ __device__ __forceinline__ void voucher_rule(int kp, int nvs, int& j, int& g) {
-    j = (kp + nvs - 1) / nvs;
-    g = (kp + j - 1) / j;
+// rows a list of a voucher piece of length len (in 1/U tile) vouches for
+__host__ __device__ __forceinline__ int piece_j(const TileInfo& ti, int len, int T) {
+    return (int)(((int64_t)ti.jfull * len + T - 1) / T);
 }
-__host__ __device__ __forceinline__ int unit_segments(int u, int T, int U, Seg (&seg)[2]) {
+// The one or two segments of unit u, in the order it runs them; returns their number.
+__host__ __device__ __forceinline__ int unit_segments(int u, int T, int U, int kp, int halves, Seg (&seg)[2]) {
     const int64_t S0 = (int64_t)u * T, S1 = S0 + T;
     const int a = (int)(S0 / U), b = (int)(S1 / U);
     const int fa = (int)(S0 - (int64_t)a * U), fb = (int)(S1 - (int64_t)b * U);
-    int u_lo, nfw, nv, head;
-    tile_slots(a, T, U, u_lo, nfw, nv, head);
-    seg[0].qtile = a; seg[0].slot = u - u_lo; seg[0].nv = nv; seg[0].p0 = (uint32_t)fa; seg[0].p1 = (uint32_t)(b > a ? U : fb);
-    if (b > a && fb > 0) {   // the interval spills into the head of the next tile
-        tile_slots(b, T, U, u_lo, nfw, nv, head);
-        seg[1].qtile = b; seg[1].slot = nfw; seg[1].nv = nv; seg[1].p0 = 0u; seg[1].p1 = (uint32_t)fb;
-        return 2;
+    const TileInfo ta = tile_info(a, T, U, kp, halves);
+    if (b == a || fb == 0) {   // a whole unit inside tile a
+        seg[0].qtile = a; seg[0].slot = (ta.head_first ? 1 : 0) + (u - ta.u_lo); seg[0].nv = ta.nfw;
+        seg[0].p0 = (uint32_t)fa; seg[0].p1 = (uint32_t)(b > a ? U : fb);
+        seg[0].j = ta.jfull; seg[0].g = ta.g;
+        return 1;
     }
-    return 1;
+    // the unit crosses into tile b = a + 1: a tail piece of tile a, a head piece of tile b
+    const TileInfo tb = tile_info(b, T, U, kp, halves);
+    Seg tail, head;
+    tail.qtile = a; tail.nv = ta.nfw; tail.p0 = (uint32_t)fa; tail.p1 = (uint32_t)U; tail.g = ta.g;
+    tail.slot = ta.tail_first ? ta.nfw - 1 : ta.nfw + ((ta.head_len > 0 && !ta.head_first) ? 1 : 0);
+    tail.j = ta.tail_first ? piece_j(ta, U - fa, T) : 1;
+    head.qtile = b; head.nv = tb.nfw; head.p0 = 0u; head.p1 = (uint32_t)fb; head.g = tb.g;
+    head.slot = tb.head_first ? 0 : tb.nfw;
+    head.j = tb.head_first ? piece_j(tb, fb, T) : 1;
+    const bool tail_runs_first = 2 * (U - fa) >= T;
+    seg[0] = tail_runs_first ? tail : head;
+    seg[1] = tail_runs_first ? head : tail;
+    return 2;
 }
 // The database tiles of one segment, in sweep order.  Contiguous form (HEAP mode): tiles [t0, t1).
 // Every role of the kernel steps one of these per tile and the epilogue is the kernel's critical path, so the state
@@ -499,10 +538,11 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     const int units_per_split = nq_tiles;   // HEAP mode only (never PAIR)
     const int split = LIST ? 0 : unit / units_per_split;
     if constexpr (LIST) {
-        nseg = unit_segments(unit, la.bal_T, la.bal_U, seg);
+        nseg = unit_segments(unit, la.bal_T, la.bal_U, la.kp, HALVES, seg);
         if (nseg == 1) seg[1] = seg[0];
     } else {
         seg[0].qtile = unit % units_per_split; seg[0].slot = split; seg[0].nv = 0; seg[0].p0 = 0u; seg[0].p1 = 0u;
+        seg[0].j = 1; seg[0].g = 1;
         heap_t0 = ntiles * split / nsplits;
         heap_t1 = ntiles * (split + 1) / nsplits;
     }
@@ -515,6 +555,8 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         r.nv = s_ == 0 ? seg[0].nv : seg[1].nv;
         r.p0 = s_ == 0 ? seg[0].p0 : seg[1].p0;
         r.p1 = s_ == 0 ? seg[0].p1 : seg[1].p1;
+        r.j = s_ == 0 ? seg[0].j : seg[1].j;
+        r.g = s_ == 0 ? seg[0].g : seg[1].g;
         return r;
     };
     auto seg_iter = [&](int s_) {
@@ -779,8 +821,8 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             const int vsplit = sg.slot * HALVES + half;
             const int nvs = sg.nv * HALVES;          // voucher virtual splits of this query tile
             const bool voucher = sg.slot < sg.nv;
-            int jv, gv;   // rows each voucher vouches for; vouchers consulted (gv * jv >= k')
-            voucher_rule(la.kp, nvs, jv, gv);
+            const int jv = sg.j;   // rows this list vouches for (vouchers)
+            const int gv = sg.g;   // voucher lists consulted: together they vouch for >= k' rows
             const int vstart = voucher ? vsplit : vsplit % nvs;   // own value first; the others spread over the vouchers
             float best[JSLOTS];  // ascending; the first JSLOTS - j slots are pinned at -inf, so best[JSLOTS-1] = j-th best
 #pragma unroll
@@ -1067,11 +1109,10 @@ merge_lists_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ c
     int32_t* ei = reinterpret_cast<int32_t*>(ek + RANK_MAX);       // [RANK_MAX]
     const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = q / tile_queries;
-    int nsplits;   // lists of this query = (segments of its tile: first wave + head, see Seg) x column halves
+    int nsplits;   // lists of this query = (pieces of its tile: first wave + second wave, see Seg) x column halves
     {
-        int u_lo, nfw, nv, head;
-        tile_slots(tile, ntile_units, total_units, u_lo, nfw, nv, head);
-        nsplits = (nfw + head) * halves;
+        const TileInfo ti = tile_info(tile, ntile_units, total_units, 0, halves);
+        nsplits = (ti.nfw + ti.nsw) * halves;
     }
     // list lengths and final thresholds: one parallel sweep (up to 296 lists), then a warp-level prefix sum
     if (tid == 0) {
@@ -1340,9 +1381,8 @@ merge_lists_warp_kernel(const uint2* __restrict__ cand, const int32_t* __restric
     int32_t* si = s_si[warp];
     int nlists;
     {
-        int u_lo, nfw, nv, head;
-        tile_slots(q / tile_queries, ntile_units, total_units, u_lo, nfw, nv, head);
-        nlists = (nfw + head) * halves;   // <= WM_LISTS (host-checked)
+        const TileInfo ti = tile_info(q / tile_queries, ntile_units, total_units, 0, halves);
+        nlists = (ti.nfw + ti.nsw) * halves;   // <= WM_LISTS (host-checked)
     }
     // list lengths, final thresholds, offsets: lane l owns lists l and l + 32
     int c0 = 0, c1 = 0;
@@ -1462,7 +1502,7 @@ static const SegCounts& segment_counts(const TensorScanPlan& plan, int64_t ntile
         for (int i = 0; i < 2 * kNumSMs; i++) sc.n[i] = 0;
         for (int u = 0; u < plan.units && u < kNumSMs; u++) {
             Seg seg[2];
-            const int nseg = unit_segments(u, plan.tile_units, plan.units, seg);
+            const int nseg = unit_segments(u, plan.tile_units, plan.units, plan.kp, EPI_WARPS_LIST / 4, seg);
             for (int sg = 0; sg < nseg; sg++) {
                 SegIter it;
                 it.init(seg[sg].p0, seg[sg].p1, plan.units, plan.round_tiles, ntiles);
@@ -1549,16 +1589,15 @@ int plan_tensor_scan(int nq, int64_t n, int d, int kp, TensorScanPlan* plan) {
             const int even = units / tiles * tiles;
             if (even >= tiles && (int64_t)units * 100 <= (int64_t)even * 106) units = even;
         }
-        int nv_min = 1 << 30, nseg_max = 0;
+        int j_max = 0, nseg_max = 0;
         for (int t = 0; t < tiles; t++) {
-            int u_lo, nfw, nv, head;
-            k2::tile_slots(t, tiles, units, u_lo, nfw, nv, head);
-            if (nv < nv_min) nv_min = nv;
-            if (nfw + head > nseg_max) nseg_max = nfw + head;
+            const k2::TileInfo ti = k2::tile_info(t, tiles, units, kp, halves);
+            if (ti.jfull > j_max) j_max = ti.jfull;
+            if (ti.nfw + ti.nsw > nseg_max) nseg_max = ti.nfw + ti.nsw;
         }
-        if ((kp + halves * nv_min - 1) / (halves * nv_min) > k2::JSLOTS) return false;   // j <= JSLOTS with every voucher consulted
+        if (j_max > k2::JSLOTS) return false;   // rows a whole unit's list vouches for
         *units_out = units;
-        *nv_min_out = nv_min;
+        *nv_min_out = j_max;
         *nseg_max_out = nseg_max;
         return true;
     };
@@ -1594,10 +1633,9 @@ int plan_tensor_scan(int nq, int64_t n, int d, int kp, TensorScanPlan* plan) {
         return B2F_OK;
     }
     plan->nlists = nseg_max * halves;           // lists allocated per query (stride)
-    int j, g;
-    k2::voucher_rule(kp, nv_min * halves, j, g);   // of the tile with the fewest vouchers (the largest j)
+    const int j = nv_min;   // (try_list returns the largest j of any tile here)
     plan->list_j = j;
-    plan->list_g = g;
+    plan->list_g = (kp + j - 1) / j;
     // database tiles per round of the interleaved sweep: about two per full-length segment
     {
         int r = 2 * ((units + plan->tile_units - 1) / plan->tile_units);
@@ -1621,16 +1659,18 @@ int plan_tensor_scan(int nq, int64_t n, int d, int kp, TensorScanPlan* plan) {
 }
 
 // diagnostics / CPU tests: the work of one unit under the balanced split, computed by the very functions the kernel runs
-int plan_unit_work(int T, int U, int R, int64_t ntiles, int unit, int32_t* seg_info, int64_t* tiles, int64_t cap, int32_t* counts) {
-    if (T < 1 || U < T || R < 1 || ntiles < 0 || unit < 0 || unit >= U || !seg_info || !counts) return -1;
+int plan_unit_work(int T, int U, int R, int64_t ntiles, int kp, int unit, int32_t* seg_info, int64_t* tiles, int64_t cap, int32_t* counts) {
+    if (T < 1 || U < T || R < 1 || ntiles < 0 || kp < 1 || unit < 0 || unit >= U || !seg_info || !counts) return -1;
     k2::Seg seg[2];
-    const int nseg = k2::unit_segments(unit, T, U, seg);
+    const int nseg = k2::unit_segments(unit, T, U, kp, k2::EPI_WARPS_LIST / 4, seg);
     for (int s = 0; s < nseg; s++) {
-        seg_info[5 * s + 0] = seg[s].qtile;
-        seg_info[5 * s + 1] = seg[s].slot;
-        seg_info[5 * s + 2] = seg[s].nv;
-        seg_info[5 * s + 3] = (int32_t)seg[s].p0;
-        seg_info[5 * s + 4] = (int32_t)seg[s].p1;
+        seg_info[7 * s + 0] = seg[s].qtile;
+        seg_info[7 * s + 1] = seg[s].slot;
+        seg_info[7 * s + 2] = seg[s].nv;
+        seg_info[7 * s + 3] = (int32_t)seg[s].p0;
+        seg_info[7 * s + 4] = (int32_t)seg[s].p1;
+        seg_info[7 * s + 5] = seg[s].j;
+        seg_info[7 * s + 6] = seg[s].g;
         k2::SegIter it;
         it.init(seg[s].p0, seg[s].p1, U, R, ntiles);
         int32_t c = 0;

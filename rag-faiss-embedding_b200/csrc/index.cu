@@ -596,9 +596,9 @@ int b2f_plan_describe(int64_t nq, int64_t n, int32_t d, int64_t k, int32_t slack
     return B2F_OK;
 }
 
-int b2f_plan_unit_work(int32_t tile_units, int32_t units, int32_t round_tiles, int64_t db_tiles, int32_t unit, int32_t seg_info[10],
-                       int64_t* tiles, int64_t cap, int32_t counts[2]) {
-    const int rc = plan_unit_work(tile_units, units, round_tiles, db_tiles, unit, seg_info, tiles, cap, counts);
+int b2f_plan_unit_work(int32_t tile_units, int32_t units, int32_t round_tiles, int64_t db_tiles, int32_t kprime, int32_t unit,
+                       int32_t seg_info[14], int64_t* tiles, int64_t cap, int32_t counts[2]) {
+    const int rc = plan_unit_work(tile_units, units, round_tiles, db_tiles, kprime, unit, seg_info, tiles, cap, counts);
     if (rc < 0) set_error("plan_unit_work: bad arguments");
     return rc < 0 ? B2F_EINVAL : rc;
 }

@@ -191,12 +191,12 @@ def test_balanced_work_split_is_an_exact_partition():
 
     lib = _capi.load()
 
-    def unit_work(T, U, R, ntiles, u, cap=60000):
-        seg, cnt, tiles = (ctypes.c_int32 * 10)(), (ctypes.c_int32 * 2)(), (ctypes.c_int64 * (2 * cap))()
-        n = lib.b2f_plan_unit_work(T, U, R, ntiles, u, seg, tiles, cap, cnt)
+    def unit_work(T, U, R, ntiles, u, cap=60000, kp=32):
+        seg, cnt, tiles = (ctypes.c_int32 * 14)(), (ctypes.c_int32 * 2)(), (ctypes.c_int64 * (2 * cap))()
+        n = lib.b2f_plan_unit_work(T, U, R, ntiles, kp, u, seg, tiles, cap, cnt)
         assert n in (1, 2), (T, U, u, n)
-        return [dict(qtile=seg[5 * s], slot=seg[5 * s + 1], nv=seg[5 * s + 2], p0=seg[5 * s + 3], p1=seg[5 * s + 4],
-                     tiles=list(tiles[s * cap:s * cap + cnt[s]])) for s in range(n)]
+        return [dict(qtile=seg[7 * s], slot=seg[7 * s + 1], nv=seg[7 * s + 2], p0=seg[7 * s + 3], p1=seg[7 * s + 4],
+                     j=seg[7 * s + 5], g=seg[7 * s + 6], tiles=list(tiles[s * cap:s * cap + cnt[s]])) for s in range(n)]
 
     cases = [(4, 74, 38, 3907), (32, 74, 6, 489), (16, 74, 10, 48829), (1, 148, 296, 3907), (1, 74, 148, 3907), (74, 74, 2, 1000),
              (73, 74, 4, 977), (37, 74, 4, 500), (5, 148, 60, 79), (64, 148, 6, 489), (3, 7, 6, 100), (7, 7, 2, 30),
@@ -213,14 +213,28 @@ def test_balanced_work_split_is_an_exact_partition():
                 per_tile[s["qtile"]] += s["tiles"]
                 assert s["slot"] not in slots[s["qtile"]]
                 slots[s["qtile"]][s["slot"]] = s
-                if i == 1:                                            # the head of the next tile: never a voucher
-                    assert s["p0"] == 0 and s["slot"] >= s["nv"] and s["qtile"] == segs[0]["qtile"] + 1
+                if i == 1:   # the piece a unit runs second is the shorter one, sits in the neighbouring tile, never vouches
+                    assert s["slot"] >= s["nv"] and abs(s["qtile"] - segs[0]["qtile"]) == 1
+                    assert s["p1"] - s["p0"] <= segs[0]["p1"] - segs[0]["p0"]
+                    assert segs[0]["slot"] < segs[0]["nv"]           # ... and the longer one, run first, does
         for t in range(T):
             assert sorted(per_tile[t]) == list(range(ntiles)), (T, U, R, ntiles, t)
             ns = len(slots[t])
             assert sorted(slots[t]) == list(range(ns))
             nv = slots[t][0]["nv"]
             assert 1 <= nv <= ns and all(s["nv"] == nv for s in slots[t].values())
+            # the tile's voucher lists (2 column halves per piece) together vouch for >= k' rows; j <= 16 register slots;
+            # with equal j any g of them do, with unequal pieces all are consulted
+            vj = [slots[t][sl]["j"] for sl in range(nv)]
+            g = slots[t][0]["g"]
+            assert all(j >= 1 for j in vj) and all(s["g"] == g for s in slots[t].values())
+            if (T, U) not in ((73, 74), (64, 148)):   # (shapes the planner rejects: a tile with less than one whole unit vouching)
+                assert all(j <= 16 for j in vj), (T, U, t, vj)
+            assert 2 * sum(vj) >= 32 and 1 <= g <= 2 * nv
+            if len(set(vj)) == 1:
+                assert g * vj[0] >= 32
+            else:
+                assert g == 2 * nv
         ideal = T * ntiles / U
         assert max(totals) - min(totals) <= 4 and max(totals) <= ideal + 3, (T, U, R, ntiles, min(totals), max(totals), ideal)
     # plans the library makes are consistent with the split: the lists allocated per query cover every tile's segments
@@ -232,9 +246,8 @@ def test_balanced_work_split_is_an_exact_partition():
         ntiles = (n + 255) // 256
         most = 0
         for u in range(units):
-            for s in unit_work(T, units, rnd, ntiles, u, cap=1):
+            for s in unit_work(T, units, rnd, ntiles, u, cap=1, kp=kp):
                 most = max(most, s["slot"] + 1)
-                assert kp <= 16 * 2 * s["nv"]
         assert most * 2 == nlists, (nq, n, most, nlists)
 
 
