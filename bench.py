@@ -268,6 +268,23 @@ def cpu_baseline(wl, nq_total, budget_s=20.0):
     return {"value": round(qps, 2), "unit": "queries/sec", "cores": int(cores), "kind": "port", "sample": sample}
 
 
+def cpu_baseline_isolated(workload, wl, nq_total, budget_s):
+    """cpu_baseline() in a fresh interpreter without the launcher's thread caps: inside the GPU arm's own process (CUDA
+    context, NCCL threads, an intra-op pool first used under torchrun's OMP_NUM_THREADS=1) the same sgemm ran at 3-10 % of
+    its speed (N = 2: 149 q/s, N = 8: 44 q/s, against ~1500 q/s for `--impl reference` on the same hosts)."""
+    env = {k_: v for k_, v in os.environ.items()
+           if k_ not in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS", "RANK", "LOCAL_RANK", "WORLD_SIZE")}
+    cmd = [sys.executable, os.path.abspath(__file__), "--cpu-baseline-only", "--workload", workload, "--nq", str(nq_total),
+           "--cpu-budget", str(budget_s)]
+    try:
+        out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+        line = [ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1]
+        return json.loads(line)
+    except Exception as exc:   # never lose the GPU line to the CPU leg
+        return {"value": None, "unit": "queries/sec", "cores": host_threads(), "kind": "port",
+                "sample": "cpu_baseline subprocess failed: %s" % exc}
+
+
 def run_reference(args, wl, rank, world):
     """--impl reference: the CPU restatement of the reference's IndexFlat path on the host cores.  The thread count is
     set HERE (all threads this process may use), never inherited from the launcher; the reference's own configured
@@ -584,7 +601,12 @@ def main():
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--nq", type=int, default=0, help="diagnostics: another batch size on the workload's rows")
+    ap.add_argument("--cpu-baseline-only", action="store_true", help="internal: print the cpu_baseline record for --nq queries and exit")
     args = ap.parse_args()
+    if args.cpu_baseline_only:
+        w0 = WORKLOADS[args.workload]
+        print(json.dumps(cpu_baseline(w0, args.nq if args.nq > 0 else w0["nq"], args.cpu_budget)), flush=True)
+        return
     wl = dict(WORKLOADS[args.workload])
     if args.nq > 0:
         wl["nq"] = args.nq
@@ -682,7 +704,7 @@ def main():
         if "parity_check" in rec:
             line["parity_check"] = rec["parity_check"]
         if not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(wl, nq, args.cpu_budget if world == 1 else min(args.cpu_budget, 10.0))
+            line["cpu_baseline"] = cpu_baseline_isolated(args.workload, wl, nq, args.cpu_budget if world == 1 else min(args.cpu_budget, 10.0))
         if series:
             line["series"] = series
         if c4 is not None:
