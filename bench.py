@@ -711,6 +711,17 @@ def main():
             line["c4"] = c4
         print(json.dumps(line), flush=True)
     if world > 1:
+        # The other ranks must SLEEP while rank 0 times the CPU leg: an NCCL barrier spins on the host, and with the
+        # container's CPU quota N - 1 spinning ranks starve the sgemm (N = 4: 45 q/s instead of ~1400).  A blocking
+        # wait on the rendezvous store does not spin.
+        try:
+            store = dist.distributed_c10d._get_default_store()
+            if rank == 0:
+                store.set("b200flat_cpu_leg_done", "1")
+            else:
+                store.wait(["b200flat_cpu_leg_done"])
+        except Exception:
+            pass
         dist.barrier()
         dist.destroy_process_group()
 
