@@ -332,9 +332,13 @@ void harvest_flag(b2f_index* ix) {
     ix->harvested_seq = s;
     ix->st.last_list_entries = (int64_t)(((uint64_t)(uint32_t)c3 << 32) | (uint32_t)c2);
     // The slack that certification needs grows with the neighbour density at rank k (i.e. with the database
-    // size and the data distribution): when more than ~2% of a batch had to fall back, keep more candidates
-    // per query from now on.
-    if (certify && c0 - c1 > (nqb / 50 > 2 ? nqb / 50 : 2) && ix->slack_boost < 224) ix->slack_boost += 32;
+    // size and the data distribution): when too many queries of a batch had to fall back, keep more candidates
+    // per query from now on.  "Too many" is where the exact scans cost more than the wider tensor pass would: the
+    // fallback walks the database once per four queries (F / 4 x n d 4 B at ~5.5 TB/s) while the batch's tensor
+    // pass costs 2 nq n d flop at ~1.3 PFLOP/s and grows by < 10 % with 32 more candidates -- break-even at
+    // F ~ nq / 1200.  (Round 1 waited for 2 % of the batch: BASELINE config 5 on 2 GPUs spent 9 of its 34 ms per search
+    // in exact scans for 0.5 % of the queries.)
+    if (certify && c0 - c1 > (nqb / 1000 > 2 ? nqb / 1000 : 2) && ix->slack_boost < 224) ix->slack_boost += 32;
 }
 
 void harvest_prof_slot(b2f_index* ix, b2f_index::ProfSlot& sl) {
