@@ -262,6 +262,12 @@ int launch_synth(uint64_t seed, int64_t row0, int64_t nrows, int d, int normaliz
 int launch_prep_queries(const float* q, int nq, int nq_pad, int d, __nv_bfloat16* qb, int64_t dpad, float* qnorm,
                         float* qerr, float* qconst, const float* mu, uint32_t* zero, int zero_words, uint32_t* fill,
                         int64_t fill_words, cudaStream_t st);
+// range pass helpers (ingest.cu)
+int launch_gather_failed(const float* q, int d, const int32_t* fail_list, const float* fail_tau, const int32_t* nfail, int nfail_host,
+                         int cap, float* qf, float* tau2, int32_t* out_map, int32_t* range_count, int32_t* fail_list2,
+                         int32_t* fail_count2, cudaStream_t st);
+int launch_range_thresholds(const float* tau2, const int32_t* out_map, int n, int d, int metric, const float* qnorm, const float* qerr,
+                            const float* qconst, float max_row_norm, float max_row_err, float mu_norm, float* thr, cudaStream_t st);
 int launch_bf16_to_f32(const __nv_bfloat16* src, int64_t pitch, int64_t n, int d, const float* mu, float* dst, cudaStream_t st);
 
 // K4: exact fp32 re-rank of coarse candidates + certification.
@@ -291,6 +297,10 @@ struct RerankArgs {
     int32_t* fail_count;            // [0] uncertified queries, [1] of which list overflows, [2..3] u64 list entries
     int32_t q_base;                 // first query of this pass within the whole batch (query chunks)
     int32_t stage1;                 // LIST merge: candidates tried first on their own (0 = off; see merge_lists_kernel)
+    float* fail_tau;                // optional [nq]: exact k-th key found for fail_list[i] (FLT_MAX: none) -- the range pass's input
+    const int32_t* out_map;         // optional: query q of this launch writes row out_map[q] of D / I (< 0: skip) and is
+                                    // recorded under that index when it fails (range pass over compacted failed queries)
+    int32_t range;                  // 1: range pass -- the lists hold EVERY row with coarse key <= the fixed threshold: re-rank all
 };
 int launch_rerank(const RerankArgs& a, cudaStream_t st);
 
@@ -316,6 +326,7 @@ struct TensorScanLists {  // LIST-mode scratch (device)
     float* final_thr;     // [nq_pad * nlists]  the threshold each list was pruned against at the end of the stream
     int32_t* die_ctr;     // [4] ticket counters of the die-aware unit assignment (zero between launches), or null
     uint8_t* big_flag;    // [nq_pad] big batches: queries the warp-per-query merge passes on to the block kernel
+    const float* range_thr;  // optional [nq_pad]: range pass -- fixed per-query thresholds (no shared thresholds, no refresh)
 };
 int plan_tensor_scan(int nq, int64_t n, int d, int kp, TensorScanPlan* plan);
 int plan_unit_work(int T, int U, int R, int64_t ntiles, int kp, int unit, int32_t* seg_info, int64_t* tiles, int64_t cap, int32_t* counts);

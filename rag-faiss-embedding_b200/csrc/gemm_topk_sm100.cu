@@ -249,6 +249,7 @@ struct ListArgs {
     int bal_T;           // balanced work split: query tile units (pair tiles when PAIR) ...
     int bal_U;           // ... shared evenly by this many units (CTAs / CTA pairs); T <= U
     int bal_R;           // database tiles per round of the interleaved sweep
+    const float* range_thr;  // range pass: fixed threshold per query -- every row at or below it is listed; no sharing, no refresh
 };
 
 // ---- balanced work split (LIST mode) -----------------------------------------------------------------------------
@@ -828,6 +829,11 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 #pragma unroll
             for (int i = 0; i < JSLOTS; i++) best[i] = (i < JSLOTS - jv) ? -kInf : kInf;
             float thr = 3.0e38f, pub = kInf;  // refreshed before the first compare; never +inf (padding rows have key +inf)
+            // range pass (second tensor pass over queries the first could not certify): the threshold is FIXED per query --
+            // every true top-k row has a coarse key at or below it (launch_range_thresholds) -- so the lists end up holding
+            // every such row; nothing is published, consulted or pruned
+            const bool ranged = la.range_thr != nullptr;
+            if (ranged) thr = active ? la.range_thr[qrow] : -kInf;
             int cnt = 0;
             uint2* mylist = la.cand + ((int64_t)(active ? qrow : 0) * la.nl_stride + vsplit) * la.cap;
             // shared thresholds are laid out [virtual split][query] so that a warp's loads for one split coalesce
@@ -836,6 +842,7 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             // waits for), and its cost is L2 round trips: `wide` keeps 32 loads in flight -- one round trip for g <= 32 --
             // where no accumulators are live (top of the tile loop, end of the segment); inside a tile 16.
             auto refresh = [&](bool wide) {
+                if (ranged) return;
                 if (voucher && best[JSLOTS - 1] < pub) {
                     pub = best[JSLOTS - 1];
                     __stcg(gq + (int64_t)vsplit * gstride, pub);
@@ -1166,6 +1173,7 @@ merge_lists_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ c
         }
     }
     __syncthreads();
+    if (ra.out_map && ra.out_map[q] < 0) return;   // range pass: an unused slot of the compacted batch
     if (s_ovf) {
         // some candidates were dropped: only the exact scan can answer (it rewrites this query's D / I rows)
         if (tid == 0) rerank_record_failure(ra, q, true);
@@ -1297,16 +1305,24 @@ merge_lists_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ c
     // they first try the best `stage1` coarse candidates alone: every other row has a coarse key >= sk[stage1], and on
     // data the bf16 pass separates well that already certifies ~95% of the queries with half the rows read.  (Small
     // batches are latency-bound: a failed first stage would cost them a dependent round trip, so they skip it.)
+    __shared__ float s_tau_last;   // exact k-th key of the last re-rank (what a failed query hands to the range pass)
     bool cert = false;
-    if (ra.certify && ra.stage1 >= ra.k && ra.stage1 < nc1)
-        cert = rerank_block(ra, q, sk, si, ra.stage1, fminf(sk[ra.stage1], tc), false, ek, ei);
-    if (!cert) cert = rerank_block(ra, q, sk, si, nc1, bound1, M < kp, ek, ei);
-    if (!cert && ra.certify && M > kp && M <= RANK_MAX) {
-        // every list entry: rows outside the lists have coarse keys above T_c
-        cert = rerank_block(ra, q, sk, si, M, tc, false, ek, ei);
-        if (tid == 0 && cert) atomicAdd(ra.fail_count + 4, 1);  // diagnostics: queries rescued by the extended pass
+    if (ra.range) {
+        // range pass: the lists hold every row whose coarse key is <= the query's fixed threshold (= tc), among them
+        // every true top-k row: re-rank them all; certification against tc holds by construction of the threshold
+        if (M <= RANK_MAX) cert = rerank_block(ra, q, sk, si, M, tc, false, ek, ei, &s_tau_last);
+        else if (tid == 0) s_tau_last = FLT_MAX;
+    } else {
+        if (ra.certify && ra.stage1 >= ra.k && ra.stage1 < nc1)
+            cert = rerank_block(ra, q, sk, si, ra.stage1, fminf(sk[ra.stage1], tc), false, ek, ei, &s_tau_last);
+        if (!cert) cert = rerank_block(ra, q, sk, si, nc1, bound1, M < kp, ek, ei, &s_tau_last);
+        if (!cert && ra.certify && M > kp && M <= RANK_MAX) {
+            // every list entry: rows outside the lists have coarse keys above T_c
+            cert = rerank_block(ra, q, sk, si, M, tc, false, ek, ei, &s_tau_last);
+            if (tid == 0 && cert) atomicAdd(ra.fail_count + 4, 1);  // diagnostics: queries rescued by the extended pass
+        }
     }
-    if (tid == 0 && ra.certify && !cert) rerank_record_failure(ra, q, false);
+    if (tid == 0 && ra.certify && !cert) rerank_record_failure(ra, q, false, s_tau_last);
 }
 
 // ---- K3b + K4 for big batches: one WARP per query ---------------------------------------------------------
@@ -1323,7 +1339,7 @@ constexpr int WM_LISTS = 64;     // lists per query
 // Exact re-rank of the first nc candidates (sk / si: coarse keys ascending) by one warp; writes the best k in faiss
 // conventions, returns whether the result is certified (warp-uniform).  ek / ei: nc floats / ints of scratch.
 __device__ __forceinline__ bool warp_rerank(const RerankArgs& a, int q, const float* sk, const int32_t* si, int nc, float bound,
-                                            bool all_rows, float* ek, int32_t* ei, int lane) {
+                                            bool all_rows, float* ek, int32_t* ei, int lane, float& tau_out) {
     const float* qv = a.q + (int64_t)q * a.d;
     const bool l2 = a.metric == B2F_METRIC_L2;
     const int sl = lane & 7;
@@ -1363,6 +1379,7 @@ __device__ __forceinline__ bool warp_rerank(const RerankArgs& a, int q, const fl
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) tau = fminf(tau, __shfl_xor_sync(kFull, tau, d));   // exactly one lane holds the k-th key
     __syncwarp();
+    tau_out = tau;
     return all_rows || rerank_certified(a, q, tau, bound);
 }
 
@@ -1442,14 +1459,15 @@ merge_lists_warp_kernel(const uint2* __restrict__ cand, const int32_t* __restric
     const int nc1 = M < kp ? M : kp;
     const float bound1 = (M > kp) ? fminf(sk[kp - 1], tc) : tc;
     bool cert = false;
+    float tau = FLT_MAX;
     if (ra.certify && ra.stage1 >= ra.k && ra.stage1 < nc1)
-        cert = warp_rerank(ra, q, sk, si, ra.stage1, fminf(sk[ra.stage1], tc), false, s_ek[warp], s_ei[warp], lane);
-    if (!cert) cert = warp_rerank(ra, q, sk, si, nc1, bound1, M < kp, s_ek[warp], s_ei[warp], lane);
+        cert = warp_rerank(ra, q, sk, si, ra.stage1, fminf(sk[ra.stage1], tc), false, s_ek[warp], s_ei[warp], lane, tau);
+    if (!cert) cert = warp_rerank(ra, q, sk, si, nc1, bound1, M < kp, s_ek[warp], s_ei[warp], lane, tau);
     if (!cert && ra.certify && M > kp) {
-        cert = warp_rerank(ra, q, sk, si, M, tc, false, s_ek[warp], s_ei[warp], lane);
+        cert = warp_rerank(ra, q, sk, si, M, tc, false, s_ek[warp], s_ei[warp], lane, tau);
         if (lane == 0 && cert) atomicAdd(ra.fail_count + 4, 1);
     }
-    if (lane == 0 && ra.certify && !cert) rerank_record_failure(ra, q, false);
+    if (lane == 0 && ra.certify && !cert) rerank_record_failure(ra, q, false, tau);
 }
 
 // ---- host side --------------------------------------------------------------------------------------
@@ -1746,6 +1764,7 @@ int launch_tensor_scan(const __nv_bfloat16* scan, int64_t dpad, const float* nor
             la.bal_T = plan.tile_units;
             la.bal_U = plan.units;
             la.bal_R = plan.round_tiles;
+            la.range_thr = lists.range_thr;
         }
         // lists.shared_thr was filled with 0x7f7f7f7f (3.39e38, "no information yet") by the query-prep kernel
         if (plan.pair_mode)
@@ -1801,7 +1820,8 @@ int launch_merge_lists(const TensorScanLists& lists, int nq, const TensorScanPla
         const char* e = getenv("B200FLAT_WARP_MERGE");   // diagnostics: 0 = off, n > 1 = batch size from which it is used
         warp_env = e ? atoi(e) : 8192;   // same-box A/B (r02n): 8192 queries 125 -> 114 us, 4096 queries 78 -> 82 us, 1024: 47 -> 73 us
     }
-    if (warp_env > 0 && nq >= warp_env && lists.big_flag && plan.nlists <= k2::WM_LISTS && plan.kp <= k2::WM_MAX / 2 && ra.D) {
+    if (warp_env > 0 && nq >= warp_env && lists.big_flag && plan.nlists <= k2::WM_LISTS && plan.kp <= k2::WM_MAX / 2 && ra.D &&
+        !ra.range && !ra.out_map) {
         k2::merge_lists_warp_kernel<<<(nq + k2::WM_WARPS - 1) / k2::WM_WARPS, k2::WM_WARPS * 32, 0, st>>>(
             reinterpret_cast<const uint2*>(lists.cand), lists.counts, lists.final_thr, plan.nlists, plan.pair_mode ? 2 * k2::BM : k2::BM,
             plan.tile_units, plan.units, k2::EPI_WARPS_LIST / 4, plan.kp, plan.list_cap, total_entries, lists.big_flag, nq, ra);

@@ -376,6 +376,87 @@ int launch_prep_queries(const float* q, int nq, int nq_pad, int d, __nv_bfloat16
 }
 
 // the authoritative rows of a bf16-storage index: r = fl32(mu + x~') (mu null: the rounded rows themselves)
+// ---- range pass (second tensor pass over the queries the first could not certify) ------------------------------------
+// gather: failed query i (fail_list[i], i < *nfail) with a usable exact k-th key tau goes to slot s of the compact batch
+// (its fp32 vector to qf[s], tau to tau2[s], its index in the whole batch to out_map[s]); the others (list overflow, fewer
+// than k valid candidates: tau = FLT_MAX) go straight to the exact scan's list.  out_map is pre-filled with -1, qf with 0.
+__global__ void __launch_bounds__(256)
+gather_failed_kernel(const float* __restrict__ q, int d, const int32_t* __restrict__ fail_list, const float* __restrict__ fail_tau,
+                     const int32_t* __restrict__ nfail, int cap, float* __restrict__ qf, float* __restrict__ tau2,
+                     int32_t* __restrict__ out_map, int32_t* __restrict__ range_count, int32_t* __restrict__ fail_list2,
+                     int32_t* __restrict__ fail_count2) {
+    const int lane = threadIdx.x & 31;
+    const int n = *nfail;
+    for (int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += gridDim.x * (blockDim.x >> 5)) {
+        const int32_t orig = fail_list[i];
+        const float tau = fail_tau[i];
+        int slot = -1;
+        if (lane == 0) {
+            if (tau < 1.0e37f) {
+                slot = atomicAdd(range_count, 1);
+                if (slot >= cap) slot = -1;   // more failures than the range pass holds: exact scan
+            }
+            if (slot < 0) fail_list2[atomicAdd(fail_count2, 1)] = orig;
+            else { tau2[slot] = tau; out_map[slot] = orig; }
+        }
+        slot = __shfl_sync(kFull, slot, 0);
+        if (slot >= 0)
+            for (int c = lane; c < d; c += 32) qf[(int64_t)slot * d + c] = q[(int64_t)orig * d + c];
+    }
+}
+
+int launch_gather_failed(const float* q, int d, const int32_t* fail_list, const float* fail_tau, const int32_t* nfail, int nfail_host,
+                         int cap, float* qf, float* tau2, int32_t* out_map, int32_t* range_count, int32_t* fail_list2,
+                         int32_t* fail_count2, cudaStream_t st) {
+    if (nfail_host <= 0) return B2F_OK;
+    int blocks = (nfail_host + 7) / 8;
+    if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
+    gather_failed_kernel<<<blocks, 256, 0, st>>>(q, d, fail_list, fail_tau, nfail, cap, qf, tau2, out_map, range_count, fail_list2, fail_count2);
+    B2F_CUDA(cudaGetLastError());
+    return B2F_OK;
+}
+
+// The fixed threshold of a range query: every row whose exact key is <= tau (the k-th key already found, so: every true
+// top-k row) has a coarse key <= thr.  Inverse of the certification test (rerank_certified) with a 1e-6 margin on tau, so
+// that re-ranking everything at or below thr certifies by construction.
+__global__ void range_thresholds_kernel(const float* __restrict__ tau2, const int32_t* __restrict__ out_map, int n, int d, int l2,
+                                        const float* __restrict__ qnorm, const float* __restrict__ qerr,
+                                        const float* __restrict__ qconst, float max_row_norm, float max_row_err, float mu_norm,
+                                        float* __restrict__ thr) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (out_map[i] < 0) {
+        thr[i] = -__int_as_float(0x7f800000);   // unused slot: nothing is listed
+        return;
+    }
+    const float tau = tau2[i];
+    const float qn2 = qnorm[i], qn = sqrtf(qn2), eq = qerr[i];
+    const float gam = 4.f * (float)(d + 16) * 5.9604645e-8f;
+    if (l2) {
+        const float nu = gam * (2.f * qn * max_row_norm + qn2 + max_row_norm * max_row_norm);
+        const float t = fmaxf(tau, 0.f) * (1.f + 2e-6f) + 1e-30f;
+        const float L = sqrtf(t) * (1.f + 1e-6f) + eq + max_row_err;   // certified <=> (sqrt(c + qn2 - nu) - eq - E)^2 (1 - 4e-7) > tau
+        thr[i] = L * L * (1.f + 1e-6f) - qn2 + nu * (1.f + 1e-6f) + 1e-30f;
+    } else {
+        const float cq = qconst ? qconst[i] : 0.f;
+        const float xmax = max_row_norm + max_row_err + mu_norm;
+        const float nu = gam * qn * max_row_norm + 2.4e-7f * (mu_norm * (xmax + qn + eq + mu_norm) + qn * max_row_norm);
+        const float slack = nu + (qn + eq) * max_row_err + max_row_norm * eq;
+        // certified <=> -thr + cq + slack < -tau  <=>  thr > tau + cq + slack
+        const float base = tau + cq + slack;
+        thr[i] = base + fabsf(base) * 2e-6f + 1e-30f;
+    }
+}
+
+int launch_range_thresholds(const float* tau2, const int32_t* out_map, int n, int d, int metric, const float* qnorm, const float* qerr,
+                            const float* qconst, float max_row_norm, float max_row_err, float mu_norm, float* thr, cudaStream_t st) {
+    if (n <= 0) return B2F_OK;
+    range_thresholds_kernel<<<(n + 255) / 256, 256, 0, st>>>(tau2, out_map, n, d, metric == B2F_METRIC_L2 ? 1 : 0, qnorm, qerr, qconst,
+                                                            max_row_norm, max_row_err, mu_norm, thr);
+    B2F_CUDA(cudaGetLastError());
+    return B2F_OK;
+}
+
 __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ src, int64_t pitch, int64_t n, int d,
                                    const float* __restrict__ mu, float* __restrict__ dst) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -131,12 +131,13 @@ __device__ __forceinline__ bool rerank_certified(const RerankArgs& a, int q, flo
 // (block-uniform).  Nothing is recorded about a failure here: the caller decides (it may retry with
 // more candidates first).
 __device__ __forceinline__ bool rerank_block(const RerankArgs& a, int q, const float* ck, const int32_t* ci, int nc, float bound,
-                                             bool all_rows, float* ek, int32_t* ei) {
+                                             bool all_rows, float* ek, int32_t* ei, float* tau_out = nullptr) {
     __shared__ float s_tau;
     __shared__ int s_cert;
     const int lane = threadIdx.x & 31;
     const float* qv = a.q + (int64_t)q * a.d;
     const bool l2 = a.metric == B2F_METRIC_L2;
+    const int64_t orow = a.out_map ? (int64_t)a.out_map[q] : (int64_t)q;   // row of D / I this query answers
     if (threadIdx.x == 0) s_tau = FLT_MAX;
     __syncthreads();
     // 8 lanes per candidate, 32 candidates per pass of the block
@@ -165,7 +166,7 @@ __device__ __forceinline__ bool rerank_block(const RerankArgs& a, int q, const f
         }
         if (rank < a.k) {
             if (a.D) {  // fused finalize: faiss conventions straight to the caller's buffers
-                const int64_t o = (int64_t)q * a.k + rank;
+                const int64_t o = orow * a.k + rank;
                 a.D[o] = mi < 0 ? (l2 ? FLT_MAX : -FLT_MAX) : (l2 ? mk : -mk);
                 a.I[o] = mi < 0 ? -1 : (int64_t)mi + a.id_offset;
             } else {
@@ -178,8 +179,8 @@ __device__ __forceinline__ bool rerank_block(const RerankArgs& a, int q, const f
     // fewer candidates than k: pad (faiss: label -1, distance +-FLT_MAX)
     for (int t = nc + threadIdx.x; t < a.k; t += kRerankThreads) {
         if (a.D) {
-            a.D[(int64_t)q * a.k + t] = l2 ? FLT_MAX : -FLT_MAX;
-            a.I[(int64_t)q * a.k + t] = -1;
+            a.D[orow * a.k + t] = l2 ? FLT_MAX : -FLT_MAX;
+            a.I[orow * a.k + t] = -1;
         } else {
             a.out_key[(int64_t)q * a.k + t] = FLT_MAX;
             a.out_id[(int64_t)q * a.k + t] = -1;
@@ -189,15 +190,19 @@ __device__ __forceinline__ bool rerank_block(const RerankArgs& a, int q, const f
     if (threadIdx.x == 0) {
         const bool certified = all_rows || rerank_certified(a, q, s_tau, bound);  // all_rows: every row of the index is already a candidate
         s_cert = certified ? 1 : 0;
+        if (tau_out) *tau_out = s_tau;
     }
     __syncthreads();
     return s_cert != 0;
 }
 
 // Records an uncertified query for the exact scan that closes the search.
-__device__ __forceinline__ void rerank_record_failure(const RerankArgs& a, int q, bool overflowed) {
+// tau: the exact k-th key of the candidates that WERE re-ranked (an upper bound of the true k-th key), FLT_MAX when
+// nothing usable was found (list overflow, fewer than k valid candidates).
+__device__ __forceinline__ void rerank_record_failure(const RerankArgs& a, int q, bool overflowed, float tau = FLT_MAX) {
     const int slot = atomicAdd(a.fail_count, 1);
-    a.fail_list[slot] = q + a.q_base;
+    a.fail_list[slot] = a.out_map ? a.out_map[q] : q + a.q_base;
+    if (a.fail_tau) a.fail_tau[slot] = tau;
     if (overflowed) atomicAdd(a.fail_count + 1, 1);
 }
 
