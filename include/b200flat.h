@@ -105,6 +105,8 @@ typedef struct b2f_stats {
     int64_t prof_main_launches;
     int64_t prof_searches;
     int64_t rescued_queries;   /* tensor path: queries certified only after re-ranking every list entry (no database pass) */
+    int64_t range_queries;     /* tensor path: uncertified queries served by the range pass (a second tensor pass with a fixed
+                                  threshold per query) instead of the exact scan */
 } b2f_stats;
 
 /* ---- lifecycle -------------------------------------------------------------------------------

@@ -60,6 +60,7 @@ class Stats(ctypes.Structure):
         ("prof_main_launches", ctypes.c_int64),
         ("prof_searches", ctypes.c_int64),
         ("rescued_queries", ctypes.c_int64),
+        ("range_queries", ctypes.c_int64),
     ]
 
     def as_dict(self):

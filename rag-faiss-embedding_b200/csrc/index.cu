@@ -62,6 +62,8 @@ struct b2f_index {
     uint32_t scan_launches = 0;       // launch parity of the scan's cross-CTA bounds
     int32_t harvested_seq = 0;        // last seq whose counters were folded into the host-side statistics
     int slack_boost = 0;              // extra candidates per query, raised when too many queries fail certification
+    bool range_mode = false;          // earlier batches left many queries uncertified: run the range pass (one host sync per search)
+    int range_quiet = 0;              // consecutive range-mode searches whose first pass certified everything
     unsigned long long* totals = nullptr;  // device [4]: fallback queries, overflowed queries, rescued queries (running totals)
     cudaEvent_t ev_done = nullptr;    // recorded at the end of every search (searches return without synchronising)
     cudaStream_t last_stream = nullptr;
@@ -336,9 +338,15 @@ void harvest_flag(b2f_index* ix) {
     // per query from now on.  "Too many" is where the exact scans cost more than the wider tensor pass would: the
     // fallback walks the database once per four queries (F / 4 x n d 4 B at ~5.5 TB/s) while the batch's tensor
     // pass costs 2 nq n d flop at ~1.3 PFLOP/s and grows by < 10 % with 32 more candidates -- break-even at
-    // F ~ nq / 1200.  (Round 1 waited for 2 % of the batch: BASELINE config 5 on 2 GPUs spent 9 of its 34 ms per search
-    // in exact scans for 0.5 % of the queries.)
-    if (certify && c0 - c1 > (nqb / 1000 > 2 ? nqb / 1000 : 2) && ix->slack_boost < 224) ix->slack_boost += 32;
+    // F ~ nq / 1200; the boost waits for 0.5 % because the range pass below is cheaper still.  (Round 1 waited for 2 % of
+    // the batch: BASELINE config 5 on 2 GPUs spent 9 of its 34 ms per search in exact scans for 0.5 % of the queries.)
+    if (certify && c0 - c1 > (nqb / 200 > 2 ? nqb / 200 : 2) && ix->slack_boost < 224) ix->slack_boost += 32;
+    // Well before that (F > nq / 1000) the range pass takes over: a second TENSOR pass over the uncertified queries with a
+    // fixed threshold per query, one database pass for all of them instead of one exact scan per four (search_locked).
+    if (certify && !ix->range_mode && c0 - c1 > (nqb / 1000 > 2 ? nqb / 1000 : 2)) {
+        ix->range_mode = true;
+        ix->range_quiet = 0;
+    }
 }
 
 void harvest_prof_slot(b2f_index* ix, b2f_index::ProfSlot& sl) {
@@ -828,6 +836,30 @@ int b2f_merge_topk(int32_t metric, int64_t nq, int64_t k, int32_t nparts, const 
 
 }  // extern "C"
 
+// ---- range pass (second tensor pass over uncertified queries) -----------------------------------------
+constexpr int kRangeCap = 1024;   // failed queries one range pass holds; more go to the exact scan
+constexpr int kRangeListCap = 256;
+
+static int plan_range_pass(int nfail, int64_t n, int d, int kp, TensorScanPlan* plan) {
+    if (plan_tensor_scan(nfail, n, d, kp, plan) != B2F_OK || !plan->list_mode) return B2F_EINVAL;
+    if (plan->list_cap < kRangeListCap) plan->list_cap = kRangeListCap;   // lists are not pruned: every row at or below the threshold
+    return B2F_OK;
+}
+static size_t range_lists_bytes(const TensorScanPlan& p) {
+    const size_t nq_pad = (size_t)p.nq_tiles * 128;
+    return 3 * align_up(nq_pad * p.nlists * 4, 256) + align_up(nq_pad * p.nlists * (size_t)p.list_cap * 8, 256) + align_up(nq_pad, 256);
+}
+static size_t range_pass_bytes(const b2f_index* ix, int nq, int kp) {
+    size_t lists = 0;
+    for (int f = 128; f <= kRangeCap; f *= 2) {   // the list geometry depends on the number of failed queries: take the largest
+        TensorScanPlan p{};
+        if (plan_range_pass(f, ix->ntotal, ix->d, kp, &p) == B2F_OK && range_lists_bytes(p) > lists) lists = range_lists_bytes(p);
+    }
+    const size_t cap = kRangeCap;
+    return align_up(cap * ix->d * 4, 256) + align_up(cap * ix->dpad * 2, 256) + 7 * align_up(cap * 4, 256) +
+           2 * align_up((size_t)nq * 4, 256) + 8192 + lists;
+}
+
 // ---- search ----------------------------------------------------------------------------------------
 // The caller holds ix->mu (search_pooled pools the queries into the index's buffer and searches them under ONE
 // lock, so a second thread cannot overwrite or re-allocate that buffer in between).
@@ -909,6 +941,7 @@ static int search_locked(b2f_index* ix, int64_t nq64, const float* q, int64_t k6
             need += 2 * align_up((size_t)chunk_nq * kp * 4, 256);       // merged coarse
         }
         need += align_up((size_t)nq * 4, 256) + 256;                    // fail list + counters
+        if (ix->range_mode) need += range_pass_bytes(ix, nq, kp);
     }
     B2F_TRY(ensure_ws(ix, need));
     Bump bump(ix->ws);
@@ -983,6 +1016,7 @@ static int search_locked(b2f_index* ix, int64_t nq64, const float* q, int64_t k6
             ci = bump.take<int32_t>((size_t)chunk_nq * kp);
         }
         int32_t* fail_list = bump.take<int32_t>(nq);
+        float* fail_tau = ix->range_mode ? bump.take<float>(nq) : nullptr;
         // [0] uncertified queries, [1] of which list overflows, [2..3] u64 list entries, [4] rescued by the extended pass
         int32_t* counters = bump.take<int32_t>(16);   // [8..11]: ticket counters of K2's die-aware unit assignment
         lists.die_ctr = counters + 8;
@@ -1025,6 +1059,7 @@ static int search_locked(b2f_index* ix, int64_t nq64, const float* q, int64_t k6
             ra.I = Id + (int64_t)c0 * k;
             ra.id_offset = P.id_offset;
             ra.fail_list = fail_list;
+            ra.fail_tau = fail_tau;
             ra.fail_count = counters;
             ra.q_base = c0;
             {   // First-stage re-rank (the best n candidates alone before the k' best): OFF.  Same-box A/B (r02n): no gain at
@@ -1049,10 +1084,96 @@ static int search_locked(b2f_index* ix, int64_t nq64, const float* q, int64_t k6
                 ix->st.last_launches += 4;
             }
         }  // query chunks
+        int32_t* scan_list = fail_list;
+        int32_t* scan_counters = counters;
+        if (ix->range_mode && certify && fail_tau) {
+            // Range pass.  Earlier batches on this index left many queries uncertified (data denser than the bf16 band even
+            // after centring): instead of one exact scan per four of them, ONE more tensor pass serves them all.  For a
+            // failed query the first pass found an exact k-th key tau, an upper bound of the true one; every true top-k row
+            // therefore has a coarse key <= thr(tau) (the certification bound, inverted), so a pass that lists EVERY row at
+            // or below that fixed threshold and re-ranks all of them is exact.  The host must know how many queries failed
+            // to plan the pass: the one synchronisation inside a search, paid only by indexes in this mode.
+            volatile int32_t* hf = ix->host_flag + 12;
+            B2F_CUDA(cudaMemcpyAsync(const_cast<int32_t*>(hf), counters, 4, cudaMemcpyDeviceToHost, st));
+            B2F_CUDA(cudaStreamSynchronize(st));
+            const int nfail = hf[0];
+            if (nfail == 0) {
+                if (++ix->range_quiet >= 8) ix->range_mode = false;   // the data (or the adaptive slack) no longer needs it
+            } else {
+                ix->range_quiet = 0;
+            }
+            TensorScanPlan rp{};
+            const int nr = nfail < kRangeCap ? nfail : kRangeCap;
+            if (nfail >= 8 && plan_range_pass(nr, ix->ntotal, ix->d, kp, &rp) == B2F_OK) {
+                const int nq_pad2 = rp.nq_tiles * 128;
+                float* qf = bump.take<float>((size_t)kRangeCap * ix->d);
+                __nv_bfloat16* qb2 = bump.take<__nv_bfloat16>((size_t)kRangeCap * ix->dpad);
+                float* qnorm2 = bump.take<float>(kRangeCap);
+                float* qerr2 = bump.take<float>(kRangeCap);
+                float* qconst2 = bump.take<float>(kRangeCap);
+                float* tau2 = bump.take<float>(kRangeCap);
+                float* thr2 = bump.take<float>(kRangeCap);
+                int32_t* out_map = bump.take<int32_t>(kRangeCap);
+                int32_t* fail_list2 = bump.take<int32_t>(nq);
+                int32_t* counters_b = bump.take<int32_t>(32);   // [0..7] as `counters`, [8..11] K2's tickets, [16] compacted queries
+                TensorScanLists l2{};
+                l2.shared_thr = bump.take<float>((size_t)nq_pad2 * rp.nlists);
+                l2.counts = bump.take<int32_t>((size_t)nq_pad2 * rp.nlists);
+                l2.final_thr = bump.take<float>((size_t)nq_pad2 * rp.nlists);
+                l2.cand = bump.take<uint2>((size_t)nq_pad2 * rp.nlists * rp.list_cap);
+                l2.big_flag = bump.take<uint8_t>((size_t)nq_pad2);
+                l2.die_ctr = counters_b + 8;
+                l2.range_thr = thr2;
+                B2F_CUDA(cudaMemsetAsync(counters_b, 0, 32 * 4, st));
+                B2F_CUDA(cudaMemsetAsync(out_map, 0xff, (size_t)kRangeCap * 4, st));
+                B2F_CUDA(cudaMemsetAsync(qf, 0, (size_t)nq_pad2 * ix->d * 4, st));
+                B2F_TRY(launch_gather_failed(qd, ix->d, fail_list, fail_tau, counters, nfail, nr, qf, tau2, out_map, counters_b + 16,
+                                             fail_list2, counters_b, st));
+                B2F_TRY(launch_prep_queries(qf, nr, nq_pad2, ix->d, qb2, ix->dpad, qnorm2, qerr2, qconst2, ix->mu_set ? ix->centre : nullptr,
+                                            nullptr, 0, reinterpret_cast<uint32_t*>(l2.shared_thr), (int64_t)nq_pad2 * rp.nlists, st));
+                B2F_TRY(launch_range_thresholds(tau2, out_map, nr, ix->d, ix->metric, qnorm2, qerr2, qconst2, sqrtf(ix->host_stats[0]),
+                                                sqrtf(ix->host_stats[1]), ix->mu_norm, thr2, st));
+                B2F_TRY(launch_tensor_scan(ix->scan, ix->dpad, ix->norms, ix->ntotal, ix->metric, qb2, nr, nq_pad2, rp, nullptr, nullptr, l2, st));
+                RerankArgs r2{};
+                r2.rows_f32 = ix->storage == B2F_STORE_F32 ? ix->rows_f32 : nullptr;
+                r2.rows_bf16 = ix->scan;
+                r2.pitch_bf16 = ix->dpad;
+                r2.centre = (ix->storage == B2F_STORE_BF16 && ix->mu_set) ? ix->centre : nullptr;
+                r2.q = qf;
+                r2.qnorm = qnorm2;
+                r2.qerr = qerr2;
+                r2.qconst = qconst2;
+                r2.mu_norm = ix->mu_norm;
+                r2.nq = nr;
+                r2.kp = kp;
+                r2.k = k;
+                r2.d = ix->d;
+                r2.metric = ix->metric;
+                r2.ntotal = ix->ntotal;
+                r2.max_row_norm = sqrtf(ix->host_stats[0]);
+                r2.max_row_err = sqrtf(ix->host_stats[1]);
+                r2.certify = 1;
+                r2.D = Dd;
+                r2.I = Id;
+                r2.id_offset = P.id_offset;
+                r2.fail_list = fail_list2;
+                r2.fail_count = counters_b;
+                r2.out_map = out_map;
+                r2.range = 1;
+                B2F_TRY(launch_merge_lists(l2, nr, rp, nullptr, r2, st));
+                // the statistics the closing kernel publishes: what the first pass counted, with the final fallback count
+                B2F_CUDA(cudaMemcpyAsync(counters_b + 1, counters + 1, 7 * 4, cudaMemcpyDeviceToDevice, st));
+                ix->st.launches += 5;
+                ix->st.last_launches += 5;
+                ix->st.range_queries += nr;
+                scan_list = fail_list2;
+                scan_counters = counters_b;
+            }
+        }
         // Closing kernel: the exact scan over the queries that could not be certified.  The count lives on the
         // device -- with none (the usual case) the kernel publishes the counters and exits -- so the host never
         // waits inside a search and consecutive searches run back to back on the GPU.
-        B2F_TRY(enqueue_scan(ix, qd, fail_list, counters, 0, k, Dd, Id, P.id_offset, scan_scratch, counters, ++ix->seq, nq,
+        B2F_TRY(enqueue_scan(ix, qd, scan_list, scan_counters, 0, k, Dd, Id, P.id_offset, scan_scratch, scan_counters, ++ix->seq, nq,
                              certify, st));
     }
     if (slot) {

@@ -390,6 +390,54 @@ def test_big_batch_warp_merge_and_first_stage(m, metric):
     _check(D2, I2, *orc.np_search_f64(xb2, xq2, k, metric), metric, min_recall=0.999 if metric == 1 else 0.0)
 
 
+@pytest.mark.parametrize("metric", [1, 0])
+def test_range_pass_serves_uncertified_queries(m, metric):
+    """Data denser than the bf16 band (clusters of 80 near-duplicates): the k' best and the extended stage cannot certify,
+    so the first search re-runs hundreds of queries through the exact scan, four per database pass.  The index notices
+    and from the next search on serves them with the range pass -- ONE more tensor pass with a fixed threshold per query
+    (every row whose coarse key can belong to a true top-k row is listed and re-ranked).  Results are exact both ways;
+    the second search must leave (almost) nothing to the exact scan."""
+    import time
+
+    import torch
+
+    rng = np.random.default_rng(9)
+    d, k, nq = 128, 10, 512
+    centres = rng.standard_normal((300, d)).astype(np.float32)
+    xb = (np.repeat(centres, 80, axis=0) + rng.standard_normal((24000, d)).astype(np.float32) * 1e-3).astype(np.float32)
+    xq = (centres[rng.integers(0, 300, nq)] + rng.standard_normal((nq, d)).astype(np.float32) * 1e-3).astype(np.float32)
+    if metric == 0:
+        xb /= np.linalg.norm(xb, axis=1, keepdims=True)
+        xq /= np.linalg.norm(xq, axis=1, keepdims=True)
+    ref = orc.np_search_f64(xb, xq, k, metric)
+    ix = _make(m, xb, metric).set_search_params(algo=m.ALGO_TENSOR)
+    tie_ok = 0.999 if metric == 1 else 0.0   # (normalised near-duplicates: fp32 inner products tie, see the test above)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    D, I = ix.search(xq, k)
+    t_first = time.perf_counter() - t0
+    _check(D, I, *ref, metric, min_recall=tie_ok)
+    st1 = ix.stats()
+    if st1["fallback_queries"] <= nq // 1000 + 2:
+        pytest.skip("the first pass certified this data: nothing for the range pass to do")
+    t0 = time.perf_counter()
+    D2, I2 = ix.search(xq, k)
+    t_second = time.perf_counter() - t0
+    _check(D2, I2, *ref, metric, min_recall=tie_ok)
+    st2 = ix.stats()
+    served = st2["range_queries"] - st1["range_queries"]
+    left = st2["fallback_queries"] - st1["fallback_queries"]
+    print(f"range pass: first search {st1['fallback_queries']} exact-scan queries in {t_first * 1e3:.2f} ms; second search "
+          f"{served} range queries, {left} exact-scan queries in {t_second * 1e3:.2f} ms")
+    assert served >= min(st1["fallback_queries"], 8), (st1, st2)
+    assert left <= max(st1["fallback_queries"] // 10, 4), (st1, st2)
+    # ... and a third search with other queries, device tensors, stays exact
+    xq3 = torch.from_numpy(xq[::-1].copy()).cuda()
+    D3, I3 = ix.search(xq3, k)
+    torch.cuda.synchronize()
+    _check(D3.cpu().numpy(), I3.cpu().numpy(), ref[0][::-1], ref[1][::-1], metric, min_recall=tie_ok)
+
+
 def test_very_large_batch_is_cut_into_list_passes(m):
     """20000 queries are far more than one wave of query tiles: the planner cuts the batch into LIST-mode passes
     (not the multi-wave HEAP selection); results must be exact and independent of the cut."""
