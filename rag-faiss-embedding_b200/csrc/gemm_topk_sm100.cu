@@ -1094,6 +1094,33 @@ __device__ __forceinline__ int block_count_le(const unsigned long long* comp, in
     return s_cnt[it % 3];
 }
 
+// One step of the 8-bit radix select after the 256-bin histogram is filled: block-wide inclusive scan (warp scans +
+// the 8 warp totals), the bin holding the `need`-th element extends `lo`, `need` becomes the rank inside that bin.
+__device__ __forceinline__ void radix_pick(int* s_hist, int* s_wsum, int* s_sel, int shift, unsigned int& lo, int& need,
+                                           int tid, int lane, int warp) {
+    __syncthreads();
+    const int h = s_hist[tid];
+    int incl = h;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int up = __shfl_up_sync(kFull, incl, d);
+        if (lane >= d) incl += up;
+    }
+    if (lane == 31) s_wsum[warp] = incl;
+    __syncthreads();
+    int base = 0;
+    for (int w = 0; w < warp; w++) base += s_wsum[w];
+    incl += base;
+    if (incl >= need && incl - h < need) {  // exactly one bin
+        s_sel[0] = tid;
+        s_sel[1] = need - (incl - h);
+    }
+    __syncthreads();
+    lo |= (unsigned int)s_sel[0] << shift;
+    need = s_sel[1];
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(MERGE_THREADS)
 merge_lists_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ counts, const float* __restrict__ final_thr,
                    int nl_stride, int tile_queries, int ntile_units, int total_units, int halves, int kp, int list_cap,
@@ -1169,7 +1196,7 @@ merge_lists_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ c
         if (lane == 0) {
             s_off[0] = 0;
             if (total_entries) atomicAdd(total_entries, (unsigned long long)run);
-            if (run > cap_entries) s_ovf = 1;
+            if (run > cap_entries && (ra.range || !ra.certify)) s_ovf = 1;
         }
     }
     __syncthreads();
@@ -1179,7 +1206,59 @@ merge_lists_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ c
         if (tid == 0) rerank_record_failure(ra, q, true);
         return;
     }
-    const int M = s_off[nsplits];
+    int M = s_off[nsplits];
+    // More entries than the merge holds in shared memory, none dropped (thresholds that never tightened: e.g. a
+    // query whose best rows all sit in one or two lists because near-duplicates are stored next to each other).
+    // The k' best are still in the lists: find the k'-th coarse key K by the same radix select run over the lists in
+    // global memory, keep the entries with keys <= K and go on with those.  Such a query seldom certifies -- but
+    // it fails WITH its exact k-th distance, which is what the range pass needs to answer it without the exact scan.
+    const bool big = M > cap_entries;
+    if (big) {
+        unsigned int lo = 0;
+        int need = kp;
+#pragma unroll 1
+        for (int pass = 0; pass < 4; pass++) {
+            const int shift = 24 - 8 * pass;
+            s_hist[tid] = 0;
+            __syncthreads();
+#pragma unroll 1
+            for (int l = 0; l < nsplits; l++) {
+                const int c = s_off[l + 1] - s_off[l];
+                const uint2* p = cand + ((int64_t)q * nl_stride + l) * list_cap;
+                for (int j0 = 0; j0 < c; j0 += MERGE_THREADS) {
+                    const int j = j0 + tid;
+                    const unsigned int key = j < c ? enc_key(__uint_as_float(p[j].x)) : 0u;
+                    const bool in = j < c && (pass == 0 || (key >> (shift + 8)) == (lo >> (shift + 8)));
+                    const unsigned int bin = (key >> shift) & 255u;
+                    const unsigned int peers = __match_any_sync(kFull, in ? bin : 256u + (unsigned)lane);
+                    if (in && lane == __ffs(peers) - 1) atomicAdd(&s_hist[bin], __popc(peers));
+                }
+            }
+            radix_pick(s_hist, s_wsum, s_sel, shift, lo, need, tid, lane, warp);
+        }
+#pragma unroll 1
+        for (int l = 0; l < nsplits; l++) {
+            const int c = s_off[l + 1] - s_off[l];
+            const uint2* p = cand + ((int64_t)q * nl_stride + l) * list_cap;
+            for (int j = tid; j < c; j += MERGE_THREADS) {
+                const uint2 e = p[j];
+                const unsigned int key = enc_key(__uint_as_float(e.x));
+                if (key <= lo) {
+                    const int slot = atomicAdd(&s_nrest, 1);
+                    if (slot < cap_entries) comp[slot] = ((unsigned long long)key << 32) | (unsigned long long)e.y;
+                }
+            }
+        }
+        __syncthreads();
+        M = s_nrest;   // >= k'
+        __syncthreads();
+        if (tid == 0) s_nrest = 0;
+        if (M > cap_entries) {   // that many equal keys: give up
+            if (tid == 0) rerank_record_failure(ra, q, true);
+            return;
+        }
+        __syncthreads();
+    } else {
     // gather the lists into one array of composites: flattened over all candidates so every thread has independent
     // loads in flight; the owning list of element i comes from a map filled by one thread per list
     for (int l = tid; l < nsplits; l += MERGE_THREADS) {
@@ -1203,6 +1282,7 @@ merge_lists_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ c
             const int i = i0 + u * MERGE_THREADS;
             if (i < M) comp[i] = ((unsigned long long)enc_key(__uint_as_float(e[u].x)) << 32) | (unsigned long long)e[u].y;
         }
+    }
     }
     __syncthreads();
     // Selection.  sk / si [0, min(k', M)): the k' best, ascending; [k', M) (when M <= RANK_MAX): the other list
@@ -1237,28 +1317,7 @@ merge_lists_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ c
                 const unsigned int peers = __match_any_sync(kFull, in ? bin : 256u + (unsigned)lane);
                 if (in && lane == __ffs(peers) - 1) atomicAdd(&s_hist[bin], __popc(peers));
             }
-            __syncthreads();
-            // inclusive scan of the 256 bins: warp scans + the 8 warp totals
-            const int h = s_hist[tid];
-            int incl = h;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int up = __shfl_up_sync(kFull, incl, d);
-                if (lane >= d) incl += up;
-            }
-            if (lane == 31) s_wsum[warp] = incl;
-            __syncthreads();
-            int base = 0;
-            for (int w = 0; w < warp; w++) base += s_wsum[w];
-            incl += base;
-            if (incl >= need && incl - h < need) {  // exactly one bin
-                s_sel[0] = tid;
-                s_sel[1] = need - (incl - h);
-            }
-            __syncthreads();
-            lo |= (unsigned int)s_sel[0] << shift;
-            need = s_sel[1];
-            __syncthreads();
+            radix_pick(s_hist, s_wsum, s_sel, shift, lo, need, tid, lane, warp);
         }
         const unsigned long long kbits = (unsigned long long)lo << 32;
         T = kbits | 0xffffffffull;
@@ -1300,7 +1359,7 @@ merge_lists_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ c
     // K4: exact fp32 re-rank of the k' best + certification + faiss-formatted output
     const float tc = dec_key(s_tc_enc);
     const int nc1 = M < kp ? M : kp;
-    const float bound1 = (M > kp) ? fminf(sk[kp - 1], tc) : tc;
+    const float bound1 = (M > kp || big) ? fminf(sk[kp - 1], tc) : tc;   // big: rows beyond the kept entries have keys >= sk[k' - 1]
     // Big batches are bound by the random row reads of the re-rank (8192 queries x 32 candidates x 1.5 KB = 400 MB), so
     // they first try the best `stage1` coarse candidates alone: every other row has a coarse key >= sk[stage1], and on
     // data the bf16 pass separates well that already certifies ~95% of the queries with half the rows read.  (Small
@@ -1316,7 +1375,7 @@ merge_lists_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ c
         if (ra.certify && ra.stage1 >= ra.k && ra.stage1 < nc1)
             cert = rerank_block(ra, q, sk, si, ra.stage1, fminf(sk[ra.stage1], tc), false, ek, ei, &s_tau_last);
         if (!cert) cert = rerank_block(ra, q, sk, si, nc1, bound1, M < kp, ek, ei, &s_tau_last);
-        if (!cert && ra.certify && M > kp && M <= RANK_MAX) {
+        if (!cert && ra.certify && !big && M > kp && M <= RANK_MAX) {
             // every list entry: rows outside the lists have coarse keys above T_c
             cert = rerank_block(ra, q, sk, si, M, tc, false, ek, ei, &s_tau_last);
             if (tid == 0 && cert) atomicAdd(ra.fail_count + 4, 1);  // diagnostics: queries rescued by the extended pass

@@ -63,6 +63,10 @@ struct b2f_index {
     int32_t harvested_seq = 0;        // last seq whose counters were folded into the host-side statistics
     int slack_boost = 0;              // extra candidates per query, raised when too many queries fail certification
     bool range_mode = false;          // earlier batches left many queries uncertified: run the range pass (one host sync per search)
+    int32_t range_ran_seq = 0;        // the search (sequence number) whose range pass served range_ran_nfail queries
+    int range_ran_nfail = 0;
+    int range_futile = 0;             // consecutive range passes that left most of their queries to the exact scan anyway
+    int range_ban = 0;                // searches to wait before the range pass may be switched on again
     int range_quiet = 0;              // consecutive range-mode searches whose first pass certified everything
     unsigned long long* totals = nullptr;  // device [4]: fallback queries, overflowed queries, rescued queries (running totals)
     cudaEvent_t ev_done = nullptr;    // recorded at the end of every search (searches return without synchronising)
@@ -343,7 +347,21 @@ void harvest_flag(b2f_index* ix) {
     if (certify && c0 - c1 > (nqb / 200 > 2 ? nqb / 200 : 2) && ix->slack_boost < 224) ix->slack_boost += 32;
     // Well before that (F > nq / 1000) the range pass takes over: a second TENSOR pass over the uncertified queries with a
     // fixed threshold per query, one database pass for all of them instead of one exact scan per four (search_locked).
-    if (certify && !ix->range_mode && c0 - c1 > (nqb / 1000 > 2 ? nqb / 1000 : 2)) {
+    // ... unless it does not help: neighbourhoods so dense that the fixed-threshold lists overflow too (thousands of
+    // near-duplicates) leave its queries to the exact scan anyway; two such searches in a row switch it off for a while.
+    if (ix->range_ban > 0) ix->range_ban--;
+    if (ix->range_mode && ix->range_ran_seq == s) {
+        if (2 * c0 > ix->range_ran_nfail) {
+            if (++ix->range_futile >= 2) {
+                ix->range_mode = false;
+                ix->range_futile = 0;
+                ix->range_ban = 256;
+            }
+        } else {
+            ix->range_futile = 0;
+        }
+    }
+    if (certify && !ix->range_mode && ix->range_ban == 0 && c0 - c1 > (nqb / 1000 > 2 ? nqb / 1000 : 2)) {
         ix->range_mode = true;
         ix->range_quiet = 0;
     }
@@ -1086,6 +1104,7 @@ static int search_locked(b2f_index* ix, int64_t nq64, const float* q, int64_t k6
         }  // query chunks
         int32_t* scan_list = fail_list;
         int32_t* scan_counters = counters;
+        int range_served = 0;
         if (ix->range_mode && certify && fail_tau) {
             // Range pass.  Earlier batches on this index left many queries uncertified (data denser than the bf16 band even
             // after centring): instead of one exact scan per four of them, ONE more tensor pass serves them all.  For a
@@ -1166,6 +1185,7 @@ static int search_locked(b2f_index* ix, int64_t nq64, const float* q, int64_t k6
                 ix->st.launches += 5;
                 ix->st.last_launches += 5;
                 ix->st.range_queries += nr;
+                range_served = nr;
                 scan_list = fail_list2;
                 scan_counters = counters_b;
             }
@@ -1175,6 +1195,10 @@ static int search_locked(b2f_index* ix, int64_t nq64, const float* q, int64_t k6
         // waits inside a search and consecutive searches run back to back on the GPU.
         B2F_TRY(enqueue_scan(ix, qd, scan_list, scan_counters, 0, k, Dd, Id, P.id_offset, scan_scratch, scan_counters, ++ix->seq, nq,
                              certify, st));
+        if (range_served) {
+            ix->range_ran_seq = ix->seq;
+            ix->range_ran_nfail = range_served;
+        }
     }
     if (slot) {
         B2F_CUDA(cudaEventRecord(slot->t1, st));

@@ -436,7 +436,10 @@ __global__ void range_thresholds_kernel(const float* __restrict__ tau2, const in
         const float nu = gam * (2.f * qn * max_row_norm + qn2 + max_row_norm * max_row_norm);
         const float t = fmaxf(tau, 0.f) * (1.f + 2e-6f) + 1e-30f;
         const float L = sqrtf(t) * (1.f + 1e-6f) + eq + max_row_err;   // certified <=> (sqrt(c + qn2 - nu) - eq - E)^2 (1 - 4e-7) > tau
-        thr[i] = L * L * (1.f + 1e-6f) - qn2 + nu * (1.f + 1e-6f) + 1e-30f;
+        // thr is a difference of numbers as large as |q~|^2 while L^2 can be thousands of times smaller (near-duplicates):
+        // the margin covers the fp32 rounding of this difference and of the one the test undoes it with, in units of the
+        // LARGE terms (16 ulp), not of the result
+        thr[i] = L * L - qn2 + nu + (L * L + qn2 + nu) * 1e-6f + 1e-30f;
     } else {
         const float cq = qconst ? qconst[i] : 0.f;
         const float xmax = max_row_norm + max_row_err + mu_norm;
@@ -444,7 +447,7 @@ __global__ void range_thresholds_kernel(const float* __restrict__ tau2, const in
         const float slack = nu + (qn + eq) * max_row_err + max_row_norm * eq;
         // certified <=> -thr + cq + slack < -tau  <=>  thr > tau + cq + slack
         const float base = tau + cq + slack;
-        thr[i] = base + fabsf(base) * 2e-6f + 1e-30f;
+        thr[i] = base + (fabsf(tau) + fabsf(cq) + slack) * 1e-6f + 1e-30f;   // margin in units of the terms (they may cancel)
     }
 }
 

@@ -29,7 +29,7 @@ def test_header_symbols_exported_and_bound():
         assert hasattr(lib, name), f"{name} declared in b200flat.h but not exported"
     assert sorted(_capi.PROTOTYPES) == declared
     assert lib.b2f_version() == 1
-    assert ctypes.sizeof(_capi.SearchParams) == 32 and ctypes.sizeof(_capi.Stats) == 120
+    assert ctypes.sizeof(_capi.SearchParams) == 32 and ctypes.sizeof(_capi.Stats) == 128
 
 
 def test_no_cpu_fallback_fails_loudly():

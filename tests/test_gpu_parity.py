@@ -390,25 +390,34 @@ def test_big_batch_warp_merge_and_first_stage(m, metric):
     _check(D2, I2, *orc.np_search_f64(xb2, xq2, k, metric), metric, min_recall=0.999 if metric == 1 else 0.0)
 
 
+def _near_duplicates(nc, dup, nq, metric, ordered=False, seed=9, d=128):
+    """nc clusters of `dup` near-duplicates (noise 1e-3: far inside the bf16 rounding band), rows in random order unless
+    `ordered`; queries next to randomly chosen cluster centres."""
+    rng = np.random.default_rng(seed)
+    centres = rng.standard_normal((nc, d)).astype(np.float32)
+    xb = (np.repeat(centres, dup, axis=0) + rng.standard_normal((nc * dup, d)).astype(np.float32) * 1e-3).astype(np.float32)
+    if not ordered:
+        xb = xb[rng.permutation(len(xb))]
+    xq = (centres[rng.integers(0, nc, nq)] + rng.standard_normal((nq, d)).astype(np.float32) * 1e-3).astype(np.float32)
+    if metric == 0:
+        xb /= np.linalg.norm(xb, axis=1, keepdims=True)
+        xq /= np.linalg.norm(xq, axis=1, keepdims=True)
+    return xb, xq
+
+
 @pytest.mark.parametrize("metric", [1, 0])
 def test_range_pass_serves_uncertified_queries(m, metric):
-    """Data denser than the bf16 band (clusters of 80 near-duplicates): the k' best and the extended stage cannot certify,
-    so the first search re-runs hundreds of queries through the exact scan, four per database pass.  The index notices
-    and from the next search on serves them with the range pass -- ONE more tensor pass with a fixed threshold per query
-    (every row whose coarse key can belong to a true top-k row is listed and re-ranked).  Results are exact both ways;
-    the second search must leave (almost) nothing to the exact scan."""
+    """Data denser than the bf16 band (clusters of 400 near-duplicates): the candidate lists cut INSIDE a cluster, so neither
+    the k' best nor the extended stage can certify and the first search re-runs every query through the exact scan, four
+    per database pass.  The index notices and from the next search on serves them with the range pass -- ONE more tensor
+    pass with a fixed threshold per query (every row whose coarse key can belong to a true top-k row is listed and
+    re-ranked).  Results are exact both ways; the second search must leave (almost) nothing to the exact scan."""
     import time
 
     import torch
 
-    rng = np.random.default_rng(9)
     d, k, nq = 128, 10, 512
-    centres = rng.standard_normal((300, d)).astype(np.float32)
-    xb = (np.repeat(centres, 80, axis=0) + rng.standard_normal((24000, d)).astype(np.float32) * 1e-3).astype(np.float32)
-    xq = (centres[rng.integers(0, 300, nq)] + rng.standard_normal((nq, d)).astype(np.float32) * 1e-3).astype(np.float32)
-    if metric == 0:
-        xb /= np.linalg.norm(xb, axis=1, keepdims=True)
-        xq /= np.linalg.norm(xq, axis=1, keepdims=True)
+    xb, xq = _near_duplicates(60, 400, nq, metric)
     ref = orc.np_search_f64(xb, xq, k, metric)
     ix = _make(m, xb, metric).set_search_params(algo=m.ALGO_TENSOR)
     tie_ok = 0.999 if metric == 1 else 0.0   # (normalised near-duplicates: fp32 inner products tie, see the test above)
@@ -418,8 +427,7 @@ def test_range_pass_serves_uncertified_queries(m, metric):
     t_first = time.perf_counter() - t0
     _check(D, I, *ref, metric, min_recall=tie_ok)
     st1 = ix.stats()
-    if st1["fallback_queries"] <= nq // 1000 + 2:
-        pytest.skip("the first pass certified this data: nothing for the range pass to do")
+    assert st1["fallback_queries"] > nq // 2 and st1["overflow_queries"] == 0, st1
     t0 = time.perf_counter()
     D2, I2 = ix.search(xq, k)
     t_second = time.perf_counter() - t0
@@ -429,13 +437,41 @@ def test_range_pass_serves_uncertified_queries(m, metric):
     left = st2["fallback_queries"] - st1["fallback_queries"]
     print(f"range pass: first search {st1['fallback_queries']} exact-scan queries in {t_first * 1e3:.2f} ms; second search "
           f"{served} range queries, {left} exact-scan queries in {t_second * 1e3:.2f} ms")
-    assert served >= min(st1["fallback_queries"], 8), (st1, st2)
-    assert left <= max(st1["fallback_queries"] // 10, 4), (st1, st2)
+    assert served == st1["fallback_queries"], (st1, st2)
+    assert left <= 4, (st1, st2)
     # ... and a third search with other queries, device tensors, stays exact
     xq3 = torch.from_numpy(xq[::-1].copy()).cuda()
     D3, I3 = ix.search(xq3, k)
     torch.cuda.synchronize()
     _check(D3.cpu().numpy(), I3.cpu().numpy(), ref[0][::-1], ref[1][::-1], metric, min_recall=tie_ok)
+    assert ix.stats()["fallback_queries"] - st2["fallback_queries"] <= 4
+
+
+@pytest.mark.parametrize("layout", ["huge", "ordered"])
+def test_neighbourhoods_beyond_every_list_fall_back_exactly(m, layout):
+    """Two shapes no candidate list can hold.  "huge": 4000 near-duplicates per cluster in random row order -- every list
+    stays within its capacity but a query has more entries than the merge stages; it selects the k' best straight from
+    the lists (no overflow is counted), fails certification WITH a k-th distance, and the range pass that is then tried
+    overflows as well, so it switches itself off again.  "ordered": clusters of 80 stored contiguously -- a query's best
+    rows all sit in one or two lists, the shared thresholds (which need good rows in MANY lists) never tighten and the
+    lists overflow.  Both are answered by the exact scan: slow, exact."""
+    metric, k, nq = 1, 10, 256
+    xb, xq = _near_duplicates(6, 4000, nq, metric) if layout == "huge" else _near_duplicates(300, 80, nq, metric, ordered=True)
+    ref = orc.np_search_f64(xb, xq, k, metric)
+    ix = _make(m, xb, metric).set_search_params(algo=m.ALGO_TENSOR)
+    seen = []
+    for it in range(5):
+        D, I = ix.search(xq, k)
+        _check(D, I, *ref, metric, min_recall=0.999)
+        seen.append(ix.stats())
+    assert seen[0]["fallback_queries"] == nq, seen[0]
+    if layout == "huge":
+        assert seen[0]["overflow_queries"] == 0, seen[0]          # the merge worked from the lists in global memory
+        assert seen[2]["range_queries"] > 0, seen[2]               # the range pass was tried ...
+        assert seen[4]["range_queries"] == seen[3]["range_queries"], seen   # ... and gave up
+    else:
+        assert seen[0]["overflow_queries"] == nq, seen[0]
+        assert seen[4]["range_queries"] == 0, seen[4]
 
 
 def test_very_large_batch_is_cut_into_list_passes(m):
