@@ -150,6 +150,7 @@ def main():
             "search_algo": {1: "scan", 2: "tensor"}.get(st["last_algo"]), "fallback_queries": st["fallback_queries"],
             "self_check": {"top1_ip_min": round(float(D[:, 0].min()), 4), "labels_in_range": bool(((I >= 0) & (I < args.chunks)).all())},
             "parity_vs_torch_fp32_bruteforce": recall, "rescued_queries": st["rescued_queries"],
+            "range_queries": st["range_queries"], "searches": st["searches"], "last_kprime": st["last_kprime"],
         }), flush=True)
     if world > 1:
         dist.barrier()

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Runs on an N-GPU box (gpurun --gpus N): the multi-GPU test tier, the bench at N (and its reference arm), optionally C5.
 #   bash tools/gpu_multi.sh <N> [c5]
-N=$1; OUT=gpurun_out/r02_n$N; mkdir -p $OUT
+N=$1; OUT=gpurun_out/r02s_n$N; mkdir -p $OUT
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517"
 (timeout 900 python -m pytest tests/test_gpu_sharded.py -m gpu -x -q > $OUT/pytest_sharded.log 2>&1; echo "pytest exit $?" >> $OUT/pytest_sharded.log); tail -4 $OUT/pytest_sharded.log
 timeout 900 $TR bench.py --gpus $N --steps 20 --warmup 5 > $OUT/bench_n$N.json 2> $OUT/bench_n$N.err; echo "bench N=$N exit $?"; tail -c 300 $OUT/bench_n$N.err
