@@ -353,6 +353,11 @@ __host__ __device__ __forceinline__ int unit_segments(int u, int T, int U, int k
 // Every role of the kernel steps one of these per tile and the epilogue is the kernel's critical path, so the state
 // is 32-bit and a step is a compare + add; a round change is two mul.hi / mul.lo pairs (the first version carried
 // 64-bit fixed point through every step: +9% executed instructions, -8% kernel throughput, ncu r02e).
+// (Cost-aware cuts were tried and dropped: a unit that runs two segments pays ~22 us for the switch -- per-unit
+// %globaltimer stamps, tools/k2_trace.py: 8192 queries on a 125 k-row shard, units with one segment issue their last MMA
+// at 614 us on average, units with two at 641 us.  Warping the cuts so that those units get ~6 tiles less and the whole
+// units the same small extra equalised the two groups (630 / 635 us) but not the kernel (0.646 -> 0.648 ms; nq = 4096
+// -1.4 %, C2 +0.7 %): the units' speeds are coupled through the chip-wide sustained tensor rate, of which K2 has 97 %.)
 struct SegIter {
     uint32_t F0, F1;      // in-tile bounds as Q0.32 fractions of the tile; full1: the segment ends at the tile's end (1.0)
     int R, NR, r, j, jend, base, ntiles;
@@ -445,6 +450,21 @@ __device__ __noinline__ float heap_push(float* hk, int32_t* hi, int tid, float k
 }
 
 
+// Diagnostics build only (-DB2F_K2_TRACE, tools/k2_trace.sh): per-CTA %globaltimer stamps of the kernel's phases.
+#ifdef B2F_K2_TRACE
+__device__ unsigned long long g_k2_trace[2 * kNumSMs * 12];
+#define K2_STAMP(slot)                                                   \
+    do {                                                                 \
+        unsigned long long t_;                                           \
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));           \
+        g_k2_trace[blockIdx.x * 12 + (slot)] = t_;                       \
+    } while (0)
+#define K2_NOTE(slot, v) g_k2_trace[blockIdx.x * 12 + (slot)] = (unsigned long long)(v)
+#else
+#define K2_STAMP(slot) do { } while (0)
+#define K2_NOTE(slot, v) do { } while (0)
+#endif
+
 template <int KP, bool L2, bool LIST, bool QRES, bool PAIR>
 __global__ void __launch_bounds__(k2_threads(LIST), 1)
 tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
@@ -476,6 +496,7 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     volatile int32_t* tile_row0 = reinterpret_cast<volatile int32_t*>(smem + L::tmem_off + 16);   // [2], written with bias[acc]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) K2_STAMP(0);
     // PAIR: a cluster of two CTAs (one TPC) works on 256 queries x one database stream; CTA rank r owns
     // queries [128 r, 128 r + 128) of the pair tile and stages rows [128 r, 128 r + 128) of every
     // 256-row database block; the leader (rank 0) issues tcgen05.mma.cta_group::2 for both.
@@ -577,6 +598,14 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     // tiles of segment s_ (host-computed with SegIter, passed by value): the loop count of the roles that need no tile index
     auto seg_tiles_of = [&](int s_) { return LIST ? seg_counts.n[2 * unit + s_] : (int)(heap_t1 - heap_t0); };
 
+#ifdef B2F_K2_TRACE
+    if (threadIdx.x == 0) {
+        uint32_t smid_;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid_));
+        K2_NOTE(8, unit + 1);
+        K2_NOTE(9, smid_);
+    }
+#endif
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_q)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_x)) : "memory");
@@ -614,6 +643,7 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     if constexpr (PAIR) cluster_sync_all();  // the peer's barriers must be initialised before any remote arrive / TMA credit
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_holder;
+    if (threadIdx.x == 0) K2_STAMP(1);
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -700,6 +730,7 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                     for (int kb = 0; kb < kblocks; kb++) {
                         mbar_wait(&full_bar[stage], phase);
                         tc_fence_after();
+                        if (gt == 0 && kb == 0 && lane == 0) K2_STAMP(2);
                         const uint32_t sa = __shfl_sync(kFull, smem_u32(smem + L::stages_off + (size_t)stage * kStageBytes), 0);
                         const uint32_t qa = __shfl_sync(kFull, smem_u32(smem + L::q_off + (size_t)kb * A_BYTES), 0);
                         const uint64_t adesc = make_smem_desc(QRES ? qa : sa);
@@ -729,6 +760,7 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                     __syncwarp();
                 }
                 if constexpr (QRES) {
+                    if (sgi + 1 < nseg && lane == 0) K2_STAMP(10);
                     if (sgi + 1 < nseg && lane == 0) {   // every MMA that reads this segment's query tile has been issued: free it
                         if constexpr (PAIR) umma_commit_pair(q_empty);
                         else umma_commit(q_empty);
@@ -736,6 +768,7 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                     __syncwarp();
                 }
             }
+            if (lane == 0) K2_STAMP(3);
         }
         __syncwarp();
     } else if (warp == 3) {
@@ -971,12 +1004,17 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                     }
                 }
             }
+            if (warp == 4 && lane == 0) K2_STAMP(4);
             if (active) {
                 // End-of-segment pruning: the final shared threshold is far tighter than the ones most
                 // entries were admitted under (the first chunk is admitted blindly), so re-filter the
                 // thread's own list in place.  Shrinks the merge input ~10x (C2: 1460 -> ~100 per query).
-                refresh(true);
+                // (tools/k2_trace.py: ~13 us per segment -- a refresh and three or four DEPENDENT round trips through a memory
+                // system the other CTAs keep saturated.  Tried and dropped, same-box A/B: requesting the first 32 entries
+                // before the refresh in the registers the accumulators no longer need -- the main loop's register allocation
+                // paid 2 % of the kernel for it; prefetch.global.L2 of the list lines -- no effect, they are L2 hits already.)
                 const int have = cnt <= la.cap ? cnt : 0;  // an overflowed list is left as is (the query falls back)
+                refresh(true);
                 int w = 0;
 #pragma unroll 1
                 for (int i0 = 0; i0 < have; i0 += 16) {
@@ -992,6 +1030,7 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 // smallest of these over the query's lists
                 la.final_thr[(int64_t)qrow * la.nl_stride + vsplit] = thr;
             }
+            if (warp == 4 && lane == 0) K2_STAMP(5);
             }  // segments
         } else {
             // ---- HEAP mode: thread-private max-heap of k' in shared memory ------------------------------
@@ -1057,12 +1096,14 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     tc_fence_before();
     __syncthreads();
     if constexpr (PAIR) cluster_sync_all();  // neither CTA may free TMEM / exit while the other still uses the pair
+    if (threadIdx.x == 0) K2_STAMP(6);
     if (warp == 2) {
         tc_fence_after();
         if constexpr (PAIR)
             asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
         else
             asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+        if (lane == 0) K2_STAMP(7);
     }
 }
 
@@ -1897,3 +1938,14 @@ int launch_merge_lists(const TensorScanLists& lists, int nq, const TensorScanPla
 }
 
 }  // namespace b2f
+
+#ifdef B2F_K2_TRACE
+// diagnostics build only: the %globaltimer stamps of the last K2 launch, 12 per CTA (0 entry, 1 set-up done, 2 first
+// tile landed, 3 last MMA issued, 4 last tile examined, 5 lists pruned, 6 all warps done, 7 TMEM freed, 8 logical unit + 1, 9 SM id, 10 first segment's MMAs issued)
+extern "C" __attribute__((visibility("default"))) int b2f_debug_k2_trace(unsigned long long* out, int n) {
+    if (n > 2 * b2f::kNumSMs * 12) n = 2 * b2f::kNumSMs * 12;
+    if (cudaMemcpyFromSymbol(out, b2f::k2::g_k2_trace, (size_t)n * 8) != cudaSuccess) return -1;
+    static unsigned long long zeros[2 * b2f::kNumSMs * 12] = {};
+    return cudaMemcpyToSymbol(b2f::k2::g_k2_trace, zeros, sizeof(zeros)) == cudaSuccess ? 0 : -1;   // re-armed for the next launch
+}
+#endif
