@@ -250,7 +250,7 @@ int launch_merge_faiss(int metric, int64_t nq, int64_t k, int nparts, const floa
 int launch_ingest(const float* src, int64_t n, int d, float* rows_f32, __nv_bfloat16* scan, int64_t dpad,
                   float* norms, float* stats, const float* mu, int ip_bias, int bf16_auth, cudaStream_t st);
 // mu[c] = mean of column c over the m rows of src
-int launch_mean_rows(const float* src, int64_t m, int d, float* mu, cudaStream_t st);
+int launch_mean_rows(const float* src, int64_t m, int d, float* mu, unsigned long long* acc, cudaStream_t st);
 // K7: pooling (+normalise) of encoder output, optionally fused with the ingest writes.
 int launch_pool(const float* hidden, const int64_t* mask, int64_t B, int64_t T, int d, int pool, int normalize,
                 float* out_f32, __nv_bfloat16* scan, int64_t dpad, float* norms, float* stats, cudaStream_t st);

@@ -43,21 +43,33 @@ __device__ __forceinline__ void emit_elem(float x, int64_t row, int col, int d, 
     ee = fmaf(e, e, ee);
 }
 
-// mu[c] += (1/m) * sum of column c over rows [0, m): the centre the scan copy is taken around.
-__global__ void __launch_bounds__(256) mean_rows_kernel(const float* __restrict__ src, int64_t m, int d, float* __restrict__ mu) {
+// mu[c] = (1/m) * sum of column c over rows [0, m): the centre the scan copy is taken around.  The same rows must give the
+// same centre bit for bit -- bf16 storage rounds the stored rows around it, so a centre that moved in its last bit would
+// give two indexes built from the same vectors rows that differ by a bf16 ulp here and there (float atomics did exactly
+// that).  Every block sums its 64 rows in a fixed order and adds the sum to a 64-bit FIXED-POINT accumulator: integer
+// addition is associative, the order in which the blocks arrive does not matter.
+constexpr double kMeanScale = 16777216.0;   // 2^24: 6e-8 absolute on a 64-row sum, |sum of all rows| up to 5e11
+__global__ void __launch_bounds__(256) mean_rows_kernel(const float* __restrict__ src, int64_t m, int d, unsigned long long* __restrict__ acc) {
     const int64_t r0 = (int64_t)blockIdx.x * 64, r1 = r0 + 64 < m ? r0 + 64 : m;
-    const float inv = 1.f / (float)m;
     for (int c = threadIdx.x; c < d; c += blockDim.x) {
         float a = 0.f;
         for (int64_t r = r0; r < r1; r++) a += src[r * d + c];
-        atomicAdd(mu + c, a * inv);
+        if (a == a && fabsf(a) < 1.0e11f)   // (NaN / inf rows do not move the centre)
+            atomicAdd(acc + c, (unsigned long long)__double2ll_rn((double)a * kMeanScale));   // two's complement: signed sums
     }
 }
+__global__ void mean_finish_kernel(const unsigned long long* __restrict__ acc, int64_t m, int d, float* __restrict__ mu) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < d) mu[c] = (float)((double)(long long)acc[c] / kMeanScale / (double)m);
+}
 
-int launch_mean_rows(const float* src, int64_t m, int d, float* mu, cudaStream_t st) {
+// acc: d 64-bit words of device scratch
+int launch_mean_rows(const float* src, int64_t m, int d, float* mu, unsigned long long* acc, cudaStream_t st) {
     if (m <= 0) return B2F_OK;
-    B2F_CUDA(cudaMemsetAsync(mu, 0, (size_t)d * 4, st));
-    mean_rows_kernel<<<(unsigned)((m + 63) / 64), 256, 0, st>>>(src, m, d, mu);
+    B2F_CUDA(cudaMemsetAsync(acc, 0, (size_t)d * 8, st));
+    mean_rows_kernel<<<(unsigned)((m + 63) / 64), 256, 0, st>>>(src, m, d, acc);
+    B2F_CUDA(cudaGetLastError());
+    mean_finish_kernel<<<(d + 255) / 256, 256, 0, st>>>(acc, m, d, mu);
     B2F_CUDA(cudaGetLastError());
     return B2F_OK;
 }

@@ -319,6 +319,27 @@ def test_centred_scan_copy_certifies_embedding_like_data(m):
     _check(D, I, *orc.np_search_f64(xb[:5000] - 3.0, xq[:64] - 3.0, k, 1), 1)
 
 
+def test_bf16_storage_is_reproducible(m):
+    """The same vectors give the same index, bit for bit: bf16 storage rounds the rows around the centre (the mean of the
+    first rows), so the centre must not depend on the order in which thread blocks finish (it is summed in 64-bit fixed
+    point).  With float atomics two indexes built from the same rows differed by a bf16 ulp in a few coordinates."""
+    rng = np.random.default_rng(31)
+    n, d = 70000, 96
+    xb = (rng.standard_normal((n, d)) + rng.standard_normal(d)[None, :] * 3).astype(np.float32)
+    first = None
+    for rep in range(4):
+        ix = m.IndexFlat(d, m.METRIC_L2, storage=m.STORE_BF16)
+        ix.add(xb[:40000])
+        ix.add(xb[40000:])
+        rows = ix.reconstruct_n()
+        if first is None:
+            first = rows
+            plain = np.abs(rows - xb).max()
+            assert plain < 0.05          # (rows are bf16-close to the input)
+        else:
+            assert np.array_equal(rows.view(np.uint32), first.view(np.uint32)), rep
+
+
 @pytest.mark.parametrize("metric", [1, 0])
 def test_centred_bf16_storage_certifies_embedding_like_data(m, metric, tmp_path):
     """The bf16-storage twin of the test above (BASELINE configs[3] stores bf16): rows sharing a large common
