@@ -1162,6 +1162,8 @@ __device__ __forceinline__ void radix_pick(int* s_hist, int* s_wsum, int* s_sel,
     __syncthreads();
 }
 
+// (register-limited to four CTAs per SM; forcing five or six with launch bounds was measured: no gain, the spills cost what
+// the extra CTAs bring)
 __global__ void __launch_bounds__(MERGE_THREADS)
 merge_lists_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ counts, const float* __restrict__ final_thr,
                    int nl_stride, int tile_queries, int ntile_units, int total_units, int halves, int kp, int list_cap,
