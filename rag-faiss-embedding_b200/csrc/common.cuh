@@ -329,6 +329,7 @@ struct TensorScanLists {  // LIST-mode scratch (device)
     const float* range_thr;  // optional [nq_pad]: range pass -- fixed per-query thresholds (no shared thresholds, no refresh)
 };
 int plan_tensor_scan(int nq, int64_t n, int d, int kp, TensorScanPlan* plan);
+void plan_force_heap(bool on);   // planning switch of the calling thread: per-thread heaps instead of LIST mode (k' = 32 / 64)
 int plan_unit_work(int T, int U, int R, int64_t ntiles, int kp, int unit, int32_t* seg_info, int64_t* tiles, int64_t cap, int32_t* counts);
 int launch_tensor_scan(const __nv_bfloat16* scan, int64_t dpad, const float* norms, int64_t n, int metric,
                        const __nv_bfloat16* qb, int nq, int nq_pad, const TensorScanPlan& plan, float* pk,

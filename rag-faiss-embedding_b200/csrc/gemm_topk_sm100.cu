@@ -1676,6 +1676,13 @@ static int launch_k2(const CUtensorMap& mq, const CUtensorMap& mx, const float* 
 
 }  // namespace k2
 
+// Planning switch of the calling thread (index.cu sets it around the planning of one search): skip LIST mode.  An index
+// whose data defeats the shared thresholds -- rows stored in an order that puts a query's best rows into one or two
+// lists, so that the thresholds never tighten and the lists overflow -- is searched with per-thread heaps instead (exact
+// top-k' of every split whatever the order, ~6x the epilogue cost), for k' = 32 / 64.
+static thread_local bool t_force_heap = false;
+void plan_force_heap(bool on) { t_force_heap = on; }
+
 int plan_tensor_scan(int nq, int64_t n, int d, int kp, TensorScanPlan* plan) {
     if (kp < 8 || kp > 256 || n <= 0 || nq <= 0) return B2F_EINVAL;
     plan->kp = kp;
@@ -1723,15 +1730,16 @@ int plan_tensor_scan(int nq, int64_t n, int d, int kp, TensorScanPlan* plan) {
     };
     // (1) CTA pairs halve the L2->SM traffic of the database blocks; worth it once the batch spans several
     //     128-query tiles (an odd tile count wastes half a pair on padding).
+    const bool heap_only = t_force_heap && (kp == 32 || kp == 64);
     const char* no_pair = getenv("B200FLAT_NO_PAIR");
     int units = 0, nv_min = 1, nseg_max = 1;
-    if (!(no_pair && no_pair[0] == '1') && kblocks <= k2::QRES_MAX_KB && plan->nq_tiles >= 2 &&
+    if (!heap_only && !(no_pair && no_pair[0] == '1') && kblocks <= k2::QRES_MAX_KB && plan->nq_tiles >= 2 &&
         (plan->nq_tiles % 2 == 0 || plan->nq_tiles >= 7) && try_list((plan->nq_tiles + 1) / 2, kNumSMs / 2, &units, &nv_min, &nseg_max)) {
         plan->pair_mode = 1;
         plan->list_mode = 1;
         plan->nq_tiles = 2 * ((plan->nq_tiles + 1) / 2);
         plan->tile_units = plan->nq_tiles / 2;
-    } else if (try_list(plan->nq_tiles, kNumSMs, &units, &nv_min, &nseg_max)) {
+    } else if (!heap_only && try_list(plan->nq_tiles, kNumSMs, &units, &nv_min, &nseg_max)) {
         plan->list_mode = 1;
         plan->tile_units = plan->nq_tiles;
     } else {

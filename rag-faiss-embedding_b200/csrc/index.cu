@@ -68,6 +68,12 @@ struct b2f_index {
     int range_futile = 0;             // consecutive range passes that left most of their queries to the exact scan anyway
     int range_ban = 0;                // searches to wait before the range pass may be switched on again
     int range_quiet = 0;              // consecutive range-mode searches whose first pass certified everything
+    // Order-robust mode.  A batch whose candidate lists overflowed en masse (rows stored so that a query's best rows sit in
+    // one or two lists: the shared thresholds never tighten) switches the index to per-thread heaps for the first pass
+    // (plan_force_heap) plus the range pass for what the heaps cannot certify; LIST mode is tried again after heap_span
+    // searches, and the span doubles every time it fails again.
+    int heap_left = 0;                // searches still to run in this mode
+    int heap_span = 64;
     unsigned long long* totals = nullptr;  // device [4]: fallback queries, overflowed queries, rescued queries (running totals)
     cudaEvent_t ev_done = nullptr;    // recorded at the end of every search (searches return without synchronising)
     cudaStream_t last_stream = nullptr;
@@ -361,6 +367,14 @@ void harvest_flag(b2f_index* ix) {
             ix->range_futile = 0;
         }
     }
+    if (certify && c1 > (nqb / 8 > 8 ? nqb / 8 : 8) && ix->heap_left == 0) {
+        ix->heap_left = ix->heap_span;
+        if (ix->heap_span < 4096) ix->heap_span *= 2;
+        if (ix->range_ban == 0) {
+            ix->range_mode = true;   // the heaps find the k' best whatever the row order; dense neighbourhoods still need the range pass
+            ix->range_quiet = 0;
+        }
+    }
     if (certify && !ix->range_mode && ix->range_ban == 0 && c0 - c1 > (nqb / 1000 > 2 ? nqb / 1000 : 2)) {
         ix->range_mode = true;
         ix->range_quiet = 0;
@@ -578,6 +592,12 @@ int b2f_index_reset(b2f_index* ix) {
     DeviceGuard g(ix->device);
     ix->ntotal = 0;
     ix->mu_set = false;
+    // what earlier searches taught the index about its data goes with the data
+    ix->slack_boost = 0;
+    ix->range_mode = false;
+    ix->range_quiet = ix->range_futile = ix->range_ban = 0;
+    ix->heap_left = 0;
+    ix->heap_span = 64;
     if (ix->search_recorded) B2F_CUDA(cudaEventSynchronize(ix->ev_done));
     if (ix->add_recorded) B2F_CUDA(cudaEventSynchronize(ix->ev_ingest));
     B2F_CUDA(cudaMemsetAsync(ix->stats, 0, 2 * sizeof(float), ix->stream));
@@ -938,13 +958,17 @@ static int search_locked(b2f_index* ix, int64_t nq64, const float* q, int64_t k6
         if (boosted > 64) kp = boosted <= 256 ? boosted : 256;
     }
     TensorScanPlan plan{};
+    const bool heap_first = ix->heap_left > 0 && P.certify >= 0;
+    plan_force_heap(heap_first);
     const int chunk_nq = (kp > 0 && ix->ntotal > 0) ? plan_tensor_chunked(nq, ix->ntotal, ix->d, kp, &plan) : 0;
+    plan_force_heap(false);
     const bool tensor_ok = chunk_nq > 0;
     if (algo == B2F_ALGO_AUTO) algo = (nq <= scan_max || !tensor_ok) ? B2F_ALGO_SCAN : B2F_ALGO_TENSOR;
     // an explicit TENSOR request on a shape the tensor path cannot plan (k' > 256, or a database of a few rows with
     // k' other than 32 / 64) is served by the exact scan, like AUTO would; stats().last_algo tells
     if (algo == B2F_ALGO_TENSOR && !tensor_ok) algo = B2F_ALGO_SCAN;
     const int certify = P.certify >= 0 ? 1 : 0;
+    if (algo == B2F_ALGO_TENSOR && heap_first) ix->heap_left--;
 
     // ---- workspace -----------------------------------------------------------------------------
     size_t need = 8192;

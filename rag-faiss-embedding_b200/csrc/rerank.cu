@@ -28,8 +28,9 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankArgs a) {
     int valid = 0;
     for (int t = threadIdx.x; t < a.kp; t += kRerankThreads) valid += ci[t] >= 0 ? 1 : 0;
     valid = __syncthreads_count(valid);  // kp <= 256 = block size: one candidate per thread
-    const bool cert = rerank_block(a, q, ck, ci, a.kp, ck[a.kp - 1], valid < a.kp, ek, ei);
-    if (threadIdx.x == 0 && a.certify && !cert) rerank_record_failure(a, q, false);
+    __shared__ float s_tau_k;   // exact k-th key of the candidates: what a failed query hands to the range pass
+    const bool cert = rerank_block(a, q, ck, ci, a.kp, ck[a.kp - 1], valid < a.kp, ek, ei, &s_tau_k);
+    if (threadIdx.x == 0 && a.certify && !cert) rerank_record_failure(a, q, false, s_tau_k);
 }
 
 int launch_rerank(const RerankArgs& a, cudaStream_t st) {

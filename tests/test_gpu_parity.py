@@ -473,9 +473,11 @@ def test_neighbourhoods_beyond_every_list_fall_back_exactly(m, layout):
     """Two shapes no candidate list can hold.  "huge": 4000 near-duplicates per cluster in random row order -- every list
     stays within its capacity but a query has more entries than the merge stages; it selects the k' best straight from
     the lists (no overflow is counted), fails certification WITH a k-th distance, and the range pass that is then tried
-    overflows as well, so it switches itself off again.  "ordered": clusters of 80 stored contiguously -- a query's best
-    rows all sit in one or two lists, the shared thresholds (which need good rows in MANY lists) never tighten and the
-    lists overflow.  Both are answered by the exact scan: slow, exact."""
+    overflows as well, so it switches itself off again: exact scans, slow, exact.  "ordered": clusters of 80 stored
+    contiguously -- a query's best rows all sit in one or two lists, the shared thresholds (which need good rows in MANY
+    lists) never tighten and the lists overflow: the first search is answered by the exact scan, and the index switches
+    to its order-robust mode -- per-thread heaps in the first pass (exact top-k' of every split whatever the order) plus
+    the range pass for the near-duplicates the heaps cannot certify -- which leaves nothing to the exact scan."""
     metric, k, nq = 1, 10, 256
     xb, xq = _near_duplicates(6, 4000, nq, metric) if layout == "huge" else _near_duplicates(300, 80, nq, metric, ordered=True)
     ref = orc.np_search_f64(xb, xq, k, metric)
@@ -492,7 +494,9 @@ def test_neighbourhoods_beyond_every_list_fall_back_exactly(m, layout):
         assert seen[4]["range_queries"] == seen[3]["range_queries"], seen   # ... and gave up
     else:
         assert seen[0]["overflow_queries"] == nq, seen[0]
-        assert seen[4]["range_queries"] == 0, seen[4]
+        assert seen[4]["overflow_queries"] == nq, seen[4]                      # no list overflowed again ...
+        assert seen[4]["fallback_queries"] - seen[1]["fallback_queries"] <= 4, seen   # ... and from the third search on nothing needs the exact scan
+        assert seen[4]["range_queries"] > 0, seen[4]
 
 
 def test_very_large_batch_is_cut_into_list_passes(m):

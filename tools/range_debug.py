@@ -3,7 +3,8 @@
 usage: range_debug.py [metric] [layout] [d] [k] [storage: f32 | bf16] [nq]
   layout "shuffled": 300 clusters x 80 near-duplicates in random row order  -> uncertified queries WITH a k-th distance
                      (the range pass serves them from the second search on)
-         "ordered" : the same rows, every cluster stored contiguously       -> thresholds never tighten, lists overflow
+         "ordered" : the same rows, every cluster stored contiguously       -> thresholds never tighten, lists overflow;
+                     the index switches to per-thread heaps + range pass (order-robust mode)
          "dense"   : 60 clusters x 400 near-duplicates, random order        -> the lists cut inside the cluster: the
                      extended certification fails too, the range pass lists the whole cluster
          "huge"    : 6 clusters x 4000 near-duplicates, random order        -> more list entries than the merge stages, and
