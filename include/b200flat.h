@@ -80,7 +80,12 @@ typedef struct b2f_search_params {
                               (0 = default: k' = k + max(22, ceil(0.9 k)), rounded up to 32 / 64 / a multiple of 8, <= 256) */
     int32_t certify;       /* tensor path: 1 (default when 0 is passed via NULL params) = prove from the
                               bf16 rounding bound that no non-candidate can beat the k-th re-ranked
-                              result; queries that fail are re-run through the exact scan. -1 = off */
+                              result; queries that fail are answered exactly another way: by the range pass (one more
+                              tensor pass with a fixed threshold per query) once an index has seen more than 0.1 % of
+                              a batch fail, else by the exact scan.  The index also adapts to what its data does to the
+                              candidate lists: +32 candidates per query after batches with > 0.5 % exact scans,
+                              per-thread heaps instead of shared-threshold lists after mass list overflows.
+                              All of it changes speed only -- results are exact either way.  -1 = certification off */
     int64_t id_offset;     /* added to every returned label (row-sharded indexes: the shard's first row) */
     int32_t profile;       /* 1 = record CUDA events around the dominant kernel (see b2f_stats) */
     int32_t reserved;
