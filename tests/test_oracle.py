@@ -95,6 +95,30 @@ def test_c_vs_f64_random(metric, nq, k):
     assert r["recall"] == 1.0 and r["id_mismatch"] == 0, r
 
 
+@pytest.mark.parametrize("metric", [orc.METRIC_L2, orc.METRIC_INNER_PRODUCT])
+def test_oracle_vs_independent_brute_force(metric):
+    """faiss itself cannot run here (section 1 of DESIGN.md), so the oracle's notion of "the true top-k" is checked
+    against an implementation this repo did not write: scikit-learn's brute-force NearestNeighbors in float64 (squared
+    euclidean; for inner product, cosine distance on normalised rows, which ranks them identically).  It pins the
+    neighbour SETS and distances, not faiss's tie order."""
+    sk = pytest.importorskip("sklearn.neighbors")
+    n, d, nq, k = 4000, 64, 33, 10
+    xb = orc.c_synth_rows(77, 0, n, d)
+    xq = orc.c_synth_rows(78, 0, nq, d)
+    if metric == orc.METRIC_INNER_PRODUCT:
+        xb = (xb / np.linalg.norm(xb, axis=1, keepdims=True)).astype(np.float32)
+        xq = (xq / np.linalg.norm(xq, axis=1, keepdims=True)).astype(np.float32)
+    nn = sk.NearestNeighbors(n_neighbors=k, algorithm="brute", metric="sqeuclidean" if metric == orc.METRIC_L2 else "cosine")
+    nn.fit(xb.astype(np.float64))
+    d_sk, i_sk = nn.kneighbors(xq.astype(np.float64))
+    d_sk = d_sk if metric == orc.METRIC_L2 else 1.0 - d_sk          # cosine distance -> inner product of unit vectors
+    for name, (D, I) in {"float64 brute force": orc.np_search_f64(xb, xq, k, metric),
+                         "C seq path": orc.c_search(xb, xq, k, metric, algo=1),
+                         "C blas path": orc.c_search(xb, xq, k, metric, algo=2)}.items():
+        assert all(set(I[q].tolist()) == set(i_sk[q].tolist()) for q in range(nq)), name
+        assert np.allclose(np.sort(D, axis=1), np.sort(d_sk, axis=1), rtol=1e-5, atol=1e-5), name
+
+
 def test_edge_cases():
     xb = orc.c_synth_rows(1, 0, 10, 8)
     # k > ntotal
